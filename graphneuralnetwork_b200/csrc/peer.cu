@@ -1,0 +1,124 @@
+// Multi-GPU halo exchange over NVLink peer memory.
+// One process per GPU.  Halo buffers are plain cudaMalloc allocations exported with CUDA
+// IPC so that every rank can map every peer's buffer.  gnn_halo_push_f32 is the fused
+// pack + transfer: each CTA copies feature rows of the local X straight into the owning
+// peer's halo buffer with 128-bit stores that travel over NVLink/NVSwitch — there is no
+// staging buffer and no separate copy engine step.  The reference has no multi-GPU path
+// for this (only nn.DataParallel, HAN/train_utils/train_eval.py:46); this is new.
+#include "common.cuh"
+
+using namespace gnn;
+
+namespace {
+
+constexpr int kMaxPeers = 16;
+
+struct PushArgs {
+  const float* X;
+  int64_t ldx;
+  int32_t F;
+  const int32_t* send_rows;
+  int64_t send_off[kMaxPeers + 1];
+  float* halo[kMaxPeers];
+  int64_t dst_off[kMaxPeers];
+  int64_t ld_halo;
+  int32_t n_peers;
+};
+
+// one warp per sent row; VEC-wide copies
+template <int VEC>
+__global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = a.send_off[a.n_peers];
+  for (int64_t k = w0; k < total; k += nw) {
+    int q = 0;
+    while (q + 1 < a.n_peers && k >= a.send_off[q + 1]) ++q;
+    const int64_t r = __ldg(a.send_rows + k);
+    const float* src = a.X + r * a.ldx;
+    float* dst = a.halo[q] + (a.dst_off[q] + (k - a.send_off[q])) * a.ld_halo;
+    for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
+      float v[VEC];
+      VecIO<float, VEC>::load(src + c, v);
+      VecIO<float, VEC>::store(dst + c, v);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int gnn_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64B_host) {
+  GNN_REQUIRE(dev_ptr && ipc_handle_64B_host && bytes > 0, GNN_ERR_BAD_ARG, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  GNN_CUDA(cudaMalloc(dev_ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*dev_ptr);
+    *dev_ptr = nullptr;
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return GNN_ERR_CUDA;
+  }
+  memcpy(ipc_handle_64B_host, &h, 64);
+  return GNN_OK;
+}
+
+int gnn_peer_open(const void* ipc_handle_64B_host, void** dev_ptr) {
+  GNN_REQUIRE(dev_ptr && ipc_handle_64B_host, GNN_ERR_BAD_ARG, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle_64B_host, 64);
+  GNN_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GNN_OK;
+}
+
+int gnn_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return GNN_OK;
+  GNN_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return GNN_OK;
+}
+
+int gnn_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return GNN_OK;
+  GNN_CUDA(cudaFree(dev_ptr));
+  return GNN_OK;
+}
+
+int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* send_rows, const int64_t* send_off_host,
+                      float* const* peer_halo_host, const int64_t* dst_off_host, int64_t ld_halo, int32_t n_peers,
+                      gnn_stream_t stream) {
+  GNN_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, GNN_ERR_UNSUPPORTED, "n_peers=%d exceeds %d", n_peers, kMaxPeers);
+  if (n_peers == 0) return GNN_OK;
+  GNN_REQUIRE(X && send_off_host && peer_halo_host && dst_off_host, GNN_ERR_BAD_ARG, "null pointer");
+  GNN_REQUIRE(F > 0 && ldx >= F && ld_halo >= F, GNN_ERR_BAD_ARG, "bad feature width / leading dimension");
+  PushArgs a{};
+  a.X = X;
+  a.ldx = ldx;
+  a.F = F;
+  a.send_rows = send_rows;
+  a.ld_halo = ld_halo;
+  a.n_peers = n_peers;
+  bool vec4 = aligned_to(X, 16) && ldx % 4 == 0 && ld_halo % 4 == 0 && F % 4 == 0;
+  for (int q = 0; q <= n_peers; ++q) a.send_off[q] = send_off_host[q];
+  for (int q = 0; q < n_peers; ++q) {
+    a.halo[q] = peer_halo_host[q];
+    a.dst_off[q] = dst_off_host[q];
+    GNN_REQUIRE(a.send_off[q + 1] >= a.send_off[q], GNN_ERR_BAD_ARG, "send_off not monotone");
+    GNN_REQUIRE(a.send_off[q + 1] == a.send_off[q] || a.halo[q] != nullptr, GNN_ERR_BAD_ARG, "null peer halo %d", q);
+    vec4 = vec4 && aligned_to(a.halo[q], 16);
+  }
+  const int64_t total = a.send_off[n_peers];
+  if (total == 0) return GNN_OK;
+  GNN_REQUIRE(send_rows != nullptr, GNN_ERR_BAD_ARG, "null send_rows");
+  int64_t grid = (total * 32 + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  grid = grid > cap ? cap : grid;
+  if (vec4) halo_push_kernel<4><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else halo_push_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
+  GNN_LAUNCH_CHECK();
+  return GNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+// Row-parallel gather-reduce: the one kernel template behind
+//   - CSR SpMM  Y = Â·X                     (replaces torch.spmm, GCN/GCN.py:43)
+//   - transpose SpMM for the backward       (autograd of GCN/GCN.py:43)
+//   - fixed-fanout gather-mean/sum/max with vector loads
+//                                           (GraphSAGE_Pytorch/models/Aggregator.py:19-24)
+//   - the ordered gather backward into the feature table.
+//
+// A row is owned by GROUP lanes (a sub-warp chosen from F), each lane owns CHUNKS
+// vectors of VEC elements (128-bit when alignment allows).  The GROUP lanes load GROUP
+// (col,val) pairs coalesced, then broadcast them by shuffle and issue U independent
+// feature-row gathers before the FMAs (memory-level parallelism).  Edges are
+// accumulated strictly in CSR order: deterministic, no atomics.
+#pragma once
+#include "common.cuh"
+
+namespace gnn {
+
+template <typename T>
+struct RowArgs {
+  const int64_t* rowptr;  // nullptr => implicit fixed fanout: row r owns slots [r*fanout,(r+1)*fanout)
+  int32_t fanout;
+  const int32_t* col32;  // CSR col / int32 index block
+  const int64_t* col64;  // int64 index block; both null => identity (source row = slot)
+  const float* val;      // nullptr => 1
+  int32_t src_div;       // >0: source row = col / src_div (gather backward: flat position -> source)
+  float scale;           // result multiplier (1/fanout for mean)
+  const T* X;
+  int64_t ldx;
+  T* Y;
+  int64_t ldy;
+  int64_t n_rows;
+  int32_t F;
+  int64_t skip_deg_gt;   // >0: rows with more edges are left to the long-row kernel
+  int32_t* argmax;       // max only, nullable, [n_rows, ldy]
+};
+
+constexpr int kRowReduceThreads = 256;
+
+template <typename T, int VEC, int GROUP, int CHUNKS, int U, int OP>
+__global__ void __launch_bounds__(kRowReduceThreads) row_reduce_kernel(const RowArgs<T> a) {
+  constexpr int ROWS_PER_CTA = kRowReduceThreads / GROUP;
+  const int lane = threadIdx.x & 31;
+  const int gl = threadIdx.x % GROUP;
+  const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane - gl));
+  const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + threadIdx.x / GROUP;
+  if (row >= a.n_rows) return;
+  int64_t s, e;
+  if (a.rowptr) {
+    s = __ldg(a.rowptr + row);
+    e = __ldg(a.rowptr + row + 1);
+  } else {
+    s = row * (int64_t)a.fanout;
+    e = s + a.fanout;
+  }
+  if (a.skip_deg_gt > 0 && e - s > a.skip_deg_gt) return;
+
+  float acc[CHUNKS][VEC];
+  int best[CHUNKS][VEC];
+#pragma unroll
+  for (int ch = 0; ch < CHUNKS; ++ch)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      acc[ch][i] = (OP == 1) ? -INFINITY : 0.f;
+      best[ch][i] = 0;
+    }
+
+  for (int64_t base = s; base < e; base += GROUP) {
+    const int64_t k = base + gl;
+    int32_t c = -1;
+    float v = 0.f;
+    if (k < e) {
+      if (a.col32) c = __ldg(a.col32 + k);
+      else if (a.col64) c = (int32_t)__ldg(a.col64 + k);
+      else c = (int32_t)k;
+      if (a.src_div > 0 && c >= 0) c /= a.src_div;
+      v = a.val ? __ldg(a.val + k) : 1.f;
+    }
+    const int cnt = (int)((e - base) < (int64_t)GROUP ? (e - base) : (int64_t)GROUP);
+    for (int j0 = 0; j0 < cnt; j0 += U) {
+      float xv[U][CHUNKS][VEC];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = j0 + u;
+        const int32_t cj = __shfl_sync(gmask, c, jj, GROUP);
+        const float vj = __shfl_sync(gmask, v, jj, GROUP);
+        const bool ok = (jj < cnt) && (cj >= 0);
+        vv[u] = ok ? vj : 0.f;
+        const T* xr = a.X + (int64_t)(ok ? cj : 0) * a.ldx;
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          const int col0 = (gl + ch * GROUP) * VEC;
+          if (ok && col0 < a.F) {
+            VecIO<T, VEC>::load(xr + col0, xv[u][ch]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) xv[u][ch][i] = (OP == 1) ? -INFINITY : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            if (OP == 1) {
+              if (xv[u][ch][i] > acc[ch][i]) {
+                acc[ch][i] = xv[u][ch][i];
+                best[ch][i] = (int)(base - s) + j0 + u;
+              }
+            } else {
+              acc[ch][i] = fmaf(vv[u], xv[u][ch][i], acc[ch][i]);
+            }
+          }
+    }
+  }
+
+  T* yr = a.Y + row * a.ldy;
+#pragma unroll
+  for (int ch = 0; ch < CHUNKS; ++ch) {
+    const int col0 = (gl + ch * GROUP) * VEC;
+    if (col0 < a.F) {
+      float o[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = (OP == 1) ? acc[ch][i] : acc[ch][i] * a.scale;
+      VecIO<T, VEC>::store(yr + col0, o);
+      if (OP == 1 && a.argmax) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (col0 + i < a.F) a.argmax[row * a.ldy + col0 + i] = best[ch][i];
+      }
+    }
+  }
+}
+
+// Long rows: one CTA per row, warps take 32-edge batches round-robin, per-warp partial
+// sums reduced through shared memory in warp order (fixed order => deterministic).
+constexpr int kLongWarps = 8;
+template <typename T, int VEC, int CHUNKS>
+__global__ void __launch_bounds__(kLongWarps * 32) row_reduce_long_kernel(const RowArgs<T> a, const int64_t* long_rows) {
+  __shared__ float part[kLongWarps][CHUNKS * 32 * VEC];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int64_t row = long_rows[blockIdx.x];
+  const int64_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
+  float acc[CHUNKS][VEC];
+#pragma unroll
+  for (int ch = 0; ch < CHUNKS; ++ch)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
+  constexpr int U = (CHUNKS == 1) ? 8 : (CHUNKS <= 3 ? 4 : 2);
+  for (int64_t base = s + (int64_t)w * 32; base < e; base += (int64_t)kLongWarps * 32) {
+    const int64_t k = base + lane;
+    int32_t c = -1;
+    float v = 0.f;
+    if (k < e) {
+      c = __ldg(a.col32 + k);
+      if (a.src_div > 0) c /= a.src_div;
+      v = a.val ? __ldg(a.val + k) : 1.f;
+    }
+    const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+    for (int j0 = 0; j0 < cnt; j0 += U) {
+      float xv[U][CHUNKS][VEC];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = j0 + u;
+        const int32_t cj = __shfl_sync(0xffffffffu, c, jj);
+        const float vj = __shfl_sync(0xffffffffu, v, jj);
+        const bool ok = (jj < cnt) && (cj >= 0);
+        vv[u] = ok ? vj : 0.f;
+        const T* xr = a.X + (int64_t)(ok ? cj : 0) * a.ldx;
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          const int col0 = (lane + ch * 32) * VEC;
+          if (ok && col0 < a.F) {
+            VecIO<T, VEC>::load(xr + col0, xv[u][ch]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) xv[u][ch][i] = 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], xv[u][ch][i], acc[ch][i]);
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < CHUNKS; ++ch)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) part[w][(ch * 32 + lane) * VEC + i] = acc[ch][i];
+  __syncthreads();
+  T* yr = a.Y + row * a.ldy;
+  for (int idx = threadIdx.x; idx < CHUNKS * 32; idx += kLongWarps * 32) {
+    const int col0 = idx * VEC;  // idx = ch*32+lane -> column (lane + ch*32)*VEC
+    if (col0 < a.F) {
+      float o[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float sum = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kLongWarps; ++ww) sum += part[ww][idx * VEC + i];
+        o[i] = sum * a.scale;
+      }
+      VecIO<T, VEC>::store(yr + col0, o);
+    }
+  }
+}
+
+// ---- host-side dispatch -----------------------------------------------------------
+template <typename T>
+inline int pick_vec(const void* X, int64_t ldx, const void* Y, int64_t ldy, int F) {
+  for (int v = 16 / (int)sizeof(T); v > 1; v >>= 1) {
+    const size_t bytes = (size_t)v * sizeof(T);
+    const int64_t fpad = ((int64_t)F + v - 1) / v * v;
+    if (aligned_to(X, bytes) && aligned_to(Y, bytes) && ldx % v == 0 && ldy % v == 0 && fpad <= ldx && fpad <= ldy)
+      return v;
+  }
+  return 1;
+}
+
+template <typename T, int VEC, int GROUP, int CHUNKS, int OP>
+inline void launch_row_reduce_inst(const RowArgs<T>& a, cudaStream_t st) {
+  constexpr int U0 = (CHUNKS == 1) ? 8 : (CHUNKS <= 3 ? 4 : 2);
+  constexpr int U = U0 < GROUP ? U0 : GROUP;
+  constexpr int ROWS_PER_CTA = kRowReduceThreads / GROUP;
+  const int64_t grid = (a.n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  row_reduce_kernel<T, VEC, GROUP, CHUNKS, U, OP><<<(unsigned)grid, kRowReduceThreads, 0, st>>>(a);
+}
+
+template <typename T, int VEC, int OP>
+inline int launch_row_reduce_vec(const RowArgs<T>& a0, cudaStream_t st) {
+  // column tiles of at most 32 lanes x 8 chunks x VEC elements
+  const int tile_cols = 32 * 8 * VEC;
+  for (int c0 = 0; c0 < a0.F; c0 += tile_cols) {
+    RowArgs<T> a = a0;
+    a.X = a0.X + c0;
+    a.Y = a0.Y + c0;
+    if (a0.argmax) a.argmax = a0.argmax + c0;
+    a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
+    const int nvec = (a.F + VEC - 1) / VEC;
+    if (nvec <= 4) launch_row_reduce_inst<T, VEC, 4, 1, OP>(a, st);
+    else if (nvec <= 8) launch_row_reduce_inst<T, VEC, 8, 1, OP>(a, st);
+    else if (nvec <= 16) launch_row_reduce_inst<T, VEC, 16, 1, OP>(a, st);
+    else if (nvec <= 32) launch_row_reduce_inst<T, VEC, 32, 1, OP>(a, st);
+    else if (nvec <= 64) launch_row_reduce_inst<T, VEC, 32, 2, OP>(a, st);
+    else if (nvec <= 96) launch_row_reduce_inst<T, VEC, 32, 3, OP>(a, st);
+    else if (nvec <= 128) launch_row_reduce_inst<T, VEC, 32, 4, OP>(a, st);
+    else if (nvec <= 160) launch_row_reduce_inst<T, VEC, 32, 5, OP>(a, st);
+    else if (nvec <= 192) launch_row_reduce_inst<T, VEC, 32, 6, OP>(a, st);
+    else launch_row_reduce_inst<T, VEC, 32, 8, OP>(a, st);
+    GNN_LAUNCH_CHECK();
+  }
+  return GNN_OK;
+}
+
+template <typename T, int OP>
+inline int launch_row_reduce(const RowArgs<T>& a, cudaStream_t st) {
+  if (a.n_rows <= 0 || a.F <= 0) return GNN_OK;
+  GNN_REQUIRE((a.n_rows + 7) / 8 < 0x7fffffffLL, GNN_ERR_UNSUPPORTED, "too many rows for one grid: %lld", (long long)a.n_rows);
+  const int vec = pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F);
+  if (sizeof(T) == 2 && vec == 8) return launch_row_reduce_vec<T, (sizeof(T) == 2 ? 8 : 4), OP>(a, st);
+  if (vec >= 4) return launch_row_reduce_vec<T, 4, OP>(a, st);
+  if (vec == 2) return launch_row_reduce_vec<T, 2, OP>(a, st);
+  return launch_row_reduce_vec<T, 1, OP>(a, st);
+}
+
+template <typename T, int VEC>
+inline int launch_row_reduce_long_vec(const RowArgs<T>& a0, const int64_t* long_rows, int64_t n_long, cudaStream_t st) {
+  const int tile_cols = 32 * 4 * VEC;  // keeps the partial-sum tile within 48 KB of static shared memory
+  for (int c0 = 0; c0 < a0.F; c0 += tile_cols) {
+    RowArgs<T> a = a0;
+    a.X = a0.X + c0;
+    a.Y = a0.Y + c0;
+    a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
+    const int nvec = (a.F + VEC - 1) / VEC;
+    const unsigned grid = (unsigned)n_long;
+    if (nvec <= 32) row_reduce_long_kernel<T, VEC, 1><<<grid, kLongWarps * 32, 0, st>>>(a, long_rows);
+    else if (nvec <= 64) row_reduce_long_kernel<T, VEC, 2><<<grid, kLongWarps * 32, 0, st>>>(a, long_rows);
+    else row_reduce_long_kernel<T, VEC, 4><<<grid, kLongWarps * 32, 0, st>>>(a, long_rows);
+    GNN_LAUNCH_CHECK();
+  }
+  return GNN_OK;
+}
+
+template <typename T>
+inline int launch_row_reduce_long(const RowArgs<T>& a, const int64_t* long_rows, int64_t n_long, cudaStream_t st) {
+  if (n_long <= 0 || a.F <= 0) return GNN_OK;
+  const int vec = pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F);
+  if (sizeof(T) == 2 && vec == 8) return launch_row_reduce_long_vec<T, (sizeof(T) == 2 ? 8 : 4)>(a, long_rows, n_long, st);
+  if (vec >= 4) return launch_row_reduce_long_vec<T, 4>(a, long_rows, n_long, st);
+  if (vec == 2) return launch_row_reduce_long_vec<T, 2>(a, long_rows, n_long, st);
+  return launch_row_reduce_long_vec<T, 1>(a, long_rows, n_long, st);
+}
+
+}  // namespace gnn

@@ -1,0 +1,273 @@
+"""torch.autograd.Function wrappers over the C ABI (the seam of SURVEY.md §1:
+drop-in nn.Module.forward -> autograd.Function -> libgnn_b200.so -> sm_100a kernels).
+
+Every function here launches the CUDA library on the caller's current stream; a CPU
+tensor raises.  torch supplies device memory, streams and autograd bookkeeping only.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .graph import CSRGraph, _p, _require_cuda, _stream_ptr, index_block_transpose
+
+
+def _rowmajor(x: torch.Tensor) -> torch.Tensor:
+    """Rows must be unit-stride in the feature dimension; the row stride is free."""
+    if x.dim() != 2:
+        raise _lib.GnnError(f"expected a 2-D feature matrix, got shape {tuple(x.shape)}")
+    if x.stride(1) != 1 and x.shape[1] > 1:
+        x = x.contiguous()
+    if x.shape[0] > 1 and x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    return x
+
+
+def _ld(x: torch.Tensor) -> int:
+    return x.stride(0) if x.shape[0] > 1 else max(x.shape[1], 1)
+
+
+def _padded_empty(rows: int, F: int, dtype, device) -> torch.Tensor:
+    """[rows, F] view of a buffer whose row stride is a multiple of 16 bytes."""
+    per16 = 16 // torch.empty((), dtype=dtype).element_size()
+    ld = (F + per16 - 1) // per16 * per16
+    return torch.empty((rows, ld), dtype=dtype, device=device)[:, :F]
+
+
+# --------------------------------------------------------------------------------------
+# GCN: Y = Â·X
+# --------------------------------------------------------------------------------------
+def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, planned: bool = True) -> torch.Tensor:
+    """One gnn_spmm_csr_{f32,bf16} launch (no autograd)."""
+    _require_cuda(X)
+    lib = _lib.load()
+    X = _rowmajor(X)
+    if X.shape[0] != g.n_cols:
+        raise _lib.GnnError(f"spmm: X has {X.shape[0]} rows, adjacency has {g.n_cols} columns")
+    F = X.shape[1]
+    if out is None:
+        out = torch.empty((g.n_rows, F), dtype=X.dtype, device=X.device)
+    st = _stream_ptr()
+    if X.dtype == torch.float32:
+        lr = g.long_rows() if planned else None
+        if lr is not None and lr.numel() > 0:
+            _lib.check(lib.gnn_spmm_csr_planned_f32(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows,
+                                                    g.n_cols, F, _ld(X), _ld(out), _p(lr), lr.numel(), None, 0, st),
+                       "gnn_spmm_csr_planned_f32")
+        else:
+            _lib.check(lib.gnn_spmm_csr_f32(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F,
+                                            _ld(X), _ld(out), st), "gnn_spmm_csr_f32")
+    elif X.dtype == torch.bfloat16:
+        _lib.check(lib.gnn_spmm_csr_bf16(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F,
+                                         _ld(X), _ld(out), st), "gnn_spmm_csr_bf16")
+    else:
+        raise _lib.GnnError(f"spmm: unsupported dtype {X.dtype} (fp32 and bf16 only)")
+    return out
+
+
+class _SpmmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, g: CSRGraph):
+        ctx.g = g
+        return spmm_raw(g, X)
+
+    @staticmethod
+    def backward(ctx, dY):
+        # autograd of torch.spmm (GCN/GCN.py:43): dX = Âᵀ·dY, no gradient to Â
+        dX = spmm_raw(ctx.g.transpose(), dY.contiguous()) if ctx.needs_input_grad[0] else None
+        return dX, None
+
+
+def spmm(g: CSRGraph, X: torch.Tensor) -> torch.Tensor:
+    """Y = Â·X with autograd (replaces torch.spmm(adj, support), GCN/GCN.py:43)."""
+    return _SpmmFn.apply(X, g)
+
+
+# --------------------------------------------------------------------------------------
+# GraphSAGE: fused gather + reduce
+# --------------------------------------------------------------------------------------
+def pad_table(table: torch.Tensor) -> torch.Tensor:
+    """Copy a feature table once into a buffer whose rows are 16-byte aligned and return
+    the [N,F] view (602 fp32 columns -> row stride 604); this is what enables the TMA path."""
+    _require_cuda(table)
+    N, F = table.shape
+    out = _padded_empty(N, F, table.dtype, table.device)
+    out.copy_(table)
+    if out.stride(0) > F:
+        out.as_strided((N, out.stride(0) - F), (out.stride(0), 1), F).zero_()
+    return out
+
+
+def gather_reduce_raw(table: torch.Tensor, idx: Optional[torch.Tensor], n_src: int, fanout: int, reduce: str = "mean",
+                      out: Optional[torch.Tensor] = None, argmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One gnn_gather_reduce_{f32,bf16} launch (no autograd).  idx=None: identity block."""
+    _require_cuda(table, idx)
+    lib = _lib.load()
+    if reduce not in _lib.REDUCE:
+        raise ValueError("Unknown aggr type, expected sum, max, or mean, but got {}".format(reduce))
+    table = _rowmajor(table)
+    N, F = table.shape
+    if idx is not None:
+        idx = idx.contiguous().view(-1)
+        if idx.dtype not in (torch.int32, torch.int64):
+            idx = idx.to(torch.int64)
+        if idx.numel() != n_src * fanout:
+            raise _lib.GnnError(f"index block has {idx.numel()} ids, expected n_src*fanout = {n_src * fanout}")
+    if out is None:
+        out = _padded_empty(n_src, F, table.dtype, table.device)
+    bits = 64 if (idx is None or idx.dtype == torch.int64) else 32
+    fn = {torch.float32: lib.gnn_gather_reduce_f32, torch.bfloat16: lib.gnn_gather_reduce_bf16}.get(table.dtype)
+    if fn is None:
+        raise _lib.GnnError(f"gather_reduce: unsupported dtype {table.dtype}")
+    _lib.check(fn(_p(table), _ld(table), N, _p(idx), bits, n_src, fanout, F, _lib.REDUCE[reduce], _p(out), _ld(out),
+                  _p(argmax), _stream_ptr()), "gnn_gather_reduce")
+    return out
+
+
+class _GatherReduceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, idx, n_src, fanout, reduce):
+        ctx.meta = (n_src, fanout, reduce, tuple(table.shape))
+        argmax = None
+        out = _padded_empty(n_src, table.shape[1], table.dtype, table.device)
+        if reduce == "max" and ctx.needs_input_grad[0]:
+            argmax = torch.empty((n_src, out.stride(0)), dtype=torch.int32, device=table.device)[:, :table.shape[1]]
+        gather_reduce_raw(table, idx, n_src, fanout, reduce, out=out, argmax=argmax)
+        ctx.save_for_backward(idx if idx is not None else torch.empty(0), argmax if argmax is not None else torch.empty(0))
+        ctx.has_idx = idx is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        n_src, fanout, reduce, (N, F) = ctx.meta
+        idx, argmax = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        if d_out.dtype != torch.float32:
+            raise _lib.GnnError("gather_reduce backward is fp32 only")
+        lib = _lib.load()
+        d_out = d_out.contiguous()
+        scale = 1.0 / fanout if reduce == "mean" else 1.0
+        if not ctx.has_idx:
+            # pre-gathered [n_src*fanout, F] input (Aggregator.py:18): dense broadcast / argmax routing
+            d_table = torch.empty((N, F), dtype=torch.float32, device=d_out.device)
+            am = argmax[:, :F].contiguous() if reduce == "max" else None
+            _lib.check(lib.gnn_gather_reduce_bwd_dense_f32(_p(d_out), _ld(d_out), _p(am), n_src, fanout, F, scale,
+                                                           _p(d_table), _stream_ptr()), "gnn_gather_reduce_bwd_dense_f32")
+            if N > n_src * fanout:
+                d_table[n_src * fanout:].zero_()
+            return d_table, None, None, None, None
+        if reduce == "max":
+            raise _lib.GnnError("max backward into a gathered table is not implemented (the reference's max path "
+                                "raises TypeError, GraphSAGE_Pytorch/models/Aggregator.py:24,29)")
+        rowptr_t, pos_t = index_block_transpose(idx, N)
+        d_table = torch.empty((N, F), dtype=torch.float32, device=d_out.device)
+        _lib.check(lib.gnn_gather_reduce_bwd_f32(_p(rowptr_t), _p(pos_t), N, fanout, scale, _p(d_out), _ld(d_out),
+                                                 _p(d_table), _ld(d_table), F, _stream_ptr()),
+                   "gnn_gather_reduce_bwd_f32")
+        return d_table, None, None, None, None
+
+
+def gather_reduce(table: torch.Tensor, idx: Optional[torch.Tensor], n_src: int, fanout: int,
+                  reduce: str = "mean") -> torch.Tensor:
+    """out[i] = reduce_k table[idx[i*fanout+k]] with autograd into `table`."""
+    if reduce not in _lib.REDUCE:
+        raise ValueError("Unknown aggr type, expected sum, max, or mean, but got {}".format(reduce))
+    return _GatherReduceFn.apply(table, idx, n_src, fanout, reduce)
+
+
+# --------------------------------------------------------------------------------------
+# GAT / HAN: fused multi-head attention aggregation
+# --------------------------------------------------------------------------------------
+def gat_scores_raw(Wh: torch.Tensor, a_src: torch.Tensor, a_dst: torch.Tensor, H: int, Fp: int):
+    _require_cuda(Wh, a_src, a_dst)
+    lib = _lib.load()
+    Wh = _rowmajor(Wh)
+    n = Wh.shape[0]
+    s = torch.empty((n, H), dtype=torch.float32, device=Wh.device)
+    t = torch.empty((n, H), dtype=torch.float32, device=Wh.device)
+    _lib.check(lib.gnn_gat_scores_f32(_p(Wh), _ld(Wh), _p(a_src.contiguous()), _p(a_dst.contiguous()), n, H, Fp, _p(s),
+                                      _p(t), _stream_ptr()), "gnn_gat_scores_f32")
+    return s, t
+
+
+def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=0, keep=None, save_stats=False):
+    _require_cuda(Wh, s, t, keep)
+    lib = _lib.load()
+    Wh = _rowmajor(Wh)
+    s = s.contiguous()
+    t = t.contiguous()
+    n = g.n_rows
+    if Wh.shape != (n, H * Fp) or g.n_cols != n:
+        raise _lib.GnnError(f"gat: Wh {tuple(Wh.shape)} does not match graph n={n}, H*Fp={H * Fp}")
+    out = torch.empty((n, H * Fp), dtype=torch.float32, device=Wh.device)
+    row_max = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
+    row_sum = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
+    col_mean = Wh.mean(dim=0).contiguous() if g.has_empty_rows() else None
+    _lib.check(lib.gnn_gat_fused_fwd_f32(_p(g.rowptr), _p(g.col), _p(Wh), _ld(Wh), _p(s), _p(t), n, H, Fp, float(alpha),
+                                         mode, elu, _p(col_mean), _p(keep), _p(out), _ld(out), _p(row_max), _p(row_sum),
+                                         _stream_ptr()), "gnn_gat_fused_fwd_f32")
+    return out, row_max, row_sum
+
+
+class _GatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Wh, s, t, g: CSRGraph, H, Fp, alpha, mode, keep):
+        Wh = _rowmajor(Wh)
+        out, row_max, row_sum = gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=0, keep=keep, save_stats=True)
+        ctx.g, ctx.cfg = g, (H, Fp, float(alpha), mode)
+        ctx.save_for_backward(Wh, s.contiguous(), t.contiguous(), row_max, row_sum, out,
+                              keep if keep is not None else torch.empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        Wh, s, t, row_max, row_sum, out, keep = ctx.saved_tensors
+        g = ctx.g
+        H, Fp, alpha, mode = ctx.cfg
+        lib = _lib.load()
+        keep = keep if keep.numel() > 0 else None
+        n = g.n_rows
+        d_out = d_out.contiguous()
+        gt = g.transpose()
+        dev = Wh.device
+        d_Wh = torch.empty((n, H * Fp), dtype=torch.float32, device=dev)
+        d_s = torch.empty((n, H), dtype=torch.float32, device=dev)
+        d_t = torch.empty((n, H), dtype=torch.float32, device=dev)
+        rowdot = torch.empty((n, H), dtype=torch.float32, device=dev)
+        scratch = torch.empty((2, max(g.nnz, 1), H), dtype=torch.float32, device=dev)
+        _lib.check(lib.gnn_gat_fused_bwd_f32(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t), _p(Wh),
+                                             _ld(Wh), _p(s), _p(t), _p(row_max), _p(row_sum), _p(out), _p(d_out),
+                                             _ld(out), n, H, Fp, alpha, mode, _p(keep), _p(d_Wh), _ld(d_Wh), _p(d_s),
+                                             _p(d_t), _p(rowdot), _p(scratch), g.nnz, _stream_ptr()),
+                   "gnn_gat_fused_bwd_f32")
+        if g.has_empty_rows():
+            # rows without edges output the mean of all Wh rows (GAT/models/layers.py:28-30)
+            deg = g.rowptr[1:] - g.rowptr[:-1]
+            d_Wh += d_out[deg == 0].sum(dim=0, keepdim=True) / n
+        return d_Wh, d_s, d_t, None, None, None, None, None, None
+
+
+def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tensor, H: int, Fp: int, alpha: float,
+                  mode: int = _lib.GAT_SOFTMAX, elu: int = 0, keep: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused edge-score + LeakyReLU + edge-softmax + weighted aggregation over all H heads.
+
+    With gradients enabled the kernel returns the pre-activation aggregate and the ELU(s)
+    are applied by torch (elementwise, outside the hot path) so autograd can differentiate
+    them; without gradients the ELU is fused into the kernel's epilogue."""
+    need_grad = torch.is_grad_enabled() and (Wh.requires_grad or s.requires_grad or t.requires_grad)
+    if not need_grad:
+        return gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep)[0]
+    out = _GatFn.apply(Wh, s, t, g, H, Fp, alpha, mode, keep)
+    for _ in range(elu):
+        out = torch.nn.functional.elu(out)
+    return out
+
+
+def attention_keep_mask(g: CSRGraph, H: int, p: float, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Per-edge, per-head post-softmax dropout factors (0 or 1/(1-p)), GAT/models/layers.py:31."""
+    keep = torch.empty((g.nnz, H), dtype=torch.float32, device=g.device)
+    keep.bernoulli_(1.0 - p, generator=generator).div_(1.0 - p)
+    return keep

@@ -1,0 +1,203 @@
+"""Device-resident graph structures built through the C ABI.
+
+`CSRGraph` is what the kernels walk: int64 rowptr, int32 col, optional fp32 val, plus a
+lazily built transpose (for the deterministic backward) and the long-row plan.  The
+builders accept exactly the adjacency forms the reference layers are handed
+(SURVEY.md §8b "Accepted adj forms"):
+  - torch sparse COO fp32          (GCN/data_utils.py:63-70)
+  - dense [N,N] fp32 / fp64 mask   (GAT/data_utils.py:85, HAN/utils/data_utils.py:85-89)
+  - fixed-fanout index blocks      (GraphSAGE_Pytorch/sample_utils.py:20-35)
+torch is used here for device memory and streams only.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.GnnError("tensor is not on a CUDA device: the message-passing path has no CPU fallback")
+
+
+class CSRGraph:
+    """CSR adjacency on the device (rows = destination nodes)."""
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int):
+        _require_cuda(rowptr, col, val)
+        assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
+        assert val is None or val.dtype == torch.float32
+        self.rowptr, self.col, self.val = rowptr.contiguous(), col.contiguous(), None if val is None else val.contiguous()
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.nnz = int(col.numel())
+        self._t: Optional["CSRGraph"] = None
+        self._perm_t: Optional[torch.Tensor] = None
+        self._long_rows: Optional[torch.Tensor] = None
+        self._zero_rows: Optional[bool] = None
+
+    @property
+    def device(self):
+        return self.rowptr.device
+
+    # -- plans ---------------------------------------------------------------------
+    def transpose(self) -> "CSRGraph":
+        """CSR of the transpose, stable in source order (gnn_csr_transpose); cached."""
+        if self._t is None:
+            lib = _lib.load()
+            dev = self.device
+            rowptr_t = torch.empty(self.n_cols + 1, dtype=torch.int64, device=dev)
+            col_t = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+            val_t = None if self.val is None else torch.empty(self.nnz, dtype=torch.float32, device=dev)
+            perm_t = torch.empty(self.nnz, dtype=torch.int64, device=dev)
+            ws_bytes = lib.gnn_csr_transpose_workspace_size(self.nnz, self.n_rows, self.n_cols)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            _lib.check(lib.gnn_csr_transpose(_p(self.rowptr), _p(self.col), _p(self.val), self.n_rows, self.n_cols,
+                                             self.nnz, _p(rowptr_t), _p(col_t), _p(val_t), _p(perm_t), _p(ws),
+                                             ws_bytes, _stream_ptr()), "gnn_csr_transpose")
+            self._t = CSRGraph(rowptr_t, col_t, val_t, self.n_cols, self.n_rows)
+            self._t._t = self
+            self._perm_t = perm_t
+        return self._t
+
+    @property
+    def perm_t(self) -> torch.Tensor:
+        self.transpose()
+        return self._perm_t
+
+    def long_rows(self) -> torch.Tensor:
+        """Rows whose nnz exceeds the spmm.long_row knob (host-side plan, cached)."""
+        if self._long_rows is None:
+            thr = _lib.get_tuning("spmm.long_row")
+            deg = self.rowptr[1:] - self.rowptr[:-1]
+            self._long_rows = torch.nonzero(deg > thr).flatten().contiguous()
+        return self._long_rows
+
+    def has_empty_rows(self) -> bool:
+        if self._zero_rows is None:
+            deg = self.rowptr[1:] - self.rowptr[:-1]
+            self._zero_rows = bool((deg == 0).any().item()) if self.n_rows > 0 else False
+        return self._zero_rows
+
+    # -- builders --------------------------------------------------------------------
+    @staticmethod
+    def from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int) -> "CSRGraph":
+        """COO -> CSR, stable in row (gnn_build_csr_from_coo)."""
+        _require_cuda(row, col, val)
+        lib = _lib.load()
+        dev = row.device
+        row = row.to(torch.int64).contiguous()
+        col = col.to(torch.int64).contiguous()
+        if val is not None:
+            val = val.to(torch.float32).contiguous()
+        nnz = int(row.numel())
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        col32 = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val32 = None if val is None else torch.empty(nnz, dtype=torch.float32, device=dev)
+        ws_bytes = lib.gnn_build_csr_from_coo_workspace_size(nnz, n_rows)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        _lib.check(lib.gnn_build_csr_from_coo(_p(row), _p(col), _p(val), nnz, n_rows, n_cols, _p(rowptr), _p(col32),
+                                              _p(val32), None, _p(ws), ws_bytes, _stream_ptr()),
+                   "gnn_build_csr_from_coo")
+        return CSRGraph(rowptr, col32, val32, n_rows, n_cols)
+
+    @staticmethod
+    def from_torch_sparse(adj: torch.Tensor) -> "CSRGraph":
+        """torch sparse COO (the tensor GCN/data_utils.py:70 builds) -> CSR.
+
+        The reference tensor is flagged uncoalesced but holds no duplicates and is
+        row-major sorted; `_indices()/_values()` are used as they are,
+        duplicates — if a caller passes any — simply stay separate edges, which sums to the
+        same product as torch.spmm."""
+        assert adj.layout == torch.sparse_coo
+        idx = adj._indices()
+        return CSRGraph.from_coo(idx[0], idx[1], adj._values(), adj.shape[0], adj.shape[1])
+
+    @staticmethod
+    def from_dense_mask(adj: torch.Tensor) -> "CSRGraph":
+        """Dense [N,M] adjacency used only as `adj > 0` -> CSR pattern in adj.nonzero() order."""
+        _require_cuda(adj)
+        if adj.dtype not in (torch.float32, torch.float64):
+            adj = adj.to(torch.float32)
+        if adj.stride(-1) != 1:
+            adj = adj.contiguous()
+        lib = _lib.load()
+        dev = adj.device
+        n_rows, n_cols = adj.shape
+        ld = adj.stride(0) if n_rows > 1 else max(n_cols, 1)
+        dt = 0 if adj.dtype == torch.float32 else 1
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        ws_bytes = lib.gnn_dense_mask_count_workspace_size(n_rows)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        _lib.check(lib.gnn_dense_mask_count(_p(adj), dt, n_rows, n_cols, ld, _p(rowptr), _p(ws), ws_bytes,
+                                            _stream_ptr()), "gnn_dense_mask_count")
+        nnz = int(rowptr[-1].item())  # one host read: nnz sizes the col array
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        _lib.check(lib.gnn_dense_mask_fill(_p(adj), dt, n_rows, n_cols, ld, _p(rowptr), _p(col), _stream_ptr()),
+                   "gnn_dense_mask_fill")
+        return CSRGraph(rowptr, col, None, n_rows, n_cols)
+
+
+class _AdjCache:
+    """Converts an adjacency tensor to CSR once and reuses it while the tensor is unchanged
+    (keyed by data_ptr, _version, shape — SURVEY.md §8b)."""
+
+    def __init__(self, max_entries: int = 16):
+        self._entries = {}
+        self._max = max_entries
+
+    def get(self, adj) -> CSRGraph:
+        if isinstance(adj, CSRGraph):
+            return adj
+        if adj.layout == torch.sparse_coo:
+            key = ("coo", adj._values().data_ptr(), adj._indices().data_ptr(), adj._values()._version, tuple(adj.shape))
+        else:
+            key = ("dense", adj.data_ptr(), adj._version, tuple(adj.shape), adj.dtype)
+        hit = self._entries.get(key)
+        if hit is not None:
+            ref, g = hit
+            if ref() is adj:
+                return g
+        g = CSRGraph.from_torch_sparse(adj) if adj.layout == torch.sparse_coo else CSRGraph.from_dense_mask(adj)
+        if len(self._entries) >= self._max:
+            self._entries.pop(next(iter(self._entries)))
+        try:
+            ref = weakref.ref(adj)
+        except TypeError:  # pragma: no cover
+            ref = lambda: adj
+        self._entries[key] = (ref, g)
+        return g
+
+
+adj_cache = _AdjCache()
+
+
+def index_block_transpose(idx: torch.Tensor, n_table_rows: int):
+    """Fixed-fanout index block -> (rowptr_t, pos_t) for the ordered gather backward."""
+    _require_cuda(idx)
+    lib = _lib.load()
+    idx = idx.contiguous().view(-1)
+    bits = 32 if idx.dtype == torch.int32 else 64
+    if idx.dtype not in (torch.int32, torch.int64):
+        idx = idx.to(torch.int64)
+    n = int(idx.numel())
+    dev = idx.device
+    rowptr_t = torch.empty(n_table_rows + 1, dtype=torch.int64, device=dev)
+    pos_t = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ws_bytes = lib.gnn_index_block_transpose_workspace_size(n, n_table_rows)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    _lib.check(lib.gnn_index_block_transpose(_p(idx), bits, n, n_table_rows, _p(rowptr_t), _p(pos_t), _p(ws), ws_bytes,
+                                             _stream_ptr()), "gnn_index_block_transpose")
+    return rowptr_t, pos_t

@@ -1,0 +1,146 @@
+"""Drop-in GAT layers and models (class names, ctor signatures, parameter names/shapes and
+forward signatures of /root/reference GAT/models/layers.py and GAT/models/GAT.py).
+
+What changes: the all-pairs `[N,N,2F']` score tensor, masked softmax and dense
+`attention·Wh` (GAT/models/layers.py:25-32) become one fused kernel over the CSR of
+`adj > 0`; `GATBase.forward` runs all heads of a layer in ONE launch by concatenating the
+per-head `W` (state_dict stays `attentions.AttentionHead{k}.W [in,F']`, `.a [2F',1]`).
+The dense `h·W` stays torch.mm; the per-node score halves `Wh·a[:F']`, `Wh·a[F':]` are a
+[N,H·F']x[H·F',2H] torch product so autograd reaches `a`.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from ..functional import attention_keep_mask, gat_aggregate
+from ..graph import adj_cache
+
+
+def _fused_heads(x, adj, Ws, a_srcs, a_dsts, alpha, mode, elu, dropout, training):
+    """All heads of one attention layer: x [N,in]; Ws list of [in,F']; a_* list of [F']."""
+    g = adj_cache.get(adj)
+    H = len(Ws)
+    Fp = Ws[0].shape[1]
+    W_cat = Ws[0] if H == 1 else torch.cat(list(Ws), dim=1)
+    Wh = torch.mm(x, W_cat)  # [N, H*F']  (layers.py:23, all heads at once)
+    Wh3 = Wh.view(-1, H, Fp)
+    a_src = a_srcs[0].view(1, Fp) if H == 1 else torch.stack(list(a_srcs), dim=0)
+    a_dst = a_dsts[0].view(1, Fp) if H == 1 else torch.stack(list(a_dsts), dim=0)
+    s = (Wh3 * a_src.unsqueeze(0)).sum(-1)  # [N,H] = Wh_i·a[:F']
+    t = (Wh3 * a_dst.unsqueeze(0)).sum(-1)  # [N,H] = Wh_j·a[F':]
+    keep = None
+    if training and dropout > 0.0:
+        keep = attention_keep_mask(g, H, dropout)  # post-softmax dropout, layers.py:31
+    return gat_aggregate(g, Wh, s, t, H, Fp, alpha, mode=mode, elu=elu, keep=keep)
+
+
+class GraphAttentionLayer(nn.Module):
+    """One attention head (GAT/models/layers.py:6-40 == HAN/models/NodeAttention.py:6-41)."""
+
+    def __init__(self, in_features, out_features, dropout, alpha, concat=True, **kwargs):
+        super(GraphAttentionLayer, self).__init__(**kwargs)
+        self.dropout = dropout
+        self.in_features = in_features
+        self.out_features = out_features
+        self.alpha = alpha
+        self.concat = concat
+        self.W = nn.Parameter(torch.empty(size=(in_features, out_features)))
+        nn.init.xavier_uniform_(self.W.data, gain=1.414)
+        self.a = nn.Parameter(torch.empty(size=(2 * out_features, 1)))
+        nn.init.xavier_uniform_(self.a.data, gain=1.414)
+        self.leakyrelu = nn.LeakyReLU(self.alpha)
+
+    def _halves(self):
+        Fp = self.out_features
+        return self.a[:Fp, 0], self.a[Fp:, 0]
+
+    def forward(self, h, adj):
+        a_src, a_dst = self._halves()
+        return _fused_heads(h, adj, [self.W], [a_src], [a_dst], self.alpha, _lib.GAT_SOFTMAX,
+                            1 if self.concat else 0, self.dropout, self.training)
+
+    def __repr__(self):
+        return self.__class__.__name__ + ' (' + str(self.in_features) + ' -> ' + str(self.out_features) + ')'
+
+
+class SpGraphAttentionLayer(nn.Module):
+    """Edge-list variant (GAT/models/layers.py:72-134): att = exp(-LeakyReLU(a·[h_i||h_j]))
+    normalised by its row sum, dropout on the un-normalised edge weights (layers.py:115)."""
+
+    def __init__(self, in_features, out_features, dropout, alpha, concat=True):
+        super(SpGraphAttentionLayer, self).__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.alpha = alpha
+        self.concat = concat
+        self.W = nn.Parameter(torch.zeros(size=(in_features, out_features)))
+        nn.init.xavier_normal_(self.W.data, gain=1.414)
+        self.a = nn.Parameter(torch.zeros(size=(1, 2 * out_features)))
+        nn.init.xavier_normal_(self.a.data, gain=1.414)
+        self.dropout = nn.Dropout(dropout)
+        self.leakyrelu = nn.LeakyReLU(self.alpha)
+
+    def _halves(self):
+        Fp = self.out_features
+        return self.a[0, :Fp], self.a[0, Fp:]
+
+    def forward(self, input, adj):
+        a_src, a_dst = self._halves()
+        return _fused_heads(input, adj, [self.W], [a_src], [a_dst], self.alpha, _lib.GAT_EXPNEG,
+                            1 if self.concat else 0, self.dropout.p, self.training)
+
+    def __repr__(self):
+        return self.__class__.__name__ + ' (' + str(self.in_features) + ' -> ' + str(self.out_features) + ')'
+
+
+class GATBase(nn.Module):
+    """GAT/models/GAT.py:7-18.  All heads in `self.attentions` run in one fused launch."""
+
+    _mode = _lib.GAT_SOFTMAX
+
+    def __init__(self, dropout, **kwargs):
+        super(GATBase, self).__init__(**kwargs)
+        self.dropout = dropout
+        self.attentions = nn.ModuleList()
+        self.out_att = None
+
+    def _heads(self, x, adj):
+        atts = list(self.attentions)
+        halves = [att._halves() for att in atts]
+        head0 = atts[0]
+        p = head0.dropout.p if isinstance(head0.dropout, nn.Dropout) else head0.dropout
+        # concat=True heads apply ELU (layers.py:35); cat over heads == column blocks k*F'..(k+1)*F'
+        return _fused_heads(x, adj, [att.W for att in atts], [h[0] for h in halves], [h[1] for h in halves],
+                            head0.alpha, self._mode, 1 if head0.concat else 0, p, self.training)
+
+    def forward(self, x, adj):
+        adj = adj_cache.get(adj)
+        x = F.dropout(x, self.dropout, training=self.training)
+        x = self._heads(x, adj)
+        x = F.dropout(x, self.dropout, training=self.training)
+        return F.elu(self.out_att(x, adj))
+
+
+class GAT(GATBase):
+    """Dense-adjacency GAT (GAT/models/GAT.py:21-28)."""
+
+    def __init__(self, nfeat, nhid, nclass, dropout, alpha, nheads, **kwargs):
+        super(GAT, self).__init__(dropout, **kwargs)
+        for i in range(nheads):
+            self.attentions.add_module(f'AttentionHead{i}',
+                                       GraphAttentionLayer(nfeat, nhid, dropout=dropout, alpha=alpha, concat=True))
+        self.out_att = GraphAttentionLayer(nhid * nheads, nclass, dropout=dropout, alpha=alpha, concat=False)
+
+
+class SpGAT(GATBase):
+    """Edge-list GAT (GAT/models/GAT.py:31-38)."""
+
+    _mode = _lib.GAT_EXPNEG
+
+    def __init__(self, nfeat, nhid, nclass, dropout, alpha, nheads, **kwargs):
+        super(SpGAT, self).__init__(dropout, **kwargs)
+        for i in range(nheads):
+            self.attentions.add_module(f'AttentionHead{i}',
+                                       SpGraphAttentionLayer(nfeat, nhid, dropout=dropout, alpha=alpha, concat=True))
+        self.out_att = SpGraphAttentionLayer(nhid * nheads, nclass, dropout=dropout, alpha=alpha, concat=False)

@@ -1,0 +1,175 @@
+"""Drop-in GraphSAGE layers (class names, ctor signatures, parameter names and forward
+signatures of /root/reference GraphSAGE_Pytorch/models/{Aggregator,SageGCN,GraphSage}.py and
+the `Aggregator` function of GraphSAGE/graph_utils.py).
+
+Two ways in:
+  * the reference call surface — `NeighborAggregator.forward(neighbor_feature)` with the
+    pre-gathered `[n_src, fanout, F]` tensor (Aggregator.py:18): the reduce over the fanout
+    axis runs in the CUDA kernel on that tensor as an identity index block;
+  * the fused fast path — `GraphSage.forward_sampled(table, blocks)`: the sampled node ids
+    of `multihop_sampling` (sample_utils.py:20-35) index a feature table resident in HBM and
+    the gather (data_utils.py:64) is fused into the reduce, so the `[n_src, fanout, F]`
+    tensor is never materialised and only the ids cross PCIe.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from ..functional import gather_reduce, pad_table
+
+
+class SampledBlock:
+    """Neighbour features given as (table, ids): rows `ids[i*fanout:(i+1)*fanout]` of `table`
+    are the neighbours of source i (the src-major layout of sample_utils.py:16)."""
+
+    def __init__(self, table: torch.Tensor, ids: torch.Tensor, fanout: int):
+        self.table, self.ids, self.fanout = table, ids, int(fanout)
+        self.n_src = ids.numel() // self.fanout
+
+
+class NeighborAggregator(nn.Module):
+    def __init__(self, input_dim, output_dim, use_bias=False, aggr_method="mean", **kwargs):
+        super(NeighborAggregator, self).__init__(*kwargs)
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.use_bias = use_bias
+        self.aggr_method = aggr_method
+        self.weight = nn.Parameter(torch.Tensor(input_dim, output_dim))
+        nn.init.xavier_uniform_(self.weight)
+        if self.use_bias:
+            self.bias = nn.Parameter(torch.zeros(self.output_dim))
+
+    def aggregate(self, neighbor_feature):
+        if self.aggr_method not in ("mean", "sum", "max"):
+            raise ValueError("Unknown aggr type, expected sum, max, or mean, but got {}".format(self.aggr_method))
+        if isinstance(neighbor_feature, SampledBlock):
+            b = neighbor_feature
+            return gather_reduce(b.table, b.ids, b.n_src, b.fanout, self.aggr_method)
+        n_src, fanout, feat = neighbor_feature.shape
+        flat = neighbor_feature.reshape(n_src * fanout, feat)
+        # `max`: the reference's `.max(dim=1)` returns a (values, indices) tuple and the
+        # following matmul raises TypeError (Aggregator.py:24,29); we implement `.values`.
+        return gather_reduce(flat, None, n_src, fanout, self.aggr_method)
+
+    def forward(self, neighbor_feature):
+        aggr_neighbor = self.aggregate(neighbor_feature)
+        neighbor_hidden = torch.matmul(aggr_neighbor, self.weight)
+        if self.use_bias:
+            neighbor_hidden += self.bias
+        return neighbor_hidden
+
+    def extra_repr(self):
+        return 'in_features={}, out_features={}, aggr_method={}'.format(
+            self.input_dim, self.output_dim, self.aggr_method)
+
+
+class SageGCN(nn.Module):
+    def __init__(self, input_dim, hidden_dim, activation=F.relu, aggr_neighbor_method="mean", aggr_hidden_method="sum",
+                 **kwargs):
+        super(SageGCN, self).__init__(**kwargs)
+        assert aggr_neighbor_method in ["mean", "sum", "max"]
+        assert aggr_hidden_method in ["sum", "concat"]
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.aggr_neighbor_method = aggr_neighbor_method
+        self.aggr_hidden_method = aggr_hidden_method
+        self.activation = activation
+        self.aggregator = NeighborAggregator(input_dim, hidden_dim, aggr_method=aggr_neighbor_method)
+        self.weight = nn.Parameter(torch.Tensor(input_dim, hidden_dim))
+        nn.init.xavier_uniform_(self.weight)
+
+    def forward(self, src_node_features, neighbor_node_features):
+        neighbor_hidden = self.aggregator(neighbor_node_features)
+        self_hidden = torch.matmul(src_node_features, self.weight)
+        if self.aggr_hidden_method == "sum":
+            hidden = self_hidden + neighbor_hidden
+        elif self.aggr_hidden_method == "concat":
+            hidden = torch.cat([self_hidden, neighbor_hidden], dim=1)
+        else:
+            raise ValueError("Expected sum or concat, got {}".format(self.aggr_hidden_method))
+        if self.activation:
+            return self.activation(hidden)
+        return hidden
+
+    def extra_repr(self):
+        output_dim = self.hidden_dim if self.aggr_hidden_method == "sum" else self.hidden_dim * 2
+        return 'in_features={}, out_features={}, aggr_hidden_method={}'.format(
+            self.input_dim, output_dim, self.aggr_hidden_method)
+
+
+class GraphSage(nn.Module):
+    def __init__(self, input_dim, hidden_dim, num_neighbors_list):
+        super(GraphSage, self).__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.num_neighbors_list = num_neighbors_list
+        self.num_layers = len(num_neighbors_list)
+        self.gcn = nn.ModuleList()
+        self.gcn.append(SageGCN(input_dim, hidden_dim[0]))
+        for index in range(0, len(hidden_dim) - 2):
+            self.gcn.append(SageGCN(hidden_dim[index], hidden_dim[index + 1]))
+        self.gcn.append(SageGCN(hidden_dim[-2], hidden_dim[-1], activation=None))
+
+    def forward(self, node_features_list):
+        """Reference call surface (GraphSage.py:18-30): pre-gathered feature tensors per hop."""
+        hidden = node_features_list
+        for l in range(self.num_layers):
+            next_hidden = []
+            gcn = self.gcn[l]
+            for hop in range(self.num_layers - l):
+                src_node_features = hidden[hop]
+                src_node_num = len(src_node_features)
+                neighbor_node_features = hidden[hop + 1].view((src_node_num, self.num_neighbors_list[hop], -1))
+                h = gcn(src_node_features, neighbor_node_features)
+                next_hidden.append(h)
+            hidden = next_hidden
+        return hidden[0]
+
+    def forward_sampled(self, table, node_id_blocks):
+        """Fused path: `table` [N,F] resident on the device (ideally `pad_table`-aligned),
+        `node_id_blocks` = the id lists `multihop_sampling` returns (lengths B, B·f1, B·f1·f2, …)
+        as int32/int64 device tensors.  Same arithmetic as `forward` on
+        `[table[ids] for ids in node_id_blocks]`, without materialising the gathers of the
+        outermost hop: layer 0 reads neighbours straight from the table."""
+        L = self.num_layers
+        assert len(node_id_blocks) == L + 1
+        gcn = self.gcn[0]
+        hidden = []
+        for hop in range(L):
+            src = table.index_select(0, node_id_blocks[hop].to(torch.int64)) if node_id_blocks[hop].dtype != torch.int64 \
+                else table.index_select(0, node_id_blocks[hop])
+            blk = SampledBlock(table, node_id_blocks[hop + 1], self.num_neighbors_list[hop])
+            hidden.append(gcn(src, blk))
+        for l in range(1, L):
+            next_hidden = []
+            gcn = self.gcn[l]
+            for hop in range(L - l):
+                src_node_features = hidden[hop]
+                n_src = len(src_node_features)
+                neigh = hidden[hop + 1].view((n_src, self.num_neighbors_list[hop], -1))
+                next_hidden.append(gcn(src_node_features, neigh))
+            hidden = next_hidden
+        return hidden[0]
+
+    def extra_repr(self):
+        return 'in_features={}, num_neighbors_list={}'.format(self.input_dim, self.num_neighbors_list)
+
+
+def Aggregator(neigh_feat, agg_func='MEAN'):
+    """GraphSAGE/graph_utils.py:4-11.  'MEAN' -> fused mean over dim 1.  The reference's 'MAX'
+    is `torch.argmax` (an int64 index tensor, a bug, graph_utils.py:8); we return the max
+    VALUES and say so in DESIGN.md."""
+    if agg_func not in ('MEAN', 'MAX'):
+        print('请选择合适的聚合函数')
+        raise ValueError(agg_func)
+    n, k, feat = neigh_feat.shape
+    return gather_reduce(neigh_feat.reshape(n * k, feat), None, n, k, 'mean' if agg_func == 'MEAN' else 'max')
+
+
+def gather_mean(feats, index_map):
+    """`torch.mean(torch.embedding(feats, index_map), dim=1)` fused
+    (GraphSAGE/GraphSAGE.py:47-49 followed by graph_utils.py:6): `index_map` is the `[n,k]`
+    int64 map of GraphSAGE/data_utils.py:105-116 with its -1-padded rows already filtered
+    (GraphSAGE.py:48-49 keeps rows whose column 0 is not -1)."""
+    n, k = index_map.shape
+    return gather_reduce(feats, index_map.reshape(-1), n, k, 'mean')

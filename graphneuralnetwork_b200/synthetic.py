@@ -1,0 +1,125 @@
+"""Seeded synthetic inputs of the BASELINE.json shapes.  The reference ships
+no datasets and there is no network, so every config is synthetic.  Host-side generators
+are numpy; the papers100M/Reddit-scale graphs are generated on the device through the C ABI.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import CSRGraph, _p, _stream_ptr
+
+CORA = dict(n=2708, undirected_pairs=5278, feats=1433, classes=7, hidden=16)
+REDDIT = dict(n=232_965, edges=114_615_892, feats=602, classes=41, batch=1024, fanout=(25, 10), hidden=(128, 41))
+ACM = dict(n=3025, feats=1870, classes=3, metapath_nnz=(29_000, 2_210_000, 300_000), heads=8, hidden=8)
+PAPERS100M = dict(n=111_059_956, edges=1_615_685_872, feats=128)
+
+
+def cora_like_edges(n=CORA["n"], pairs=CORA["undirected_pairs"], seed=0) -> np.ndarray:
+    """`pairs` distinct undirected pairs (i<j), uniform, returned as a directed [pairs,2] int32
+    list — the shape of a .cites file before GCN/data_utils.py:35 symmetrises it."""
+    rng = np.random.default_rng(seed)
+    got = set()
+    out = np.empty((pairs, 2), dtype=np.int32)
+    k = 0
+    while k < pairs:
+        i, j = rng.integers(0, n, size=2)
+        if i == j:
+            continue
+        a, b = (int(i), int(j)) if i < j else (int(j), int(i))
+        if (a, b) in got:
+            continue
+        got.add((a, b))
+        out[k] = (a, b)
+        k += 1
+    return out
+
+
+def row_normalised_features(n, f, seed=0) -> np.ndarray:
+    """rand features, row-normalised like GCN/data_utils.py:39-51 leaves them."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, f), dtype=np.float32)
+    return x / x.sum(1, keepdims=True)
+
+
+def symmetric_mask(n, target_nnz, seed=0, dtype=np.float64) -> np.ndarray:
+    """Symmetric 0/1 adjacency with self-loops and about `target_nnz` non-zeros — the dense
+    float64 metapath adjacency of HAN/utils/data_utils.py:85-89."""
+    rng = np.random.default_rng(seed)
+    pairs = max((target_nnz - n) // 2, 0)
+    adj = np.zeros((n, n), dtype=dtype)
+    i = rng.integers(0, n, size=pairs)
+    j = rng.integers(0, n, size=pairs)
+    adj[i, j] = 1
+    adj[j, i] = 1
+    adj[np.arange(n), np.arange(n)] = 1
+    return adj
+
+
+def adjacency_lists(n, avg_degree, seed=0, min_degree=1):
+    """dict node -> set(neighbours) (the `adj_lists` of GraphSAGE_Pytorch/data_utils.py:31-40),
+    undirected, skewed degrees."""
+    rng = np.random.default_rng(seed)
+    m = int(n * avg_degree / 2)
+    w = 1.0 / np.arange(1, n + 1) ** 0.5
+    w /= w.sum()
+    a = rng.choice(n, size=m, p=w)
+    b = rng.integers(0, n, size=m)
+    adj = {i: set() for i in range(n)}
+    for x, y in zip(a.tolist(), b.tolist()):
+        if x != y:
+            adj[x].add(y)
+            adj[y].add(x)
+    for i in range(n):
+        while len(adj[i]) < min_degree:
+            j = int(rng.integers(0, n))
+            if j != i:
+                adj[i].add(j)
+                adj[j].add(i)
+    return adj
+
+
+def uniform_blocks(n_nodes, batch, fanouts, seed=0, dtype=torch.int64, device="cpu", generator=None):
+    """Throughput-run index blocks: uniform ids of lengths B, B·f1, B·f1·f2."""
+    g = generator or torch.Generator(device="cpu").manual_seed(seed)
+    sizes = [batch]
+    for f in fanouts:
+        sizes.append(sizes[-1] * f)
+    return [torch.randint(0, n_nodes, (s,), generator=g, dtype=torch.int64).to(dtype).to(device) for s in sizes]
+
+
+def powerlaw_csr(n_rows: int, mean_degree: float, *, n_cols: int | None = None, row_offset: int = 0,
+                 exponent: float = 2.5, skew: float = 3.0, max_degree: int = 1 << 20, seed: int = 0,
+                 device="cuda", with_values: bool = True, deg_all: torch.Tensor | None = None) -> CSRGraph:
+    """Power-law CSR generated on the device (gnn_synth_*): Pareto degrees with the requested
+    mean, neighbour ids skewed to low ids (hubs), one self-loop per row, GCN-normalised
+    values d_i^-1/2·d_j^-1/2 from the row degrees.  `row_offset`/`n_cols` generate one row
+    block of a larger graph (each rank of the partitioned run builds only its own rows)."""
+    lib = _lib.load()
+    n_cols = n_rows if n_cols is None else n_cols
+    dev = torch.device(device)
+    deg = torch.empty(n_rows, dtype=torch.int64, device=dev)
+    _lib.check(lib.gnn_synth_powerlaw_degrees(n_rows, row_offset, float(mean_degree), float(exponent), int(max_degree),
+                                              seed, _p(deg), _stream_ptr()), "gnn_synth_powerlaw_degrees")
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    nnz = int(rowptr[-1].item())
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    _lib.check(lib.gnn_synth_powerlaw_fill(n_rows, row_offset, n_cols, _p(rowptr), float(skew), seed, _p(col),
+                                           _stream_ptr()), "gnn_synth_powerlaw_fill")
+    val = None
+    if with_values:
+        if deg_all is None:
+            if n_cols != n_rows or row_offset != 0:
+                deg_all = torch.empty(n_cols, dtype=torch.int64, device=dev)
+                _lib.check(lib.gnn_synth_powerlaw_degrees(n_cols, 0, float(mean_degree), float(exponent),
+                                                          int(max_degree), seed, _p(deg_all), _stream_ptr()),
+                           "gnn_synth_powerlaw_degrees")
+            else:
+                deg_all = deg
+        val = torch.empty(nnz, dtype=torch.float32, device=dev)
+        _lib.check(lib.gnn_synth_gcn_values(n_rows, row_offset, _p(rowptr), _p(col), _p(deg_all), _p(val),
+                                            _stream_ptr()), "gnn_synth_gcn_values")
+    del deg
+    return CSRGraph(rowptr, col, val, n_rows, n_cols)

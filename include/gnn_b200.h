@@ -1,0 +1,225 @@
+/*
+ * gnn_b200.h — C ABI of the B200-native message-passing kernels.
+ *
+ * This is the drop-in boundary.  The reference
+ * (kaddly/GraphNeuralNetwork) has no FFI: its seam is the Python
+ * nn.Module.forward of each layer, which bottoms out in ATen calls.  Every entry
+ * point below replaces one of those ATen call sites; the citation after "replaces"
+ * is the reference file:line whose arithmetic the entry point reproduces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *    name ends in _host;
+ *  - the caller owns every buffer; the library never allocates outputs; scratch is
+ *    passed in as (workspace, workspace_bytes) after a *_workspace_size query;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), makes
+ *    no hidden synchronisation, and is re-entrant;
+ *  - return value: 0 = GNN_OK, otherwise a gnn_status; never throws, never aborts.
+ *    gnn_last_error_string() returns a thread-local description of the last failure;
+ *  - deterministic: no floating-point atomics anywhere; the same inputs give the
+ *    same bits on every run.
+ *  - index types: rowptr int64, col int32 (SURVEY.md §7 "Index width").
+ */
+#ifndef GNN_B200_H
+#define GNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gnn_stream_t; /* cudaStream_t */
+
+typedef enum {
+  GNN_OK = 0,
+  GNN_ERR_BAD_ARG = 1,
+  GNN_ERR_MISALIGNED = 2,
+  GNN_ERR_UNSUPPORTED = 3,
+  GNN_ERR_CUDA = 4,
+  GNN_ERR_WORKSPACE = 5
+} gnn_status;
+
+/* reduce op of the fixed-fanout gather (GraphSAGE_Pytorch/models/Aggregator.py:19-24) */
+typedef enum { GNN_REDUCE_MEAN = 0, GNN_REDUCE_SUM = 1, GNN_REDUCE_MAX = 2 } gnn_reduce;
+
+/* edge-score mode of the fused attention kernel */
+typedef enum {
+  GNN_GAT_SOFTMAX = 0, /* GAT/models/layers.py:26-32: softmax_j(LeakyReLU(s_i+t_j)) */
+  GNN_GAT_EXPNEG = 1   /* GAT/models/layers.py:108-122: exp(-LeakyReLU(.)) / rowsum  */
+} gnn_gat_mode;
+
+/* ---- library ---------------------------------------------------------- */
+int gnn_version(void);
+const char* gnn_last_error_string(void);
+const char* gnn_status_string(int status);
+/* number of kernels this library has launched in the calling process (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t gnn_launch_count(void);
+/* tuning knobs for measurement sweeps ("sage.smem_kb", "sage.chunk_rows",
+ * "sage.force_ldg", "spmm.long_row", ...).  Returns GNN_ERR_BAD_ARG for unknown keys. */
+int gnn_set_tuning(const char* key, int value);
+int gnn_get_tuning(const char* key, int* value);
+
+/* ---- graph construction (bit-exact index work) -------------------------- */
+
+/* COO (as produced by GCN/data_utils.py:63-70 sparse_mx_to_torch_sparse_tensor:
+ * int64 indices [2,nnz] row-major sorted, fp32 values) -> CSR.  The sort is stable
+ * in (row), so the within-row order of the input is preserved; for the reference's
+ * already row-major-sorted COO the result is the identity permutation.
+ * perm_out (nullable, int64[nnz]) receives the input position of every output slot. */
+size_t gnn_build_csr_from_coo_workspace_size(int64_t nnz, int64_t n_rows);
+int gnn_build_csr_from_coo(const int64_t* coo_row, const int64_t* coo_col, const float* coo_val /*nullable*/,
+                           int64_t nnz, int64_t n_rows, int64_t n_cols,
+                           int64_t* rowptr /*[n_rows+1]*/, int32_t* col /*[nnz]*/, float* val /*nullable [nnz]*/,
+                           int64_t* perm_out /*nullable [nnz]*/,
+                           void* workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* Dense mask (GAT/models/layers.py:29 / HAN/models/NodeAttention.py:28: `adj > 0`)
+ * -> CSR pattern, columns ascending, i.e. the order of `adj.nonzero()`
+ * (GAT/models/layers.py:98).  Two steps because nnz is only known after the count.
+ * adj_dtype: 0 = fp32 (GAT/data_utils.py:85), 1 = fp64 (HAN/utils/data_utils.py:85-89). */
+size_t gnn_dense_mask_count_workspace_size(int64_t n_rows);
+int gnn_dense_mask_count(const void* adj, int adj_dtype, int64_t n_rows, int64_t n_cols, int64_t ld,
+                         int64_t* rowptr /*[n_rows+1], out*/,
+                         void* workspace, size_t workspace_bytes, gnn_stream_t stream);
+int gnn_dense_mask_fill(const void* adj, int adj_dtype, int64_t n_rows, int64_t n_cols, int64_t ld,
+                        const int64_t* rowptr, int32_t* col /*[nnz]*/, gnn_stream_t stream);
+
+/* CSR -> CSR of the transpose (the structure the deterministic backward walks:
+ * autograd of GCN/GCN.py:43 is Âᵀ·dY; GAT/models/layers.py:63 is aᵀ·dY).
+ * Stable in the original row order, so each transposed row lists its sources in
+ * ascending original-row order.  perm_t (nullable) = original edge slot per new slot. */
+size_t gnn_csr_transpose_workspace_size(int64_t nnz, int64_t n_rows, int64_t n_cols);
+int gnn_csr_transpose(const int64_t* rowptr, const int32_t* col, const float* val /*nullable*/,
+                      int64_t n_rows, int64_t n_cols, int64_t nnz,
+                      int64_t* rowptr_t /*[n_cols+1]*/, int32_t* col_t /*[nnz]*/, float* val_t /*nullable*/,
+                      int64_t* perm_t /*nullable [nnz]*/,
+                      void* workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* Fixed-fanout index block idx[n_src*fanout] (GraphSAGE_Pytorch/sample_utils.py:16
+ * src-major layout; GraphSAGE/data_utils.py:105-116 [n,k] map) -> per-table-row list
+ * of the flat positions that reference it (ascending): the transposed structure the
+ * deterministic gather backward walks.  idx_bits is 32 or 64; negative ids are skipped. */
+size_t gnn_index_block_transpose_workspace_size(int64_t n_idx, int64_t n_table_rows);
+int gnn_index_block_transpose(const void* idx, int idx_bits, int64_t n_idx, int64_t n_table_rows,
+                              int64_t* rowptr_t /*[n_table_rows+1]*/, int32_t* pos_t /*[n_idx]*/,
+                              void* workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---- GCN: Y = Â·X (replaces torch.spmm, GCN/GCN.py:43) ------------------------------ */
+/* Row-parallel CSR SpMM, sub-warp per row chosen from F, 128-bit feature loads,
+ * sequential in-order accumulation per row (deterministic).  val == NULL => pattern
+ * only (all ones).  X [n_cols, ldx], Y [n_rows, ldy], F <= ldx, ldy.
+ * The bf16 variant reads/writes bf16 and accumulates in fp32.
+ * Backward (dX = Âᵀ·dY) is the same call on the gnn_csr_transpose output. */
+size_t gnn_spmm_csr_workspace_size(int64_t n_rows, int64_t nnz, int32_t F);
+int gnn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                     const float* X, float* Y, int64_t n_rows, int64_t n_cols, int32_t F,
+                     int64_t ldx, int64_t ldy, gnn_stream_t stream);
+int gnn_spmm_csr_bf16(const int64_t* rowptr, const int32_t* col, const float* val,
+                      const void* X, void* Y, int64_t n_rows, int64_t n_cols, int32_t F,
+                      int64_t ldx, int64_t ldy, gnn_stream_t stream);
+/* Same, with the rows whose nnz exceeds the "spmm.long_row" knob split over whole
+ * CTAs: long_rows[n_long] (ascending row ids, int64) come from the caller's plan;
+ * workspace holds the per-chunk partial sums (gnn_spmm_csr_workspace_size). */
+int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                             const float* X, float* Y, int64_t n_rows, int64_t n_cols, int32_t F,
+                             int64_t ldx, int64_t ldy,
+                             const int64_t* long_rows, int64_t n_long,
+                             void* workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---- GraphSAGE: fused gather + reduce over fixed-fanout index blocks ----------- */
+/* out[i,:] = reduce_k table[idx[i*fanout+k], :]
+ * (replaces the CPU gather GraphSAGE_Pytorch/data_utils.py:64 + .mean/.sum/.max(dim=1)
+ *  Aggregator.py:19-24; GraphSAGE/graph_utils.py:6 + torch.embedding GraphSAGE.py:47-49).
+ * idx == NULL => identity block: neighbours of source i are table rows
+ * [i*fanout,(i+1)*fanout) — the pre-gathered [n_src,fanout,F] tensor of Aggregator.py:18.
+ * idx_bits 32|64.  Negative ids contribute nothing (mean still divides by fanout).
+ * argmax (nullable, int32 [n_src, ld_out], max mode only) records the winning k.
+ * When the table rows are 16-byte aligned (ld_table*sizeof(T) % 16 == 0) the rows are
+ * fetched with TMA bulk copies into a shared-memory ring; otherwise with vector loads. */
+int gnn_gather_reduce_f32(const float* table, int64_t ld_table, int64_t n_table_rows,
+                          const void* idx, int idx_bits, int64_t n_src, int32_t fanout, int32_t F,
+                          int reduce, float* out, int64_t ld_out, int32_t* argmax, gnn_stream_t stream);
+int gnn_gather_reduce_bf16(const void* table, int64_t ld_table, int64_t n_table_rows,
+                           const void* idx, int idx_bits, int64_t n_src, int32_t fanout, int32_t F,
+                           int reduce, void* out, int64_t ld_out, int32_t* argmax, gnn_stream_t stream);
+/* Backward of mean/sum into the table: dTable[r,:] = scale * sum_{p: idx[p]==r} dOut[p/fanout,:]
+ * walking the gnn_index_block_transpose structure (ordered, no atomics). */
+int gnn_gather_reduce_bwd_f32(const int64_t* rowptr_t, const int32_t* pos_t, int64_t n_table_rows,
+                              int32_t fanout, float scale, const float* d_out, int64_t ld_dout,
+                              float* d_table, int64_t ld_dtable, int32_t F, gnn_stream_t stream);
+/* Backward of the identity block (pre-gathered input): dNeigh[i,k,:] = scale*dOut[i,:],
+ * or for max: dNeigh[i,argmax,:] = dOut[i,:], 0 elsewhere. */
+int gnn_gather_reduce_bwd_dense_f32(const float* d_out, int64_t ld_dout, const int32_t* argmax /*nullable*/,
+                                    int64_t n_src, int32_t fanout, int32_t F, float scale,
+                                    float* d_neigh /*[n_src,fanout,F] contiguous*/, gnn_stream_t stream);
+
+/* ---- GAT / HAN: fused multi-head attention aggregation ---------------------------- */
+/* Per-node, per-head halves of the edge score (GAT/models/layers.py:25-26 decomposes
+ * exactly: a·[Wh_i || Wh_j] = a[:F']·Wh_i + a[F':]·Wh_j):
+ *   s[i,h] = sum_f Wh[i,h*Fp+f]*a_src[h,f],  t[i,h] = sum_f Wh[i,h*Fp+f]*a_dst[h,f]. */
+int gnn_gat_scores_f32(const float* Wh, int64_t ldw, const float* a_src, const float* a_dst,
+                       int64_t n, int32_t H, int32_t Fp, float* s, float* t, gnn_stream_t stream);
+/* out[i, h*Fp+f] = act( sum_j att[i,j,h] * Wh[j, h*Fp+f] ), j over CSR row i, with
+ *   mode SOFTMAX: att = softmax_j(LeakyReLU_alpha(s[i,h]+t[j,h]))   (layers.py:26-32)
+ *   mode EXPNEG : att = exp(-LeakyReLU_alpha(.)) / sum_j exp(-LeakyReLU_alpha(.)) (layers.py:108-122)
+ * apply_elu: 0 none, 1 ELU (layers.py:35), 2 ELU twice (HAN/models/NodeAttention.py:35 then :62).
+ * Rows with no edge reproduce the reference's softmax over an all -9e15 row: the
+ * uniform mean over ALL nodes, passed in as col_mean[H*Fp] (nullable if no such row).
+ * edge_keep (nullable, fp32 [nnz,H]): post-softmax dropout factor per edge and head
+ * (0 or 1/(1-p)), layers.py:31.  row_max/row_sum [n,H] are saved for the backward. */
+int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw,
+                          const float* s, const float* t, int64_t n, int32_t H, int32_t Fp,
+                          float alpha, int mode, int apply_elu, const float* col_mean,
+                          const float* edge_keep, float* out, int64_t ldo,
+                          float* row_max, float* row_sum, gnn_stream_t stream);
+/* Backward.  d_out is the gradient w.r.t. the PRE-activation aggregate (the wrapper
+ * applies the ELU derivative); out_pre is that aggregate.  Produces
+ *   d_s [n,H]   (row-parallel over the CSR),
+ *   d_Wh [n,H*Fp] and d_t [n,H] (row-parallel over the transposed CSR: rowptr_t/col_t,
+ *   with perm_t mapping transposed slots to the forward edge slots of edge_scratch).
+ * Both passes are ordered reductions — the edge-gradient SDDMM (layers.py:59-61) and the
+ * transpose SpMM (layers.py:63) without the dense N×N intermediate and without atomics. */
+int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
+                          const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t,
+                          const float* Wh, int64_t ldw, const float* s, const float* t,
+                          const float* row_max, const float* row_sum,
+                          const float* out_pre, const float* d_out, int64_t ldo,
+                          int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
+                          const float* edge_keep,
+                          float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot /*[n,H] scratch*/,
+                          float* edge_scratch /*[2,nnz,H]: per-edge attention weight and dz*/, int64_t nnz,
+                          gnn_stream_t stream);
+
+/* ---- synthetic graphs for the benchmark shapes ---------------- */
+/* Power-law CSR generated on the device, row by row, from a counter-based hash of
+ * (seed,row,k): degrees ~ truncated Pareto with the given mean, targets skewed to
+ * low ids (hubs), columns ascending within a row, one self-loop per row, values
+ * d_i^-1/2 d_j^-1/2 as GCN/data_utils.py:54-60 computes them.  Two steps. */
+int gnn_synth_powerlaw_degrees(int64_t n_rows, int64_t row_offset, double mean_degree, double exponent,
+                               int64_t max_degree, uint64_t seed, int64_t* deg /*[n_rows]*/, gnn_stream_t stream);
+int gnn_synth_powerlaw_fill(int64_t n_rows, int64_t row_offset, int64_t n_cols, const int64_t* rowptr,
+                            double skew, uint64_t seed, int32_t* col, gnn_stream_t stream);
+int gnn_synth_gcn_values(int64_t n_rows, int64_t row_offset, const int64_t* rowptr, const int32_t* col,
+                         const int64_t* deg_all /*[n_cols] global degrees*/, float* val, gnn_stream_t stream);
+
+/* ---- multi-GPU halo exchange over NVLink peer memory ------------ */
+/* Peer buffers are plain cudaMalloc allocations exported with CUDA IPC, one process per
+ * GPU.  gnn_halo_push copies, for every peer q, the rows send_rows[send_off[q]..send_off[q+1])
+ * of the local X straight into peer q's halo buffer at row dst_off[q] with 128-bit
+ * stores over NVLink — pack and transfer in one kernel, no staging buffer. */
+int gnn_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64B_host);
+int gnn_peer_open(const void* ipc_handle_64B_host, void** dev_ptr);
+int gnn_peer_close(void* dev_ptr);
+int gnn_peer_free(void* dev_ptr);
+int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F,
+                      const int32_t* send_rows, const int64_t* send_off_host /*[n_peers+1]*/,
+                      float* const* peer_halo_host /*[n_peers] device ptrs*/, const int64_t* dst_off_host /*[n_peers]*/,
+                      int64_t ld_halo, int32_t n_peers, gnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNN_B200_H */

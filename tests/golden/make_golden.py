@@ -1,0 +1,196 @@
+"""Generate the golden fixtures in tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+    python tests/golden/make_golden.py
+The reference modules are imported through oracle/ref_loader.py and driven with seeded
+synthetic inputs; inputs that are cheap to regenerate are stored as seeds + a checksum,
+everything else (weights, index blocks, outputs, gradients) is stored verbatim.  The
+fixtures travel to the GPU box, where the reference does not exist.
+"""
+import hashlib
+import os
+import random
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader as R  # noqa: E402
+from graphneuralnetwork_b200 import synthetic as S  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def params_np(model):
+    return {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def grads_np(model):
+    return {"grad." + k: p.grad.detach().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(arrays)} arrays")
+
+
+def make_gcn():
+    gcn_mod, du = R.gcn()
+    n = S.CORA["n"]
+    edges = S.cora_like_edges(seed=0)
+    # the reference's own pipeline: preprocess_data:35, load_cora:78, sparse_mx_to_torch_sparse_tensor:63-70
+    adj = sp.coo_matrix((np.ones(edges.shape[0]), (edges[:, 0], edges[:, 1])), shape=(n, n), dtype=np.float32)
+    adj = adj + adj.T.multiply(adj.T > adj) - adj.multiply(adj.T > adj)
+    adj_n = du.normalize_adj(adj + sp.eye(adj.shape[0]))
+    adj_t = du.sparse_mx_to_torch_sparse_tensor(adj_n)
+    idx = adj_t._indices().numpy()
+    val = adj_t._values().numpy()
+    X = S.row_normalised_features(n, S.CORA["feats"], seed=1)
+    labels = np.random.default_rng(2).integers(0, S.CORA["classes"], size=n)
+    torch.manual_seed(0)
+    model = gcn_mod.GCN_Model(S.CORA["feats"], S.CORA["hidden"], S.CORA["classes"], 2, 0.5)
+    model.eval()
+    Xt = torch.from_numpy(X)
+    out = model(Xt, adj_t)
+    idx_train = torch.arange(140)
+    loss = torch.nn.functional.cross_entropy(out[idx_train], torch.from_numpy(labels)[idx_train])
+    loss.backward()
+    # one isolated layer, for the spmm check alone
+    layer_out = model.gcn_blocks.gcn0(Xt, adj_t).detach().numpy()
+    save("gcn_cora.npz", edges=edges, coo_row=idx[0].astype(np.int32), coo_col=idx[1].astype(np.int32), coo_val=val,
+         x_seed=np.int64(1), x_sha=np.array(sha(X)), labels=labels.astype(np.int64), out=out.detach().numpy(),
+         layer0_out=layer_out, loss=np.float64(loss.item()), **params_np(model), **grads_np(model))
+
+
+def _gat_adj(n, pairs, seed):
+    """GAT/data_utils.py:73-85: same normalisation as GCN, kept dense fp32."""
+    _, du = R.gcn()
+    edges = S.cora_like_edges(n=n, pairs=pairs, seed=seed)
+    adj = sp.coo_matrix((np.ones(edges.shape[0]), (edges[:, 0], edges[:, 1])), shape=(n, n), dtype=np.float32)
+    adj = adj + adj.T.multiply(adj.T > adj) - adj.multiply(adj.T > adj)
+    adj = du.normalize_adj(adj + sp.eye(n))
+    return edges, np.asarray(adj.todense(), dtype=np.float32)
+
+
+def make_gat_small():
+    gat_mod, _ = R.gat_models()
+    n, nfeat, nhid, nheads, nclass = 300, 50, 8, 8, 7
+    edges, adj = _gat_adj(n, 700, seed=3)
+    adj[17, :] = 0  # one isolated row: the reference soft-maxes it to the uniform mean (layers.py:28-30)
+    X = S.row_normalised_features(n, nfeat, seed=4)
+    labels = np.random.default_rng(5).integers(0, nclass, size=n)
+    out = {}
+    for kind, cls in (("dense", gat_mod.GAT), ("sparse", gat_mod.SpGAT)):
+        torch.manual_seed(1)
+        model = cls(nfeat, nhid, nclass, 0.0, 0.2, nheads)  # dropout 0: train == eval, grads comparable
+        model.train()
+        a = torch.from_numpy(adj if kind == "dense" else np.where(np.arange(n)[:, None] == 17, np.eye(n, dtype=np.float32)[17], adj))
+        o = model(torch.from_numpy(X), a)
+        loss = torch.nn.functional.cross_entropy(o, torch.from_numpy(labels))
+        loss.backward()
+        out.update({f"{kind}.out": o.detach().numpy(), f"{kind}.loss": np.float64(loss.item())})
+        out.update({f"{kind}.{k}": v for k, v in params_np(model).items()})
+        out.update({f"{kind}.{k}": v for k, v in grads_np(model).items()})
+    save("gat_small.npz", edges=edges, adj=adj, X=X, labels=labels.astype(np.int64), isolated_row=np.int64(17), **out)
+
+
+def make_gat_cora():
+    gat_mod, _ = R.gat_models()
+    n = S.CORA["n"]
+    edges, adj = _gat_adj(n, S.CORA["undirected_pairs"], seed=0)
+    X = S.row_normalised_features(n, S.CORA["feats"], seed=1)
+    torch.manual_seed(2)
+    model = gat_mod.GAT(S.CORA["feats"], 8, S.CORA["classes"], 0.6, 0.2, 8)
+    model.eval()
+    with torch.no_grad():
+        out = model(torch.from_numpy(X), torch.from_numpy(adj))
+    save("gat_cora.npz", edges=edges, adj_sha=np.array(sha(adj)), x_seed=np.int64(1), x_sha=np.array(sha(X)),
+         out=out.numpy(), **params_np(model))
+
+
+def make_sage():
+    ref = R.sage_pytorch()
+    n, feat, hidden, fan, B = 500, 602, [128, 41], [5, 3], 32
+    adj_lists = S.adjacency_lists(n, 8, seed=6)
+    table = np.random.default_rng(7).standard_normal((n, feat), dtype=np.float32)
+    random.seed(0)
+    src = list(range(40, 40 + B))
+    blocks = ref["sample_utils"].multihop_sampling(src, fan, adj_lists)
+    feats = [torch.from_numpy(table[np.asarray(b, dtype=np.int64)]) for b in blocks]
+    labels = np.random.default_rng(8).integers(0, hidden[-1], size=B)
+    torch.manual_seed(3)
+    model = ref["GraphSage"].GraphSage(feat, hidden, fan)
+    model.train()
+    out = model(feats)
+    loss = torch.nn.functional.cross_entropy(out, torch.from_numpy(labels))
+    loss.backward()
+    extra = {}
+    for method in ("mean", "sum"):
+        agg = ref["Aggregator"].NeighborAggregator(feat, 16, aggr_method=method)
+        with torch.no_grad():
+            agg.weight.copy_(torch.eye(feat)[:, :16])
+            neigh = feats[1].view(B, fan[0], -1)
+            extra[f"agg.{method}"] = agg(neigh).numpy()  # == reduce(neigh)[:, :16]
+    adj_flat = np.concatenate([np.asarray(sorted(adj_lists[i]), dtype=np.int32) for i in range(n)])
+    adj_ptr = np.cumsum([0] + [len(adj_lists[i]) for i in range(n)]).astype(np.int64)
+    save("sage_small.npz", table_seed=np.int64(7), table_sha=np.array(sha(table)), adj_ptr=adj_ptr, adj_flat=adj_flat,
+         block0=np.asarray(blocks[0], np.int64), block1=np.asarray(blocks[1], np.int64),
+         block2=np.asarray(blocks[2], np.int64), labels=labels.astype(np.int64), out=out.detach().numpy(),
+         loss=np.float64(loss.item()), **params_np(model), **grads_np(model), **extra)
+
+
+def make_sage_v2():
+    ref = R.sage_v2()
+    n, feat, out_size, B, k, L = 300, 64, 32, 8, 4, 2
+    adj_lists = S.adjacency_lists(n, 6, seed=9)
+    table = np.random.default_rng(10).standard_normal((n, feat), dtype=np.float32)
+    random.seed(1)
+    collate = ref["data_utils"].collate_fn(adj_lists, table.tolist(), L, k, False, False)
+    data = [(i, int(i % 3)) for i in range(20, 20 + B)]
+    (center_feats, center_map, neigh_feats, neigh_map), labels = collate(data)
+    torch.manual_seed(4)
+    model = ref["GraphSAGE"].GraphSAGE(L, feat, out_size, gcn=False, agg_func='MEAN', Unsupervised=False, class_size=3)
+    model.train()
+    feats_out, classes = model(center_feats, center_map, neigh_feats, neigh_map, None, None, None, None, None)
+    loss = torch.nn.functional.cross_entropy(classes, labels)
+    loss.backward()
+    save("sage_v2_small.npz", center_feats=center_feats.numpy(), center_map=center_map.numpy(),
+         neigh_feats=neigh_feats.numpy(), neigh_map=neigh_map.numpy(), labels=labels.numpy(),
+         feats_out=feats_out.detach().numpy(), classes=classes.detach().numpy(), loss=np.float64(loss.item()),
+         **params_np(model), **grads_np(model))
+
+
+def make_han():
+    ref = R.han()
+    n, fin, M, heads, hid, ncls = 150, 40, 3, [8], 8, 3
+    gs = [S.symmetric_mask(n, t, seed=11 + i) for i, t in enumerate((400, 6000, 1500))]
+    X = np.random.default_rng(14).standard_normal((n, fin), dtype=np.float32)
+    labels = np.random.default_rng(15).integers(0, ncls, size=n)
+    torch.manual_seed(5)
+    model = ref["HAN"].HANModel(M, fin, hid, ncls, heads, 0.0)
+    model.train()
+    out = model([torch.from_numpy(g) for g in gs], torch.from_numpy(X))
+    loss = torch.nn.functional.cross_entropy(out, torch.from_numpy(labels))
+    loss.backward()
+    packed = np.stack([np.packbits(g.astype(np.uint8), axis=1) for g in gs])
+    save("han_small.npz", masks_packed=packed, n=np.int64(n), X=X, labels=labels.astype(np.int64),
+         out=out.detach().numpy(), loss=np.float64(loss.item()), **params_np(model), **grads_np(model))
+
+
+if __name__ == "__main__":
+    assert R.available(), "reference not found"
+    torch.set_num_threads(8)
+    make_gcn()
+    make_gat_small()
+    make_gat_cora()
+    make_sage()
+    make_sage_v2()
+    make_han()
