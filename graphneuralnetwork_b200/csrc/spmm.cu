@@ -13,7 +13,8 @@ int spmm_impl(const int64_t* rowptr, const int32_t* col, const float* val, const
               cudaStream_t st) {
   GNN_REQUIRE(n_rows >= 0 && n_cols >= 0 && F >= 0, GNN_ERR_BAD_ARG, "negative size");
   if (n_rows == 0 || F == 0) return GNN_OK;
-  GNN_REQUIRE(rowptr && col && X && Y, GNN_ERR_BAD_ARG, "null pointer (rowptr/col/X/Y)");
+  // col may be null only for a graph without edges (nnz lives on the device; rowptr decides)
+  GNN_REQUIRE(rowptr && X && Y, GNN_ERR_BAD_ARG, "null pointer (rowptr/X/Y)");
   GNN_REQUIRE(ldx >= F && ldy >= F, GNN_ERR_BAD_ARG, "leading dimension smaller than F (ldx=%lld ldy=%lld F=%d)",
               (long long)ldx, (long long)ldy, F);
   GNN_REQUIRE(n_cols < 0x7fffffffLL, GNN_ERR_UNSUPPORTED, "n_cols does not fit int32 column ids");
