@@ -34,10 +34,10 @@ int num_sms() {
 static std::mutex g_tune_mu;
 static std::map<std::string, int>& tune_map() {
   static std::map<std::string, int> m = {
-      {"sage.smem_kb", 72},      // shared-memory ring per CTA of the TMA gather (3 CTAs/SM)
+      {"sage.smem_kb", 48},      // shared-memory ring per CTA of the TMA gather (4 CTAs/SM)
       {"sage.chunk_bytes", 12288},  // bytes per ring stage
       {"sage.force_ldg", 0},     // 1: never take the TMA path
-      {"sage.ctas_per_sm", 3},
+      {"sage.ctas_per_sm", 4},
       {"spmm.long_row", 2048},   // rows above this nnz go to the CTA-per-chunk path (planned call)
       {"spmm.chunk", 8192},      // edges per long-row chunk
       {"spmm.unroll", 0},        // 0 = heuristic

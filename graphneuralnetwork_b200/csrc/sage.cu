@@ -270,7 +270,7 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, const v
     kc = kc > fanout ? fanout : kc;
     const int nchunk = (fanout + kc - 1) / kc;
     kc = (fanout + nchunk - 1) / nchunk;  // balance the chunks of one source
-    const size_t budget = (size_t)tuning("sage.smem_kb", 72) * 1024;
+    const size_t budget = (size_t)tuning("sage.smem_kb", 48) * 1024;
     int stages = (int)(budget / ((size_t)kc * row_bytes));
     while (stages < 2 && kc > 1) {
       kc = (kc + 1) / 2;
@@ -281,7 +281,7 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, const v
     a.kc = kc;
     a.stages = stages;
     const size_t smem_bytes = (size_t)stages * kc * row_bytes + (size_t)stages * (16 + 4) + 16;
-    int64_t grid = (int64_t)num_sms() * tuning("sage.ctas_per_sm", 3);
+    int64_t grid = (int64_t)num_sms() * tuning("sage.ctas_per_sm", 4);
     grid = grid > n_src ? n_src : grid;
     switch (reduce) {
       case GNN_REDUCE_MAX: return launch_tma<T, GNN_REDUCE_MAX>(a, smem_bytes, (int)grid, st);

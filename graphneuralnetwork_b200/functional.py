@@ -50,20 +50,20 @@ def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, p
     if out is None:
         out = torch.empty((g.n_rows, F), dtype=X.dtype, device=X.device)
     st = _stream_ptr()
-    if X.dtype == torch.float32:
-        lr = g.long_rows() if planned else None
-        if lr is not None and lr.numel() > 0:
-            _lib.check(lib.gnn_spmm_csr_planned_f32(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows,
-                                                    g.n_cols, F, _ld(X), _ld(out), _p(lr), lr.numel(), None, 0, st),
-                       "gnn_spmm_csr_planned_f32")
-        else:
-            _lib.check(lib.gnn_spmm_csr_f32(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F,
-                                            _ld(X), _ld(out), st), "gnn_spmm_csr_f32")
-    elif X.dtype == torch.bfloat16:
-        _lib.check(lib.gnn_spmm_csr_bf16(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F,
-                                         _ld(X), _ld(out), st), "gnn_spmm_csr_bf16")
-    else:
+    if X.dtype not in (torch.float32, torch.bfloat16):
         raise _lib.GnnError(f"spmm: unsupported dtype {X.dtype} (fp32 and bf16 only)")
+    f32 = X.dtype == torch.float32
+    plan = g.long_row_plan() if planned else None
+    if plan is not None:
+        lr, thr, chunk_off, n_chunks, chunk, ws = plan
+        fn = lib.gnn_spmm_csr_planned_f32 if f32 else lib.gnn_spmm_csr_planned_bf16
+        _lib.check(fn(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F, _ld(X), _ld(out),
+                      _p(lr), lr.numel(), thr, _p(chunk_off), n_chunks, chunk, _p(ws), ws.numel(), st),
+                   "gnn_spmm_csr_planned")
+    else:
+        fn = lib.gnn_spmm_csr_f32 if f32 else lib.gnn_spmm_csr_bf16
+        _lib.check(fn(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F, _ld(X), _ld(out), st),
+                   "gnn_spmm_csr")
     return out
 
 

@@ -46,6 +46,7 @@ class CSRGraph:
         self._t: Optional["CSRGraph"] = None
         self._perm_t: Optional[torch.Tensor] = None
         self._long_rows: Optional[torch.Tensor] = None
+        self._plan = None
         self._zero_rows: Optional[bool] = None
 
     @property
@@ -84,6 +85,28 @@ class CSRGraph:
             deg = self.rowptr[1:] - self.rowptr[:-1]
             self._long_rows = torch.nonzero(deg > thr).flatten().contiguous()
         return self._long_rows
+
+    def long_row_plan(self):
+        """Host-side plan for power-law graphs, computed once per graph: rows longer than the
+        `spmm.long_row` knob are cut into chunks of `spmm.chunk` edges.  Returns
+        (long_rows int64[n_long], threshold, chunk_off int64[n_long+1], n_chunks, chunk_edges,
+        workspace uint8 tensor) or None when no row is long."""
+        if self._plan is None:
+            thr = _lib.get_tuning("spmm.long_row")
+            chunk = _lib.get_tuning("spmm.chunk")
+            lr = self.long_rows()
+            if lr.numel() == 0:
+                self._plan = False
+            else:
+                deg = self.rowptr[lr + 1] - self.rowptr[lr]
+                counts = (deg + chunk - 1) // chunk
+                chunk_off = torch.zeros(lr.numel() + 1, dtype=torch.int64, device=self.device)
+                torch.cumsum(counts, 0, out=chunk_off[1:])
+                n_chunks = int(chunk_off[-1].item())
+                ws_bytes = _lib.load().gnn_spmm_csr_workspace_size(n_chunks, 2)  # bf16 tiles are the wider
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+                self._plan = (lr, thr, chunk_off, n_chunks, chunk, ws)
+        return self._plan or None
 
     def has_empty_rows(self) -> bool:
         if self._zero_rows is None:

@@ -113,21 +113,32 @@ int gnn_index_block_transpose(const void* idx, int idx_bits, int64_t n_idx, int6
  * only (all ones).  X [n_cols, ldx], Y [n_rows, ldy], F <= ldx, ldy.
  * The bf16 variant reads/writes bf16 and accumulates in fp32.
  * Backward (dX = Âᵀ·dY) is the same call on the gnn_csr_transpose output. */
-size_t gnn_spmm_csr_workspace_size(int64_t n_rows, int64_t nnz, int32_t F);
 int gnn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val,
                      const float* X, float* Y, int64_t n_rows, int64_t n_cols, int32_t F,
                      int64_t ldx, int64_t ldy, gnn_stream_t stream);
 int gnn_spmm_csr_bf16(const int64_t* rowptr, const int32_t* col, const float* val,
                       const void* X, void* Y, int64_t n_rows, int64_t n_cols, int32_t F,
                       int64_t ldx, int64_t ldy, gnn_stream_t stream);
-/* Same, with the rows whose nnz exceeds the "spmm.long_row" knob split over whole
- * CTAs: long_rows[n_long] (ascending row ids, int64) come from the caller's plan;
- * workspace holds the per-chunk partial sums (gnn_spmm_csr_workspace_size). */
+/* Same, with a plan for power-law graphs: the rows whose nnz exceeds the caller's threshold
+ * (long_rows[n_long], ascending row ids) are cut into chunks of chunk_edges edges, one CTA
+ * per chunk; chunk_off[n_long+1] is the exclusive prefix sum of ceil(nnz_row/chunk_edges)
+ * and n_chunks its last entry.  Per-chunk partial sums live in the workspace
+ * (gnn_spmm_csr_workspace_size) and are added per row in chunk order: deterministic.
+ * All other rows take the row-block streaming kernel.  The plan is host logic computed once
+ * per graph (graphneuralnetwork_b200/graph.py CSRGraph.long_row_plan). */
+size_t gnn_spmm_csr_workspace_size(int64_t n_chunks, int32_t elem_size);
 int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const float* val,
                              const float* X, float* Y, int64_t n_rows, int64_t n_cols, int32_t F,
                              int64_t ldx, int64_t ldy,
-                             const int64_t* long_rows, int64_t n_long,
+                             const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
+                             const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
                              void* workspace, size_t workspace_bytes, gnn_stream_t stream);
+int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const float* val,
+                              const void* X, void* Y, int64_t n_rows, int64_t n_cols, int32_t F,
+                              int64_t ldx, int64_t ldy,
+                              const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
+                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
+                              void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 
 /* ---- GraphSAGE: fused gather + reduce over fixed-fanout index blocks ----------- */
 /* out[i,:] = reduce_k table[idx[i*fanout+k], :]

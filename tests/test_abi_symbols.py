@@ -42,7 +42,7 @@ def test_version_and_error_strings(lib):
 def test_tuning_knobs(lib):
     _lib.set_tuning("sage.smem_kb", 64)
     assert _lib.get_tuning("sage.smem_kb") == 64
-    _lib.set_tuning("sage.smem_kb", 72)
+    _lib.set_tuning("sage.smem_kb", 48)
     try:
         _lib.set_tuning("no.such.key", 1)
     except _lib.GnnError as e:

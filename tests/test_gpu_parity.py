@@ -144,6 +144,29 @@ def test_spmm_f32_shapes(lib, F):
     assert rel_err(Fn.spmm_raw(csr1, cuda(X)).cpu().numpy(), ogcn.spmm_f64(rowptr, col, None, X)) < TOL32
 
 
+@pytest.mark.parametrize("F", [4, 16, 64, 602])
+def test_spmm_long_rows_chunked(lib, F):
+    """Hub rows are cut into 8192-edge chunks (one CTA each) and re-added in chunk order."""
+    n = 1500
+    rng = np.random.default_rng(F)
+    deg = rng.poisson(6, size=n)
+    deg[3], deg[700], deg[701], deg[1499] = 20000, 8192, 8193, 2049
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    col = rng.integers(0, n, size=rowptr[-1]).astype(np.int32)
+    val = rng.standard_normal(rowptr[-1]).astype(np.float32)
+    X = rng.standard_normal((n, F)).astype(np.float32)
+    csr = CSRGraph(cuda(rowptr), cuda(col), cuda(val), n, n)
+    lr, thr, chunk_off, n_chunks, chunk, _ = csr.long_row_plan()
+    assert lr.tolist() == [3, 700, 701, 1499] and chunk_off.tolist() == [0, 3, 4, 6, 7] and n_chunks == 7
+    ref = ogcn.spmm_f64(rowptr, col, val, X)
+    Y = Fn.spmm_raw(csr, cuda(X))
+    assert rel_err(Y.cpu().numpy(), ref) < TOL32
+    assert torch.equal(Fn.spmm_raw(csr, cuda(X)), Y)
+    Xb = cuda(X).to(torch.bfloat16)
+    Yb = Fn.spmm_raw(csr, Xb)
+    assert rel_err(Yb.float().cpu().numpy(), ogcn.spmm_f64(rowptr, col, val, Xb.float().cpu().numpy())) < TOLBF
+
+
 def test_spmm_strided_and_empty(lib):
     rowptr, col, val = random_csr(100, 100, 5, seed=9)
     csr = CSRGraph(cuda(rowptr), cuda(col), cuda(val), 100, 100)
