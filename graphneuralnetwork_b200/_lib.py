@@ -37,9 +37,9 @@ SIGNATURES = {
     "gnn_spmm_csr_f32": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr]),
     "gnn_spmm_csr_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr]),
     "gnn_spmm_csr_planned_f32": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr, i64, i64, ptr, i64, i32,
-                                        ptr, size_t, ptr]),
+                                        cint, ptr, size_t, ptr]),
     "gnn_spmm_csr_planned_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr, i64, i64, ptr, i64, i32,
-                                         ptr, size_t, ptr]),
+                                         cint, ptr, size_t, ptr]),
     "gnn_gather_reduce_f32": (cint, [ptr, i64, i64, ptr, cint, i64, i32, i32, cint, ptr, i64, ptr, ptr]),
     "gnn_gather_reduce_bf16": (cint, [ptr, i64, i64, ptr, cint, i64, i32, i32, cint, ptr, i64, ptr, ptr]),
     "gnn_gather_reduce_bwd_f32": (cint, [ptr, ptr, i64, i32, f32, ptr, i64, ptr, i64, i32, ptr]),
@@ -50,7 +50,7 @@ SIGNATURES = {
     "gnn_gat_fused_bwd_f32": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
                                      i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, ptr, i64, ptr]),
     "gnn_synth_powerlaw_degrees": (cint, [i64, i64, f64, f64, i64, u64, ptr, ptr]),
-    "gnn_synth_powerlaw_fill": (cint, [i64, i64, i64, ptr, f64, u64, ptr, ptr]),
+    "gnn_synth_powerlaw_fill": (cint, [i64, i64, i64, ptr, f64, f64, i64, u64, ptr, ptr]),
     "gnn_synth_gcn_values": (cint, [i64, i64, ptr, ptr, ptr, ptr, ptr]),
     "gnn_peer_alloc": (cint, [size_t, C.POINTER(ptr), ptr]),
     "gnn_peer_open": (cint, [ptr, C.POINTER(ptr)]),

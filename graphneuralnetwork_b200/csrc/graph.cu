@@ -157,7 +157,7 @@ __global__ void synth_degrees_kernel(int64_t n_rows, int64_t row_offset, double 
 // k of a row with d other edges is drawn from stratum [k/d,(k+1)/d) of [0,1) and mapped
 // through x -> n_cols * x^skew: ascending within the row and skewed to low ids (hubs).
 __global__ void synth_fill_kernel(int64_t n_rows, int64_t row_offset, int64_t n_cols, const int64_t* rowptr,
-                                  double skew, uint64_t seed, int32_t* col) {
+                                  double skew, double p_local, int64_t window, uint64_t seed, int32_t* col) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -168,9 +168,21 @@ __global__ void synth_fill_kernel(int64_t n_rows, int64_t row_offset, int64_t n_
     const uint64_t rs = mix64(seed ^ mix64((uint64_t)self * 0x100000001b3ULL + 7));
     if (lane == 0) col[s] = (int32_t)self;
     for (int64_t k = lane; k < d; k += 32) {
-      const double u = u01(mix64(rs + (uint64_t)k));
-      const double x = ((double)k + u) / (double)d;
-      int64_t c = (int64_t)((double)n_cols * pow(x, skew));
+      const uint64_t h = mix64(rs + (uint64_t)k);
+      const double u = u01(h);
+      int64_t c;
+      if (p_local > 0.0 && u01(mix64(h ^ 0xa5a5a5a5a5a5a5a5ULL)) < p_local) {
+        // community edge: within +-window of the row (a locality-preserving node ordering)
+        const double w = u01(mix64(h + 0x1234567ULL));
+        const int64_t off = 1 + (int64_t)((double)window * w * w);
+        c = (h & 1) ? self + off : self - off;
+        c = c < 0 ? -c : c;
+        c = c >= n_cols ? 2 * (n_cols - 1) - c : c;
+        c = c < 0 ? 0 : c;
+      } else {
+        const double x = ((double)k + u) / (double)d;
+        c = (int64_t)((double)n_cols * pow(x, skew));
+      }
       c = c >= n_cols ? n_cols - 1 : c;
       col[s + 1 + k] = (int32_t)c;
     }
@@ -391,12 +403,13 @@ int gnn_synth_powerlaw_degrees(int64_t n_rows, int64_t row_offset, double mean_d
 }
 
 int gnn_synth_powerlaw_fill(int64_t n_rows, int64_t row_offset, int64_t n_cols, const int64_t* rowptr, double skew,
-                            uint64_t seed, int32_t* col, gnn_stream_t stream) {
-  GNN_REQUIRE(n_rows >= 0 && n_cols > 0 && n_cols < 0x7fffffffLL && rowptr && col && skew >= 1.0, GNN_ERR_BAD_ARG,
-              "bad argument");
+                            double p_local, int64_t window, uint64_t seed, int32_t* col, gnn_stream_t stream) {
+  GNN_REQUIRE(n_rows >= 0 && n_cols > 0 && n_cols < 0x7fffffffLL && rowptr && col && skew >= 1.0 && p_local >= 0.0 &&
+                  p_local <= 1.0 && window >= 0,
+              GNN_ERR_BAD_ARG, "bad argument");
   if (n_rows == 0) return GNN_OK;
   synth_fill_kernel<<<grid_for(n_rows * 32), 256, 0, (cudaStream_t)stream>>>(n_rows, row_offset, n_cols, rowptr, skew,
-                                                                             seed, col);
+                                                                             p_local, window, seed, col);
   GNN_LAUNCH_CHECK();
   return GNN_OK;
 }

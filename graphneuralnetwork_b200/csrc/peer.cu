@@ -25,23 +25,40 @@ struct PushArgs {
   int32_t n_peers;
 };
 
-// one warp per sent row; VEC-wide copies
+// One warp per sent row, kPushUnroll rows in flight per warp (all loads issued before the
+// first store).  The grid is deliberately small (one CTA per SM): NVLink needs ~1.5 MB in
+// flight, and the remaining thread slots of every SM stay free for the local-column SpMM
+// that runs concurrently on the main stream.
+constexpr int kPushUnroll = 4;
 template <int VEC>
 __global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t total = a.send_off[a.n_peers];
-  for (int64_t k = w0; k < total; k += nw) {
-    int q = 0;
-    while (q + 1 < a.n_peers && k >= a.send_off[q + 1]) ++q;
-    const int64_t r = __ldg(a.send_rows + k);
-    const float* src = a.X + r * a.ldx;
-    float* dst = a.halo[q] + (a.dst_off[q] + (k - a.send_off[q])) * a.ld_halo;
+  for (int64_t k0 = w0 * kPushUnroll; k0 < total; k0 += nw * kPushUnroll) {
+    const float* src[kPushUnroll];
+    float* dst[kPushUnroll];
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) {
+      const int64_t k = k0 + u;
+      src[u] = nullptr;
+      dst[u] = nullptr;
+      if (k < total) {
+        int q = 0;
+        while (q + 1 < a.n_peers && k >= a.send_off[q + 1]) ++q;
+        src[u] = a.X + (int64_t)__ldg(a.send_rows + k) * a.ldx;
+        dst[u] = a.halo[q] + (a.dst_off[q] + (k - a.send_off[q])) * a.ld_halo;
+      }
+    }
     for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
-      float v[VEC];
-      VecIO<float, VEC>::load(src + c, v);
-      VecIO<float, VEC>::store(dst + c, v);
+      float v[kPushUnroll][VEC];
+#pragma unroll
+      for (int u = 0; u < kPushUnroll; ++u)
+        if (src[u]) VecIO<float, VEC>::load(src[u] + c, v[u]);
+#pragma unroll
+      for (int u = 0; u < kPushUnroll; ++u)
+        if (dst[u]) VecIO<float, VEC>::store(dst[u] + c, v[u]);
     }
   }
 }
@@ -113,7 +130,7 @@ int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* sen
   if (total == 0) return GNN_OK;
   GNN_REQUIRE(send_rows != nullptr, GNN_ERR_BAD_ARG, "null send_rows");
   int64_t grid = (total * 32 + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * tuning("halo.ctas_per_sm", 1);
   grid = grid > cap ? cap : grid;
   if (vec4) halo_push_kernel<4><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
   else halo_push_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);

@@ -29,6 +29,7 @@ struct SpmmArgs {
   int64_t n_rows;
   int32_t F;
   int64_t skip_deg_gt;  // >0: rows with more edges belong to the long-row kernels
+  int32_t accumulate;   // 1: Y += Â·X (second pass of the partitioned SpMM), 0: Y = Â·X
 };
 
 constexpr int kSpmmThreads = 256;
@@ -59,7 +60,15 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rbs_kernel(const SpmmArgs<T
 #pragma unroll
     for (int ch = 0; ch < CHUNKS; ++ch) {
       const int col0 = (gl + ch * GROUP) * VEC;
-      if (col0 < a.F) VecIO<T, VEC>::store(yr + col0, acc[ch]);
+      if (col0 < a.F) {
+        if (a.accumulate) {
+          float prev[VEC];
+          VecIO<T, VEC>::load(yr + col0, prev);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[ch][i] += prev[i];
+        }
+        VecIO<T, VEC>::store(yr + col0, acc[ch]);
+      }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
     }
@@ -278,13 +287,18 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     spmm_long_finalize_kernel(const int64_t* __restrict__ long_rows, const int64_t* __restrict__ chunk_off,
                               const float* __restrict__ partial, int ldp, int col_base, int Ftile, T* __restrict__ Y,
-                              int64_t ldy) {
+                              int64_t ldy, int accumulate) {
   const int64_t r = blockIdx.x;
   const int64_t row = __ldg(long_rows + r);
   const int64_t c0 = __ldg(chunk_off + r), c1 = __ldg(chunk_off + r + 1);
   for (int f = threadIdx.x; f < Ftile; f += blockDim.x) {
     float sum = 0.f;
     for (int64_t c = c0; c < c1; ++c) sum += __ldg(partial + c * ldp + f);
+    if (accumulate) {
+      float prev[1];
+      VecIO<T, 1>::load(Y + row * ldy + col_base + f, prev);
+      sum += prev[0];
+    }
     float o[1] = {sum};
     VecIO<T, 1>::store(Y + row * ldy + col_base + f, o);
   }
@@ -367,7 +381,7 @@ inline int spmm_long_vec(const SpmmArgs<T>& a0, const int64_t* long_rows, int64_
 #undef GNN_LONG
     GNN_LAUNCH_CHECK();
     spmm_long_finalize_kernel<T><<<(unsigned)n_long, 256, 0, st>>>(long_rows, chunk_off, partial, ldp, c0, a.F, a0.Y,
-                                                                   a0.ldy);
+                                                                   a0.ldy, a0.accumulate);
     GNN_LAUNCH_CHECK();
   }
   return GNN_OK;

@@ -39,8 +39,9 @@ def _padded_empty(rows: int, F: int, dtype, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # GCN: Y = Â·X
 # --------------------------------------------------------------------------------------
-def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, planned: bool = True) -> torch.Tensor:
-    """One gnn_spmm_csr_{f32,bf16} launch (no autograd)."""
+def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, planned: bool = True,
+             accumulate: bool = False) -> torch.Tensor:
+    """Y = Â·X (or Y += Â·X into `out`) through gnn_spmm_csr_* (no autograd)."""
     _require_cuda(X)
     lib = _lib.load()
     X = _rowmajor(X)
@@ -54,11 +55,12 @@ def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, p
         raise _lib.GnnError(f"spmm: unsupported dtype {X.dtype} (fp32 and bf16 only)")
     f32 = X.dtype == torch.float32
     plan = g.long_row_plan() if planned else None
-    if plan is not None:
-        lr, thr, chunk_off, n_chunks, chunk, ws = plan
+    if plan is not None or accumulate:
+        lr, thr, chunk_off, n_chunks, chunk, ws = plan if plan is not None else (None, 0, None, 0, 0, None)
         fn = lib.gnn_spmm_csr_planned_f32 if f32 else lib.gnn_spmm_csr_planned_bf16
         _lib.check(fn(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F, _ld(X), _ld(out),
-                      _p(lr), lr.numel(), thr, _p(chunk_off), n_chunks, chunk, _p(ws), ws.numel(), st),
+                      _p(lr), 0 if lr is None else lr.numel(), thr, _p(chunk_off), n_chunks, chunk,
+                      1 if accumulate else 0, _p(ws), 0 if ws is None else ws.numel(), st),
                    "gnn_spmm_csr_planned")
     else:
         fn = lib.gnn_spmm_csr_f32 if f32 else lib.gnn_spmm_csr_bf16

@@ -91,11 +91,14 @@ def uniform_blocks(n_nodes, batch, fanouts, seed=0, dtype=torch.int64, device="c
 
 def powerlaw_csr(n_rows: int, mean_degree: float, *, n_cols: int | None = None, row_offset: int = 0,
                  exponent: float = 2.5, skew: float = 3.0, max_degree: int = 1 << 20, seed: int = 0,
-                 device="cuda", with_values: bool = True, deg_all: torch.Tensor | None = None) -> CSRGraph:
+                 device="cuda", with_values: bool = True, deg_all: torch.Tensor | None = None,
+                 p_local: float = 0.0, window: int = 0) -> CSRGraph:
     """Power-law CSR generated on the device (gnn_synth_*): Pareto degrees with the requested
     mean, neighbour ids skewed to low ids (hubs), one self-loop per row, GCN-normalised
     values d_i^-1/2·d_j^-1/2 from the row degrees.  `row_offset`/`n_cols` generate one row
-    block of a larger graph (each rank of the partitioned run builds only its own rows)."""
+    block of a larger graph (each rank of the partitioned run builds only its own rows).
+    `p_local` > 0 draws that share of the edges within +-`window` of the row id instead — the
+    structure a locality-preserving (METIS-like) node ordering gives a 1-D partition."""
     lib = _lib.load()
     n_cols = n_rows if n_cols is None else n_cols
     dev = torch.device(device)
@@ -106,8 +109,8 @@ def powerlaw_csr(n_rows: int, mean_degree: float, *, n_cols: int | None = None, 
     torch.cumsum(deg, 0, out=rowptr[1:])
     nnz = int(rowptr[-1].item())
     col = torch.empty(nnz, dtype=torch.int32, device=dev)
-    _lib.check(lib.gnn_synth_powerlaw_fill(n_rows, row_offset, n_cols, _p(rowptr), float(skew), seed, _p(col),
-                                           _stream_ptr()), "gnn_synth_powerlaw_fill")
+    _lib.check(lib.gnn_synth_powerlaw_fill(n_rows, row_offset, n_cols, _p(rowptr), float(skew), float(p_local),
+                                           int(window), seed, _p(col), _stream_ptr()), "gnn_synth_powerlaw_fill")
     val = None
     if with_values:
         if deg_all is None:

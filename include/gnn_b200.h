@@ -124,7 +124,9 @@ int gnn_spmm_csr_bf16(const int64_t* rowptr, const int32_t* col, const float* va
  * per chunk; chunk_off[n_long+1] is the exclusive prefix sum of ceil(nnz_row/chunk_edges)
  * and n_chunks its last entry.  Per-chunk partial sums live in the workspace
  * (gnn_spmm_csr_workspace_size) and are added per row in chunk order: deterministic.
- * All other rows take the row-block streaming kernel.  The plan is host logic computed once
+ * All other rows take the row-block streaming kernel.  n_long may be 0 (no plan arrays
+ * needed); accumulate=1 adds into Y (the remote-column pass of the partitioned SpMM,
+ * SURVEY.md §8e).  The plan is host logic computed once
  * per graph (graphneuralnetwork_b200/graph.py CSRGraph.long_row_plan). */
 size_t gnn_spmm_csr_workspace_size(int64_t n_chunks, int32_t elem_size);
 int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const float* val,
@@ -132,12 +134,14 @@ int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const fl
                              int64_t ldx, int64_t ldy,
                              const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
+                             int accumulate /*1: Y += A*X*/,
                              void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const float* val,
                               const void* X, void* Y, int64_t n_rows, int64_t n_cols, int32_t F,
                               int64_t ldx, int64_t ldy,
                               const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                               const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
+                              int accumulate,
                               void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 
 /* ---- GraphSAGE: fused gather + reduce over fixed-fanout index blocks ----------- */
@@ -212,7 +216,8 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
 int gnn_synth_powerlaw_degrees(int64_t n_rows, int64_t row_offset, double mean_degree, double exponent,
                                int64_t max_degree, uint64_t seed, int64_t* deg /*[n_rows]*/, gnn_stream_t stream);
 int gnn_synth_powerlaw_fill(int64_t n_rows, int64_t row_offset, int64_t n_cols, const int64_t* rowptr,
-                            double skew, uint64_t seed, int32_t* col, gnn_stream_t stream);
+                            double skew, double p_local /*share of edges within +-window of the row*/,
+                            int64_t window, uint64_t seed, int32_t* col, gnn_stream_t stream);
 int gnn_synth_gcn_values(int64_t n_rows, int64_t row_offset, const int64_t* rowptr, const int32_t* col,
                          const int64_t* deg_all /*[n_cols] global degrees*/, float* val, gnn_stream_t stream);
 
