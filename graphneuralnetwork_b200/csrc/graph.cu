@@ -174,7 +174,8 @@ __global__ void synth_fill_kernel(int64_t n_rows, int64_t row_offset, int64_t n_
       if (p_local > 0.0 && u01(mix64(h ^ 0xa5a5a5a5a5a5a5a5ULL)) < p_local) {
         // community edge: within +-window of the row (a locality-preserving node ordering)
         const double w = u01(mix64(h + 0x1234567ULL));
-        const int64_t off = 1 + (int64_t)((double)window * w * w);
+        const int64_t wabs = window < 0 ? -window : window;
+        const int64_t off = 1 + (int64_t)((double)wabs * w * w);
         c = (h & 1) ? self + off : self - off;
         c = c < 0 ? -c : c;
         c = c >= n_cols ? 2 * (n_cols - 1) - c : c;
@@ -182,6 +183,10 @@ __global__ void synth_fill_kernel(int64_t n_rows, int64_t row_offset, int64_t n_
       } else {
         const double x = ((double)k + u) / (double)d;
         c = (int64_t)((double)n_cols * pow(x, skew));
+        c = c >= n_cols ? n_cols - 1 : c;
+        // window < 0: scatter the popular ids over the whole id range with a fixed bijection
+        // (hubs of a real graph are not sorted by id); popularity itself is unchanged
+        if (window < 0) c = (int64_t)(((uint64_t)c * 2654435761ULL) % (uint64_t)n_cols);  // c < 2^31: no overflow
       }
       c = c >= n_cols ? n_cols - 1 : c;
       col[s + 1 + k] = (int32_t)c;
@@ -405,7 +410,7 @@ int gnn_synth_powerlaw_degrees(int64_t n_rows, int64_t row_offset, double mean_d
 int gnn_synth_powerlaw_fill(int64_t n_rows, int64_t row_offset, int64_t n_cols, const int64_t* rowptr, double skew,
                             double p_local, int64_t window, uint64_t seed, int32_t* col, gnn_stream_t stream) {
   GNN_REQUIRE(n_rows >= 0 && n_cols > 0 && n_cols < 0x7fffffffLL && rowptr && col && skew >= 1.0 && p_local >= 0.0 &&
-                  p_local <= 1.0 && window >= 0,
+                  p_local <= 1.0,
               GNN_ERR_BAD_ARG, "bad argument");
   if (n_rows == 0) return GNN_OK;
   synth_fill_kernel<<<grid_for(n_rows * 32), 256, 0, (cudaStream_t)stream>>>(n_rows, row_offset, n_cols, rowptr, skew,

@@ -23,6 +23,7 @@ struct PushArgs {
   int64_t dst_off[kMaxPeers];
   int64_t ld_halo;
   int32_t n_peers;
+  int64_t rot;  // rows are pushed starting at this offset of send_rows and wrapping around
 };
 
 // One warp per sent row, kPushUnroll rows in flight per warp (all loads issued before the
@@ -41,10 +42,14 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a) {
     float* dst[kPushUnroll];
 #pragma unroll
     for (int u = 0; u < kPushUnroll; ++u) {
-      const int64_t k = k0 + u;
+      // rotated order: rank r starts with the segment of peer r+1, so at any moment every
+      // receiver is written by a different sender (no ingress hot spot in the all-to-all)
+      int64_t k = k0 + u;
       src[u] = nullptr;
       dst[u] = nullptr;
       if (k < total) {
+        k += a.rot;
+        k = k >= total ? k - total : k;
         int q = 0;
         while (q + 1 < a.n_peers && k >= a.send_off[q + 1]) ++q;
         src[u] = a.X + (int64_t)__ldg(a.send_rows + k) * a.ldx;
@@ -105,7 +110,7 @@ int gnn_peer_free(void* dev_ptr) {
 
 int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* send_rows, const int64_t* send_off_host,
                       float* const* peer_halo_host, const int64_t* dst_off_host, int64_t ld_halo, int32_t n_peers,
-                      gnn_stream_t stream) {
+                      int32_t first_peer, gnn_stream_t stream) {
   GNN_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, GNN_ERR_UNSUPPORTED, "n_peers=%d exceeds %d", n_peers, kMaxPeers);
   if (n_peers == 0) return GNN_OK;
   GNN_REQUIRE(X && send_off_host && peer_halo_host && dst_off_host, GNN_ERR_BAD_ARG, "null pointer");
@@ -128,6 +133,8 @@ int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* sen
   }
   const int64_t total = a.send_off[n_peers];
   if (total == 0) return GNN_OK;
+  GNN_REQUIRE(first_peer >= 0 && first_peer < n_peers, GNN_ERR_BAD_ARG, "first_peer out of range");
+  a.rot = a.send_off[first_peer] % total;
   GNN_REQUIRE(send_rows != nullptr, GNN_ERR_BAD_ARG, "null send_rows");
   int64_t grid = (total * 32 + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * tuning("halo.ctas_per_sm", 1);

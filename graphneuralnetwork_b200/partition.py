@@ -193,7 +193,7 @@ class PartitionedSpmm:
             b = self._step & 1
             ptrs = (C.c_void_p * plan.world)(*self._peer_ptrs[b])
             _lib.check(lib.gnn_halo_push_f32(X.data_ptr(), X.stride(0), self.F, plan.send_rows.data_ptr(), self._send_off,
-                                             ptrs, self._dst_off, self.ld, plan.world,
+                                             ptrs, self._dst_off, self.ld, plan.world, (plan.rank + 1) % plan.world,
                                              torch.cuda.current_stream().cuda_stream), "gnn_halo_push_f32")
             # stream-ordered barrier: returns (on this stream) once every rank's push has completed
             dist.all_reduce(self._flag, group=self.group)

@@ -92,13 +92,17 @@ def uniform_blocks(n_nodes, batch, fanouts, seed=0, dtype=torch.int64, device="c
 def powerlaw_csr(n_rows: int, mean_degree: float, *, n_cols: int | None = None, row_offset: int = 0,
                  exponent: float = 2.5, skew: float = 3.0, max_degree: int = 1 << 20, seed: int = 0,
                  device="cuda", with_values: bool = True, deg_all: torch.Tensor | None = None,
-                 p_local: float = 0.0, window: int = 0) -> CSRGraph:
+                 p_local: float = 0.0, window: int = 0, scatter_hubs: bool = False) -> CSRGraph:
     """Power-law CSR generated on the device (gnn_synth_*): Pareto degrees with the requested
     mean, neighbour ids skewed to low ids (hubs), one self-loop per row, GCN-normalised
     values d_i^-1/2·d_j^-1/2 from the row degrees.  `row_offset`/`n_cols` generate one row
     block of a larger graph (each rank of the partitioned run builds only its own rows).
     `p_local` > 0 draws that share of the edges within +-`window` of the row id instead — the
-    structure a locality-preserving (METIS-like) node ordering gives a 1-D partition."""
+    structure a locality-preserving (METIS-like) node ordering gives a 1-D partition.
+    `scatter_hubs` maps the popular (hub) ids through a fixed bijection of the id range, so
+    hubs are spread over all row blocks as in a real graph instead of sitting at the low ids."""
+    if scatter_hubs:
+        window = -max(int(window), 1)
     lib = _lib.load()
     n_cols = n_rows if n_cols is None else n_cols
     dev = torch.device(device)

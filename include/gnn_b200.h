@@ -216,8 +216,9 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
 int gnn_synth_powerlaw_degrees(int64_t n_rows, int64_t row_offset, double mean_degree, double exponent,
                                int64_t max_degree, uint64_t seed, int64_t* deg /*[n_rows]*/, gnn_stream_t stream);
 int gnn_synth_powerlaw_fill(int64_t n_rows, int64_t row_offset, int64_t n_cols, const int64_t* rowptr,
-                            double skew, double p_local /*share of edges within +-window of the row*/,
-                            int64_t window, uint64_t seed, int32_t* col, gnn_stream_t stream);
+                            double skew, double p_local /*share of edges within +-|window| of the row*/,
+                            int64_t window /*<0: also scatter the hub ids by a fixed bijection*/,
+                            uint64_t seed, int32_t* col, gnn_stream_t stream);
 int gnn_synth_gcn_values(int64_t n_rows, int64_t row_offset, const int64_t* rowptr, const int32_t* col,
                          const int64_t* deg_all /*[n_cols] global degrees*/, float* val, gnn_stream_t stream);
 
@@ -233,7 +234,9 @@ int gnn_peer_free(void* dev_ptr);
 int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F,
                       const int32_t* send_rows, const int64_t* send_off_host /*[n_peers+1]*/,
                       float* const* peer_halo_host /*[n_peers] device ptrs*/, const int64_t* dst_off_host /*[n_peers]*/,
-                      int64_t ld_halo, int32_t n_peers, gnn_stream_t stream);
+                      int64_t ld_halo, int32_t n_peers,
+                      int32_t first_peer /*segment pushed first; (rank+1)%n_peers staggers the all-to-all*/,
+                      gnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ from graphneuralnetwork_b200.partition import PartitionedSpmm, balanced_bounds, 
 
 
 def build_rank_block(n, deg, rank, world, dev, seed=0, exponent=2.5, skew=3.0, p_local=0.0, window=0,
-                     max_degree=1 << 20):
+                     max_degree=1 << 20, scatter=False):
     lib = _lib.load()
     deg_all = torch.empty(n, dtype=torch.int64, device=dev)
     _lib.check(lib.gnn_synth_powerlaw_degrees(n, 0, float(deg), float(exponent), int(max_degree), seed, _p(deg_all),
@@ -29,7 +29,7 @@ def build_rank_block(n, deg, rank, world, dev, seed=0, exponent=2.5, skew=3.0, p
     del rowptr_g
     lo, hi = bounds[rank], bounds[rank + 1]
     csr = S.powerlaw_csr(hi - lo, deg, n_cols=n, row_offset=lo, exponent=exponent, skew=skew, max_degree=max_degree,
-                         seed=seed, device=dev, deg_all=deg_all, p_local=p_local, window=window)
+                         seed=seed, device=dev, deg_all=deg_all, p_local=p_local, window=window, scatter_hubs=scatter)
     del deg_all
     return csr, bounds, nnz_total
 
@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--transports", nargs="+", default=["p2p", "nccl"])
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--phases", action="store_true")
+    ap.add_argument("--scatter", action="store_true")
     ap.add_argument("--halo-ctas", type=int, default=1)
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -55,7 +56,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_tuning("halo.ctas_per_sm", a.halo_ctas)
-    csr, bounds, nnz_total = build_rank_block(a.n, a.deg, rank, world, dev, skew=a.skew, p_local=a.p_local, window=a.window)
+    csr, bounds, nnz_total = build_rank_block(a.n, a.deg, rank, world, dev, skew=a.skew, p_local=a.p_local, window=a.window,
+                                                  scatter=a.scatter)
     plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world)
     n_loc = plan.n_local
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -90,7 +92,7 @@ def main():
                 hal = [int(s[0]) for s in allstats]
                 print(json.dumps({"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F,
                                   "transport": transport, "overlap": overlap, "halo_ctas": a.halo_ctas, "ms": ms.item(),
-                                  "edges_per_s": nnz_total / ms.item() * 1e3, "p_local": a.p_local, "window": a.window,
+                                  "edges_per_s": nnz_total / ms.item() * 1e3, "p_local": a.p_local, "window": a.window, "scatter": a.scatter, "skew": a.skew,
                                   "halo_rows_max": max(hal), "halo_rows_mean": sum(hal) / world,
                                   "halo_gb_recv_max": max(hal) * a.F * 4 / 1e9,
                                   "send_rows_max": max(int(s[3]) for s in allstats),
@@ -122,7 +124,8 @@ def main():
                                   "exchange_gbs_recv": max(int(s[0]) for s in allstats) * a.F * 4 / t_x / 1e6}), flush=True)
         if a.check:
             # every rank rebuilds the FULL graph (small n only) and checks its own rows
-            full = S.powerlaw_csr(a.n, a.deg, seed=0, device=dev, skew=a.skew, p_local=a.p_local, window=a.window)
+            full = S.powerlaw_csr(a.n, a.deg, seed=0, device=dev, skew=a.skew, p_local=a.p_local, window=a.window,
+                                  scatter_hubs=a.scatter)
             Xs = [torch.empty(bounds[q + 1] - bounds[q], a.F, device=dev) for q in range(world)]
             if world > 1:
                 dist.all_gather(Xs, X)
