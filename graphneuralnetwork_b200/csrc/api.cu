@@ -42,6 +42,7 @@ static std::map<std::string, int>& tune_map() {
       {"spmm.chunk", 8192},      // edges per long-row chunk
       {"spmm.unroll", 0},        // 0 = heuristic
       {"gat.stage_edges", 128},  // logits staged per warp pass
+      {"gat.coop_min_avg_deg", 48},  // nnz/n at which a whole CTA (not a warp) takes a row
       {"halo.ctas_per_sm", 1},   // footprint of the NVLink push kernel (the rest of the SM runs the SpMM)
   };
   return m;

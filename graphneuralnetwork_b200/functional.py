@@ -208,8 +208,8 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
     row_max = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     row_sum = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     col_mean = Wh.mean(dim=0).contiguous() if g.has_empty_rows() else None
-    _lib.check(lib.gnn_gat_fused_fwd_f32(_p(g.rowptr), _p(g.col), _p(Wh), _ld(Wh), _p(s), _p(t), n, H, Fp, float(alpha),
-                                         mode, elu, _p(col_mean), _p(keep), _p(out), _ld(out), _p(row_max), _p(row_sum),
+    _lib.check(lib.gnn_gat_fused_fwd_f32(_p(g.rowptr), _p(g.col), _p(Wh), _ld(Wh), _p(s), _p(t), n, g.nnz, H, Fp,
+                                         float(alpha), mode, elu, _p(col_mean), _p(keep), _p(out), _ld(out), _p(row_max), _p(row_sum),
                                          _stream_ptr()), "gnn_gat_fused_fwd_f32")
     return out, row_max, row_sum
 

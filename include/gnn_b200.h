@@ -184,9 +184,12 @@ int gnn_gat_scores_f32(const float* Wh, int64_t ldw, const float* a_src, const f
  * Rows with no edge reproduce the reference's softmax over an all -9e15 row: the
  * uniform mean over ALL nodes, passed in as col_mean[H*Fp] (nullable if no such row).
  * edge_keep (nullable, fp32 [nnz,H]): post-softmax dropout factor per edge and head
- * (0 or 1/(1-p)), layers.py:31.  row_max/row_sum [n,H] are saved for the backward. */
+ * (0 or 1/(1-p)), layers.py:31.  row_max/row_sum [n,H] are saved for the backward.
+ * Schedule: one warp per row, or one CTA per row (4 warps on alternate 128-edge chunks, merged
+ * in warp order) when nnz/n >= the "gat.coop_min_avg_deg" knob. */
 int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw,
-                          const float* s, const float* t, int64_t n, int32_t H, int32_t Fp,
+                          const float* s, const float* t, int64_t n, int64_t nnz /*schedule hint, 0 if unknown*/,
+                          int32_t H, int32_t Fp,
                           float alpha, int mode, int apply_elu, const float* col_mean,
                           const float* edge_keep, float* out, int64_t ldo,
                           float* row_max, float* row_sum, gnn_stream_t stream);

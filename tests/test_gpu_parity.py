@@ -434,6 +434,29 @@ def test_gat_fused_shapes_vs_f64(lib, H, Fp, deg):
     assert rel_err(t2.cpu().numpy(), np.einsum("nhf,hf->nh", Wh.astype(np.float64), a_dst)) < TOL32
 
 
+@pytest.mark.parametrize("nhid,density", [(8, 0.6), (5, 0.6), (8, 0.02), (5, 0.02), (16, 0.5)])
+def test_gat_forward_backward_vs_cpu_autograd(lib, nhid, density):
+    """Dense (CTA-per-row schedule) and sparse (warp-per-row) graphs, power-of-two and odd head
+    widths, against torch autograd of the oracle's dense formulation on the CPU."""
+    n, nfeat, nheads, ncls = 160, 30, 4, 7
+    rng = np.random.default_rng(int(nhid * 100 + density * 1000))
+    adj = (rng.random((n, n)) < density).astype(np.float32)
+    adj[np.arange(n), np.arange(n)] = 1
+    X = rng.standard_normal((n, nfeat)).astype(np.float32)
+    labels = rng.integers(0, ncls, n)
+    torch.manual_seed(nhid)
+    model = layers.GAT(nfeat, nhid, ncls, 0.0, 0.2, nheads)
+    cpu_params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = ogat.gat_model(torch.from_numpy(X), cpu_params, torch.from_numpy(adj), 0.2, nheads)
+    torch.nn.functional.cross_entropy(ref, torch.from_numpy(labels)).backward()
+    model = model.to(DEV).train()
+    out = model(cuda(X), cuda(adj))
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL32
+    torch.nn.functional.cross_entropy(out, cuda(labels)).backward()
+    for name, p in model.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), cpu_params[name].grad.numpy()) < 2e-5, name
+
+
 def test_han_small_vs_reference_golden(lib):
     g = load_golden("han_small.npz")
     n = int(g["n"])

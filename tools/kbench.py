@@ -89,7 +89,10 @@ def bench_spmm(args, n, mean_deg, tag):
 
 def bench_gat(args):
     for n, mean_deg, tag in ((2708, 4.9, "cora"), (3025, 730, "acm_dense"), (232_965, 100, "reddit_d100")):
-        csr = S.powerlaw_csr(n, mean_deg, seed=0, device=DEV, with_values=False, max_degree=min(n - 1, 20000))
+        # skew=1: uniform targets, so in-degrees stay moderate like in the symmetric adjacencies
+        # GAT/HAN are given (the transposed graph the backward walks has no 100k-edge rows)
+        csr = S.powerlaw_csr(n, mean_deg, seed=0, device=DEV, with_values=False, max_degree=min(n - 1, 20000),
+                             skew=1.0)
         H, Fp = 8, 8
         Wh = torch.randn(n, H * Fp, device=DEV, requires_grad=True)
         s = torch.randn(n, H, device=DEV, requires_grad=True)
