@@ -1,10 +1,11 @@
 from .gcn import GCN_Model, Graph_conv_layer
 from .gat import GAT, GATBase, GraphAttentionLayer, SpGAT, SpGraphAttentionLayer
 from .han import GATConv, HANLayer, HANModel, SemanticAttention
-from .sage import Aggregator, GraphSage, NeighborAggregator, SageGCN, SampledBlock, gather_mean
+from .sage import (Aggregator, CapturedGraphSage, GraphSage, NeighborAggregator, SageGCN, SampledBlock,
+                   gather_mean)
 
 __all__ = [
     "GCN_Model", "Graph_conv_layer", "GAT", "GATBase", "GraphAttentionLayer", "SpGAT", "SpGraphAttentionLayer",
     "GATConv", "HANLayer", "HANModel", "SemanticAttention", "Aggregator", "GraphSage", "NeighborAggregator",
-    "SageGCN", "SampledBlock", "gather_mean",
+    "SageGCN", "SampledBlock", "gather_mean", "CapturedGraphSage",
 ]

@@ -173,3 +173,45 @@ def gather_mean(feats, index_map):
     (GraphSAGE.py:48-49 keeps rows whose column 0 is not -1)."""
     n, k = index_map.shape
     return gather_reduce(feats, index_map.reshape(-1), n, k, 'mean')
+
+
+class CapturedGraphSage:
+    """Inference runner for the fused path: `GraphSage.forward_sampled` captured once into a
+    CUDA graph (the aggregation kernels of libgnn_b200.so and the torch matmuls alike), then
+    replayed per minibatch.  Per call only the sampled ids cross PCIe (pinned host -> static
+    device buffers) and the logits come back; launch overhead is one graph launch.
+
+        runner = CapturedGraphSage(model, table, batch=1024)
+        logits_host = runner(host_id_blocks)        # list of pinned int32/int64 id tensors
+    """
+
+    def __init__(self, model: GraphSage, table: torch.Tensor, batch: int, id_dtype=torch.int32):
+        self.model, self.table = model, table
+        dev = table.device
+        sizes = [batch]
+        for f in model.num_neighbors_list:
+            sizes.append(sizes[-1] * f)
+        self.ids = [torch.zeros(s, dtype=id_dtype, device=dev) for s in sizes]
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.kernel_launches_per_replay = 0
+        from .. import _lib
+        with torch.no_grad(), torch.cuda.stream(self.stream):
+            for _ in range(2):  # warm-up outside capture (allocator, cuBLAS handles, smem attributes)
+                model.forward_sampled(table, self.ids)
+            self.stream.synchronize()
+            before = _lib.launch_count()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.logits = model.forward_sampled(table, self.ids)
+            self.kernel_launches_per_replay = _lib.launch_count() - before
+        self.logits_host = torch.empty(self.logits.shape, dtype=self.logits.dtype).pin_memory()
+
+    @torch.no_grad()
+    def __call__(self, host_id_blocks):
+        with torch.cuda.stream(self.stream):
+            for dst, src in zip(self.ids, host_id_blocks):
+                dst.copy_(src, non_blocking=True)          # H2D: this minibatch's sampled ids
+            self.graph.replay()
+            self.logits_host.copy_(self.logits, non_blocking=True)  # D2H: the result
+        self.stream.synchronize()
+        return self.logits_host
