@@ -43,7 +43,9 @@ static std::map<std::string, int>& tune_map() {
       {"spmm.unroll", 0},        // 0 = heuristic
       {"gat.stage_edges", 128},  // logits staged per warp pass
       {"gat.coop_min_avg_deg", 48},  // nnz/n at which a whole CTA (not a warp) takes a row
-      {"halo.ctas_per_sm", 1},   // footprint of the NVLink push kernel (the rest of the SM runs the SpMM)
+      {"halo.ctas_per_sm", 1},
+      {"halo.schedule", 0},      // 0 rotated segments, 1 warps interleaved over peers
+      {"halo.unroll", 4},        // rows in flight per warp of the push kernel   // footprint of the NVLink push kernel (the rest of the SM runs the SpMM)
   };
   return m;
 }

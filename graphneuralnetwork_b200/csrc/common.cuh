@@ -129,6 +129,50 @@ struct VecIO<__nv_bfloat16, 8> {
   }
 };
 
+// ---- raw (still packed) vector staging: keeps bf16 rows at half the registers while the
+// gathers are in flight; unpacked only when they are consumed --------------------------------
+template <typename T, int VEC>
+struct VecRaw {
+  static constexpr int W = (sizeof(T) * VEC + 3) / 4;  // 32-bit words
+  uint32_t w[W];
+};
+template <typename T, int VEC>
+__device__ __forceinline__ VecRaw<T, VEC> load_raw(const T* p) {
+  VecRaw<T, VEC> r;
+  constexpr int B = (int)sizeof(T) * VEC;
+  if constexpr (B == 16) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  } else if constexpr (B == 8) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    r.w[0] = v.x; r.w[1] = v.y;
+  } else if constexpr (B == 4) {
+    r.w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+  } else {
+    r.w[0] = __ldg(reinterpret_cast<const unsigned short*>(p));
+  }
+  return r;
+}
+template <typename T, int VEC>
+__device__ __forceinline__ VecRaw<T, VEC> zero_raw() {
+  VecRaw<T, VEC> r;
+#pragma unroll
+  for (int i = 0; i < VecRaw<T, VEC>::W; ++i) r.w[i] = 0u;
+  return r;
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void unpack_raw(const VecRaw<T, VEC>& r, float (&o)[VEC]) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = __uint_as_float(r.w[i]);
+  } else if constexpr (VEC == 1) {
+    o[0] = __uint_as_float(r.w[0] << 16);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC / 2; ++i) bf16x2_to_f32(r.w[i], o[2 * i], o[2 * i + 1]);
+  }
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) -------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -23,46 +23,69 @@ struct PushArgs {
   int64_t dst_off[kMaxPeers];
   int64_t ld_halo;
   int32_t n_peers;
-  int64_t rot;  // rows are pushed starting at this offset of send_rows and wrapping around
+  int64_t rot;  // first peer served (warp slots are dealt to peers rot, rot+1, ... mod n_peers)
 };
 
-// One warp per sent row, kPushUnroll rows in flight per warp (all loads issued before the
-// first store).  The grid is deliberately small (one CTA per SM): NVLink needs ~1.5 MB in
-// flight, and the remaining thread slots of every SM stay free for the local-column SpMM
-// that runs concurrently on the main stream.
-constexpr int kPushUnroll = 4;
-template <int VEC>
+// One warp per sent row, UNROLL rows in flight per warp (all index loads, then all row loads,
+// then the stores).  The grid is deliberately small (one CTA per SM): NVLink needs ~1.5 MB in
+// flight, and the remaining thread slots of every SM stay free for the local-column SpMM that
+// runs concurrently on the main stream.
+// All-to-all schedules (both avoid the ingress hot spot of "everybody pushes to peer 0 first",
+// which cost 2.5x at 8 GPUs):
+//   SCHED 0  rotated: rank r walks its segments in the order r+1, r+2, ... (one receiver at a time)
+//   SCHED 1  interleaved: warp w serves peer first_peer + w % n_peers (all receivers at once)
+template <int VEC, int UNROLL, int SCHED>
 __global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a) {
   const int lane = threadIdx.x & 31;
-  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t total = a.send_off[a.n_peers];
-  for (int64_t k0 = w0 * kPushUnroll; k0 < total; k0 += nw * kPushUnroll) {
-    const float* src[kPushUnroll];
-    float* dst[kPushUnroll];
+  int64_t k_begin, k_step, k_end, seg0 = 0;
+  float* halo_q = nullptr;
+  if (SCHED == 1) {
+    const int slot = (int)(w % a.n_peers);
+    const int q = (int)((a.rot + slot) % a.n_peers);
+    const int64_t nwq = (nw - slot + a.n_peers - 1) / a.n_peers;  // warps dealt to this peer
+    seg0 = a.send_off[q];
+    k_begin = (w / a.n_peers) * UNROLL;
+    k_step = nwq * UNROLL;
+    k_end = a.send_off[q + 1] - seg0;
+    halo_q = a.halo[q] + a.dst_off[q] * a.ld_halo;
+  } else {
+    k_begin = w * UNROLL;
+    k_step = nw * UNROLL;
+    k_end = total;
+  }
+  const int64_t rot_rows = a.send_off[a.rot];
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += k_step) {
+    const float* src[UNROLL];
+    float* dst[UNROLL];
 #pragma unroll
-    for (int u = 0; u < kPushUnroll; ++u) {
-      // rotated order: rank r starts with the segment of peer r+1, so at any moment every
-      // receiver is written by a different sender (no ingress hot spot in the all-to-all)
+    for (int u = 0; u < UNROLL; ++u) {
       int64_t k = k0 + u;
       src[u] = nullptr;
       dst[u] = nullptr;
-      if (k < total) {
-        k += a.rot;
-        k = k >= total ? k - total : k;
-        int q = 0;
-        while (q + 1 < a.n_peers && k >= a.send_off[q + 1]) ++q;
-        src[u] = a.X + (int64_t)__ldg(a.send_rows + k) * a.ldx;
-        dst[u] = a.halo[q] + (a.dst_off[q] + (k - a.send_off[q])) * a.ld_halo;
+      if (k < k_end) {
+        if (SCHED == 1) {
+          src[u] = a.X + (int64_t)__ldg(a.send_rows + seg0 + k) * a.ldx;
+          dst[u] = halo_q + k * a.ld_halo;
+        } else {
+          k += rot_rows;
+          k = k >= total ? k - total : k;
+          int q = 0;
+          while (q + 1 < a.n_peers && k >= a.send_off[q + 1]) ++q;
+          src[u] = a.X + (int64_t)__ldg(a.send_rows + k) * a.ldx;
+          dst[u] = a.halo[q] + (a.dst_off[q] + (k - a.send_off[q])) * a.ld_halo;
+        }
       }
     }
     for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
-      float v[kPushUnroll][VEC];
+      float v[UNROLL][VEC];
 #pragma unroll
-      for (int u = 0; u < kPushUnroll; ++u)
+      for (int u = 0; u < UNROLL; ++u)
         if (src[u]) VecIO<float, VEC>::load(src[u] + c, v[u]);
 #pragma unroll
-      for (int u = 0; u < kPushUnroll; ++u)
+      for (int u = 0; u < UNROLL; ++u)
         if (dst[u]) VecIO<float, VEC>::store(dst[u] + c, v[u]);
     }
   }
@@ -134,13 +157,27 @@ int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* sen
   const int64_t total = a.send_off[n_peers];
   if (total == 0) return GNN_OK;
   GNN_REQUIRE(first_peer >= 0 && first_peer < n_peers, GNN_ERR_BAD_ARG, "first_peer out of range");
-  a.rot = a.send_off[first_peer] % total;
+  a.rot = first_peer;
   GNN_REQUIRE(send_rows != nullptr, GNN_ERR_BAD_ARG, "null send_rows");
+  // the grid must deal at least one warp to every peer: never fewer than n_peers warps
   int64_t grid = (total * 32 + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * tuning("halo.ctas_per_sm", 1);
   grid = grid > cap ? cap : grid;
-  if (vec4) halo_push_kernel<4><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
-  else halo_push_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
+  const int64_t min_grid = (n_peers + 7) / 8;
+  grid = grid < min_grid ? min_grid : grid;
+  const int sched = tuning("halo.schedule", 0);
+  const int unroll = tuning("halo.unroll", 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = (unsigned)grid;
+  if (vec4) {
+    if (sched == 1 && unroll >= 8) halo_push_kernel<4, 8, 1><<<g, 256, 0, st>>>(a);
+    else if (sched == 1) halo_push_kernel<4, 4, 1><<<g, 256, 0, st>>>(a);
+    else if (unroll >= 8) halo_push_kernel<4, 8, 0><<<g, 256, 0, st>>>(a);
+    else halo_push_kernel<4, 4, 0><<<g, 256, 0, st>>>(a);
+  } else {
+    if (sched == 1) halo_push_kernel<1, 4, 1><<<g, 256, 0, st>>>(a);
+    else halo_push_kernel<1, 4, 0><<<g, 256, 0, st>>>(a);
+  }
   GNN_LAUNCH_CHECK();
   return GNN_OK;
 }

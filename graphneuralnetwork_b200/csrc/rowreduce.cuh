@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(kRowReduceThreads) row_reduce_kernel(const Row
     }
     const int cnt = (int)((e - base) < (int64_t)GROUP ? (e - base) : (int64_t)GROUP);
     for (int j0 = 0; j0 < cnt; j0 += U) {
-      float xv[U][CHUNKS][VEC];
+      VecRaw<T, VEC> xv[U][CHUNKS];
       float vv[U];
+      bool xok[U][CHUNKS];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int jj = j0 + u;
@@ -90,29 +91,28 @@ __global__ void __launch_bounds__(kRowReduceThreads) row_reduce_kernel(const Row
 #pragma unroll
         for (int ch = 0; ch < CHUNKS; ++ch) {
           const int col0 = (gl + ch * GROUP) * VEC;
-          if (ok && col0 < a.F) {
-            VecIO<T, VEC>::load(xr + col0, xv[u][ch]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) xv[u][ch][i] = (OP == 1) ? -INFINITY : 0.f;
-          }
+          xok[u][ch] = ok && col0 < a.F;
+          xv[u][ch] = xok[u][ch] ? load_raw<T, VEC>(xr + col0) : zero_raw<T, VEC>();
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int ch = 0; ch < CHUNKS; ++ch)
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          float x[VEC];
+          unpack_raw<T, VEC>(xv[u][ch], x);
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
             if (OP == 1) {
-              if (xv[u][ch][i] > acc[ch][i]) {
-                acc[ch][i] = xv[u][ch][i];
+              if (xok[u][ch] && x[i] > acc[ch][i]) {
+                acc[ch][i] = x[i];
                 best[ch][i] = (int)(base - s) + j0 + u;
               }
             } else {
-              acc[ch][i] = fmaf(vv[u], xv[u][ch][i], acc[ch][i]);
+              acc[ch][i] = fmaf(vv[u], x[i], acc[ch][i]);
             }
           }
+        }
     }
   }
 
@@ -134,84 +134,6 @@ __global__ void __launch_bounds__(kRowReduceThreads) row_reduce_kernel(const Row
   }
 }
 
-// Long rows: one CTA per row, warps take 32-edge batches round-robin, per-warp partial
-// sums reduced through shared memory in warp order (fixed order => deterministic).
-constexpr int kLongWarps = 8;
-template <typename T, int VEC, int CHUNKS>
-__global__ void __launch_bounds__(kLongWarps * 32) row_reduce_long_kernel(const RowArgs<T> a, const int64_t* long_rows) {
-  __shared__ float part[kLongWarps][CHUNKS * 32 * VEC];
-  const int lane = threadIdx.x & 31;
-  const int w = threadIdx.x >> 5;
-  const int64_t row = long_rows[blockIdx.x];
-  const int64_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
-  float acc[CHUNKS][VEC];
-#pragma unroll
-  for (int ch = 0; ch < CHUNKS; ++ch)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
-  constexpr int U = (CHUNKS == 1) ? 8 : (CHUNKS <= 3 ? 4 : 2);
-  for (int64_t base = s + (int64_t)w * 32; base < e; base += (int64_t)kLongWarps * 32) {
-    const int64_t k = base + lane;
-    int32_t c = -1;
-    float v = 0.f;
-    if (k < e) {
-      c = __ldg(a.col32 + k);
-      if (a.src_div > 0) c /= a.src_div;
-      v = a.val ? __ldg(a.val + k) : 1.f;
-    }
-    const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
-    for (int j0 = 0; j0 < cnt; j0 += U) {
-      float xv[U][CHUNKS][VEC];
-      float vv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int jj = j0 + u;
-        const int32_t cj = __shfl_sync(0xffffffffu, c, jj);
-        const float vj = __shfl_sync(0xffffffffu, v, jj);
-        const bool ok = (jj < cnt) && (cj >= 0);
-        vv[u] = ok ? vj : 0.f;
-        const T* xr = a.X + (int64_t)(ok ? cj : 0) * a.ldx;
-#pragma unroll
-        for (int ch = 0; ch < CHUNKS; ++ch) {
-          const int col0 = (lane + ch * 32) * VEC;
-          if (ok && col0 < a.F) {
-            VecIO<T, VEC>::load(xr + col0, xv[u][ch]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) xv[u][ch][i] = 0.f;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int ch = 0; ch < CHUNKS; ++ch)
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], xv[u][ch][i], acc[ch][i]);
-    }
-  }
-#pragma unroll
-  for (int ch = 0; ch < CHUNKS; ++ch)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) part[w][(ch * 32 + lane) * VEC + i] = acc[ch][i];
-  __syncthreads();
-  T* yr = a.Y + row * a.ldy;
-  for (int idx = threadIdx.x; idx < CHUNKS * 32; idx += kLongWarps * 32) {
-    const int col0 = idx * VEC;  // idx = ch*32+lane -> column (lane + ch*32)*VEC
-    if (col0 < a.F) {
-      float o[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float sum = 0.f;
-#pragma unroll
-        for (int ww = 0; ww < kLongWarps; ++ww) sum += part[ww][idx * VEC + i];
-        o[i] = sum * a.scale;
-      }
-      VecIO<T, VEC>::store(yr + col0, o);
-    }
-  }
-}
-
 // ---- host-side dispatch -----------------------------------------------------------
 template <typename T>
 inline int pick_vec(const void* X, int64_t ldx, const void* Y, int64_t ldy, int F) {
@@ -226,7 +148,8 @@ inline int pick_vec(const void* X, int64_t ldx, const void* Y, int64_t ldy, int 
 
 template <typename T, int VEC, int GROUP, int CHUNKS, int OP>
 inline void launch_row_reduce_inst(const RowArgs<T>& a, cudaStream_t st) {
-  constexpr int U0 = (CHUNKS == 1) ? 8 : (CHUNKS <= 3 ? 4 : 2);
+  constexpr int WORDS = CHUNKS * VecRaw<T, VEC>::W;
+  constexpr int U0 = (WORDS <= 4) ? 8 : (WORDS <= 12 ? 4 : 2);
   constexpr int U = U0 < GROUP ? U0 : GROUP;
   constexpr int ROWS_PER_CTA = kRowReduceThreads / GROUP;
   const int64_t grid = (a.n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
@@ -268,34 +191,6 @@ inline int launch_row_reduce(const RowArgs<T>& a, cudaStream_t st) {
   if (vec >= 4) return launch_row_reduce_vec<T, 4, OP>(a, st);
   if (vec == 2) return launch_row_reduce_vec<T, 2, OP>(a, st);
   return launch_row_reduce_vec<T, 1, OP>(a, st);
-}
-
-template <typename T, int VEC>
-inline int launch_row_reduce_long_vec(const RowArgs<T>& a0, const int64_t* long_rows, int64_t n_long, cudaStream_t st) {
-  const int tile_cols = 32 * 4 * VEC;  // keeps the partial-sum tile within 48 KB of static shared memory
-  for (int c0 = 0; c0 < a0.F; c0 += tile_cols) {
-    RowArgs<T> a = a0;
-    a.X = a0.X + c0;
-    a.Y = a0.Y + c0;
-    a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
-    const int nvec = (a.F + VEC - 1) / VEC;
-    const unsigned grid = (unsigned)n_long;
-    if (nvec <= 32) row_reduce_long_kernel<T, VEC, 1><<<grid, kLongWarps * 32, 0, st>>>(a, long_rows);
-    else if (nvec <= 64) row_reduce_long_kernel<T, VEC, 2><<<grid, kLongWarps * 32, 0, st>>>(a, long_rows);
-    else row_reduce_long_kernel<T, VEC, 4><<<grid, kLongWarps * 32, 0, st>>>(a, long_rows);
-    GNN_LAUNCH_CHECK();
-  }
-  return GNN_OK;
-}
-
-template <typename T>
-inline int launch_row_reduce_long(const RowArgs<T>& a, const int64_t* long_rows, int64_t n_long, cudaStream_t st) {
-  if (n_long <= 0 || a.F <= 0) return GNN_OK;
-  const int vec = pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F);
-  if (sizeof(T) == 2 && vec == 8) return launch_row_reduce_long_vec<T, (sizeof(T) == 2 ? 8 : 4)>(a, long_rows, n_long, st);
-  if (vec >= 4) return launch_row_reduce_long_vec<T, 4>(a, long_rows, n_long, st);
-  if (vec == 2) return launch_row_reduce_long_vec<T, 2>(a, long_rows, n_long, st);
-  return launch_row_reduce_long_vec<T, 1>(a, long_rows, n_long, st);
 }
 
 }  // namespace gnn

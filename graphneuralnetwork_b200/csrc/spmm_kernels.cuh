@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rbs_kernel(const SpmmArgs<T
       }
       const int cnt = (int)((E1 - base) < (int64_t)GROUP ? (E1 - base) : (int64_t)GROUP);
       for (int j0 = 0; j0 < cnt; j0 += U) {
-        float xv[U][CHUNKS][VEC];
+        VecRaw<T, VEC> xv[U][CHUNKS];
         float vv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -108,12 +108,7 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rbs_kernel(const SpmmArgs<T
 #pragma unroll
           for (int ch = 0; ch < CHUNKS; ++ch) {
             const int col0 = (gl + ch * GROUP) * VEC;
-            if (ok && col0 < a.F) {
-              VecIO<T, VEC>::load(xr + col0, xv[u][ch]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < VEC; ++i) xv[u][ch][i] = 0.f;
-            }
+            xv[u][ch] = (ok && col0 < a.F) ? load_raw<T, VEC>(xr + col0) : zero_raw<T, VEC>();
           }
         }
 #pragma unroll
@@ -127,9 +122,12 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rbs_kernel(const SpmmArgs<T
               cur_end = __shfl_sync(gmask, hi, cur, GROUP);
             }
 #pragma unroll
-            for (int ch = 0; ch < CHUNKS; ++ch)
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+              float x[VEC];
+              unpack_raw<T, VEC>(xv[u][ch], x);
 #pragma unroll
-              for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], xv[u][ch][i], acc[ch][i]);
+              for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], x[i], acc[ch][i]);
+            }
           }
         }
       }
@@ -153,7 +151,7 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rbs_kernel(const SpmmArgs<T
       }
       const int cnt = (int)((e - base) < (int64_t)GROUP ? (e - base) : (int64_t)GROUP);
       for (int j0 = 0; j0 < cnt; j0 += U) {
-        float xv[U][CHUNKS][VEC];
+        VecRaw<T, VEC> xv[U][CHUNKS];
         float vv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -166,20 +164,18 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rbs_kernel(const SpmmArgs<T
 #pragma unroll
           for (int ch = 0; ch < CHUNKS; ++ch) {
             const int col0 = (gl + ch * GROUP) * VEC;
-            if (ok && col0 < a.F) {
-              VecIO<T, VEC>::load(xr + col0, xv[u][ch]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < VEC; ++i) xv[u][ch][i] = 0.f;
-            }
+            xv[u][ch] = (ok && col0 < a.F) ? load_raw<T, VEC>(xr + col0) : zero_raw<T, VEC>();
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int ch = 0; ch < CHUNKS; ++ch)
+          for (int ch = 0; ch < CHUNKS; ++ch) {
+            float x[VEC];
+            unpack_raw<T, VEC>(xv[u][ch], x);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], xv[u][ch][i], acc[ch][i]);
+            for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], x[i], acc[ch][i]);
+          }
       }
     }
     flush(r);
@@ -230,7 +226,7 @@ __global__ void __launch_bounds__(kLongChunkWarps * 32)
     }
     const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
     for (int j0 = 0; j0 < cnt; j0 += EPW * U) {
-      float xv[U][CHUNKS][VEC];
+      VecRaw<T, VEC> xv[U][CHUNKS];
       float vv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -243,20 +239,18 @@ __global__ void __launch_bounds__(kLongChunkWarps * 32)
 #pragma unroll
         for (int ch = 0; ch < CHUNKS; ++ch) {
           const int col0 = (gl + ch * GROUP) * VEC;
-          if (ok && col0 < a.F) {
-            VecIO<T, VEC>::load(xr + col0, xv[u][ch]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) xv[u][ch][i] = 0.f;
-          }
+          xv[u][ch] = (ok && col0 < a.F) ? load_raw<T, VEC>(xr + col0) : zero_raw<T, VEC>();
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int ch = 0; ch < CHUNKS; ++ch)
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          float x[VEC];
+          unpack_raw<T, VEC>(xv[u][ch], x);
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], xv[u][ch][i], acc[ch][i]);
+          for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(vv[u], x[i], acc[ch][i]);
+        }
     }
   }
   // combine the edge slots of the warp (fixed butterfly), then the warps (fixed order)
@@ -318,7 +312,9 @@ inline int spmm_pick_vec(const void* X, int64_t ldx, const void* Y, int64_t ldy,
 
 template <typename T, int VEC, int GROUP, int CHUNKS>
 inline void spmm_rbs_launch(const SpmmArgs<T>& a, cudaStream_t st) {
-  constexpr int U0 = (CHUNKS == 1) ? 8 : (CHUNKS <= 3 ? 4 : 2);
+  // gathers in flight per lane: about 8 x 16 bytes of staging registers
+  constexpr int WORDS = CHUNKS * VecRaw<T, VEC>::W;
+  constexpr int U0 = (WORDS <= 4) ? 8 : (WORDS <= 12 ? 4 : 2);
   constexpr int U = U0 < GROUP ? U0 : GROUP;
   const int64_t grid = (a.n_rows + kSpmmThreads - 1) / kSpmmThreads;  // 256 rows per CTA for every GROUP
   spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U><<<(unsigned)grid, kSpmmThreads, 0, st>>>(a);

@@ -105,10 +105,10 @@ def pad_table(table: torch.Tensor) -> torch.Tensor:
 def gather_reduce_raw(table: torch.Tensor, idx: Optional[torch.Tensor], n_src: int, fanout: int, reduce: str = "mean",
                       out: Optional[torch.Tensor] = None, argmax: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One gnn_gather_reduce_{f32,bf16} launch (no autograd).  idx=None: identity block."""
+    if reduce not in _lib.REDUCE:  # the reference's own error (GraphSAGE_Pytorch/models/Aggregator.py:26)
+        raise ValueError("Unknown aggr type, expected sum, max, or mean, but got {}".format(reduce))
     _require_cuda(table, idx)
     lib = _lib.load()
-    if reduce not in _lib.REDUCE:
-        raise ValueError("Unknown aggr type, expected sum, max, or mean, but got {}".format(reduce))
     table = _rowmajor(table)
     N, F = table.shape
     if idx is not None:

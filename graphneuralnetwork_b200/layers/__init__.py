@@ -4,7 +4,10 @@ from .han import GATConv, HANLayer, HANModel, SemanticAttention
 from .sage import (Aggregator, CapturedGraphSage, GraphSage, NeighborAggregator, SageGCN, SampledBlock,
                    gather_mean)
 
+from .sage_v2 import GraphSAGE, SageLayer
+
 __all__ = [
+    "GraphSAGE", "SageLayer",
     "GCN_Model", "Graph_conv_layer", "GAT", "GATBase", "GraphAttentionLayer", "SpGAT", "SpGraphAttentionLayer",
     "GATConv", "HANLayer", "HANModel", "SemanticAttention", "Aggregator", "GraphSage", "NeighborAggregator",
     "SageGCN", "SampledBlock", "gather_mean", "CapturedGraphSage",

@@ -345,6 +345,22 @@ def test_graphsage_v2_blocks_vs_reference_golden(lib):
     assert rel_err(h2.cpu().numpy(), g["feats_out"]) < TOL32
 
 
+def test_graphsage_v2_model_vs_reference_golden(lib):
+    """The drop-in GraphSAGE (dedup variant) on the reference collate_fn's own batch: forward,
+    loss and every parameter gradient."""
+    g = load_golden("sage_v2_small.npz")
+    model = load_params(layers.GraphSAGE(2, 64, 32, gcn=False, agg_func='MEAN', Unsupervised=False, class_size=3), g)
+    model.train()
+    feats, classes = model(cuda(g["center_feats"]), cuda(g["center_map"]), cuda(g["neigh_feats"]), cuda(g["neigh_map"]),
+                           None, None, None, None, None)
+    assert rel_err(feats.detach().cpu().numpy(), g["feats_out"]) < TOL32
+    assert rel_err(classes.detach().cpu().numpy(), g["classes"]) < TOL32
+    loss = torch.nn.functional.cross_entropy(classes, cuda(g["labels"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    check_grads(model, g)
+
+
 # ---------------------------------------------------------------- GAT / HAN fused attention
 def test_gat_small_vs_reference_golden(lib):
     g = load_golden("gat_small.npz")

@@ -74,8 +74,9 @@ def bench_spmm(args, n, mean_deg, tag):
     emit(bench=tag + "_graph", n=n, nnz=csr.nnz, max_deg=int(deg.max()), long_rows=int(csr.long_rows().numel()))
     for F in args.Fs:
         for dt in ([torch.float32, torch.bfloat16] if args.bf16 else [torch.float32]):
-            X = torch.randn(n, F, device=DEV).to(dt)
-            Y = torch.empty(n, F, device=DEV, dtype=dt)
+            # 16-byte rows, as bench.py and the drop-in layers allocate them (602 -> ld 604 / 608)
+            X = Fn.pad_table(torch.randn(n, F, device=DEV).to(dt))
+            Y = Fn._padded_empty(n, F, dt, DEV)
             es = X.element_size()
             B = csr.nnz * 8 + csr.nnz * F * es + n * F * es + (n + 1) * 8
             comp = csr.nnz * 8 + 2 * n * F * es + (n + 1) * 8

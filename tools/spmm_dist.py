@@ -49,6 +49,9 @@ def main():
     ap.add_argument("--phases", action="store_true")
     ap.add_argument("--scatter", action="store_true")
     ap.add_argument("--halo-ctas", type=int, default=1)
+    ap.add_argument("--halo-sched", type=int, default=0)
+    ap.add_argument("--halo-unroll", type=int, default=8)
+    ap.add_argument("--overlap-only", action="store_true")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
@@ -56,6 +59,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_tuning("halo.ctas_per_sm", a.halo_ctas)
+    _lib.set_tuning("halo.schedule", a.halo_sched)
+    _lib.set_tuning("halo.unroll", a.halo_unroll)
     csr, bounds, nnz_total = build_rank_block(a.n, a.deg, rank, world, dev, skew=a.skew, p_local=a.p_local, window=a.window,
                                                   scatter=a.scatter)
     plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world)
@@ -73,7 +78,7 @@ def main():
     for transport in (a.transports if world > 1 else ["none"]):
         op = PartitionedSpmm(plan, a.F, dev, transport=transport)
         Y = torch.empty(n_loc, a.F, device=dev)
-        for overlap in ([True, False] if world > 1 else [True]):
+        for overlap in ([True] if (a.overlap_only or world == 1) else [True, False]):
             for _ in range(a.warmup):
                 op.forward(X, out=Y, overlap=overlap)
             torch.cuda.synchronize()
@@ -91,7 +96,7 @@ def main():
             if rank == 0:
                 hal = [int(s[0]) for s in allstats]
                 print(json.dumps({"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F,
-                                  "transport": transport, "overlap": overlap, "halo_ctas": a.halo_ctas, "ms": ms.item(),
+                                  "transport": transport, "overlap": overlap, "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": a.halo_unroll, "ms": ms.item(),
                                   "edges_per_s": nnz_total / ms.item() * 1e3, "p_local": a.p_local, "window": a.window, "scatter": a.scatter, "skew": a.skew,
                                   "halo_rows_max": max(hal), "halo_rows_mean": sum(hal) / world,
                                   "halo_gb_recv_max": max(hal) * a.F * 4 / 1e9,
