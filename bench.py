@@ -9,16 +9,16 @@ Headline workload `sage_reddit` = BASELINE.json configs[2], the config the metri
 on for one B200: GraphSAGE_Pytorch mean aggregator, fanout (25,10), batch 1024, Reddit-shaped
 synthetic graph (232,965 nodes x 602 fp32 features resident in HBM).  One step = one minibatch
 through the aggregation hot path:
-    hop-2 fused gather-mean  [25600 x 10 x 602]   (gnn_gather_reduce_f32, TMA ring)
-    hop-1 fused gather-mean  [ 1024 x 25 x 602]
+    hop-2 fused gather-mean  [25600 x 10 x 602]  } one launch (gnn_gather_reduce_multi_f32,
+    hop-1 fused gather-mean  [ 1024 x 25 x 602]  } TMA ring)
     layer-2 mean             [ 1024 x 25 x 128]   (identity block over the hidden tensor)
 value    = sampled edges aggregated per second, kernels only, inputs resident in HBM.
 e2e      = the same metric through the public drop-in API (CapturedGraphSage over
            GraphSage.forward_sampled): every step copies that step's sampled ids from pinned
            host memory, runs the whole model forward (aggregation kernels + torch matmuls) and
            reads the logits back to the host.
-roofline = the hop-2 kernel: algorithmic bytes n_src*fanout*(4+F*4)+n_src*F*4 per launch over
-           its CUDA-event duration, against the measured HBM peak (MEASURED_PEAKS.json).
+roofline = the gather kernel (both hops): algorithmic bytes sum of n_src*fanout*(4+F*4)+n_src*F*4
+           per launch over its CUDA-event duration, against the measured HBM peak.
 With N>1 every rank runs its own minibatches on its own replica of the table (SURVEY.md §8e:
 "SAGE minibatch: replicas only") -> weak scaling, no data-path collective.
 
@@ -183,10 +183,10 @@ def run_sage_b200(args, rank, world, dev):
         blk = dev_blocks[i % pool]
         if ev is not None:
             ev[0].record()
-        Fn.gather_reduce_raw(table, blk[2], B * f1, f2, "mean", out=out2)
+        # hop-2 and hop-1 gather-means share one launch (same table, different fanouts)
+        Fn.gather_reduce_multi_raw(table, [(blk[2], B * f1, f2), (blk[1], B, f1)], "mean", outs=[out2, out1])
         if ev is not None:
             ev[1].record()
-        Fn.gather_reduce_raw(table, blk[1], B, f1, "mean", out=out1)
         Fn.gather_reduce_raw(hidden1, None, B, f1, "mean", out=out0)
 
     def barrier():
@@ -228,8 +228,9 @@ def run_sage_b200(args, rank, world, dev):
         barrier()
     # the same hop-2 launch with the L2 flushed before every rep (the conservative figure: in the
     # timed region ~22% of the 561 MB table survives in the 126 MB L2 from step to step)
-    k2_cold_ms = cuda_time(lambda: Fn.gather_reduce_raw(table, dev_blocks[0][2], B * f1, f2, "mean", out=out2), 20,
-                           flush_dev=dev)
+    k2_cold_ms = cuda_time(lambda: Fn.gather_reduce_multi_raw(table, [(dev_blocks[0][2], B * f1, f2),
+                                                                     (dev_blocks[0][1], B, f1)], "mean",
+                                                             outs=[out2, out1]), 20, flush_dev=dev)
     # the captured forward must equal the eager drop-in forward on the same ids
     with torch.no_grad():
         eager = model.forward_sampled(table, dev_blocks[(args.warmup + args.steps - 1) % pool])
@@ -241,8 +242,8 @@ def run_sage_b200(args, rank, world, dev):
         ms_total, e2e_ms, k2_ms, k2_cold_ms = t.tolist()
 
     peak, peak_src = hbm_peak()
-    k2_bytes = sage_algorithmic_bytes(B * f1, f2, F)
-    step_bytes = k2_bytes + sage_algorithmic_bytes(B, f1, F) + (B * f1 * H1 * 4 + B * H1 * 4)
+    k2_bytes = sage_algorithmic_bytes(B * f1, f2, F) + sage_algorithmic_bytes(B, f1, F)
+    step_bytes = k2_bytes + (B * f1 * H1 * 4 + B * H1 * 4)
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
     h2d = sum(int(b.numel()) * b.element_size() for b in host_blocks[0])
     d2h = runner.logits_host.numel() * 4
@@ -255,12 +256,13 @@ def run_sage_b200(args, rank, world, dev):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": SAGE_WORKLOAD,
-                   "edges_per_step": SAGE_EDGES, "launches_per_step": 3, "minibatch_pool": pool,
+                   "edges_per_step": SAGE_EDGES, "launches_per_step": 2, "minibatch_pool": pool,
                    "l2_policy": "inputs larger than L2: 561 MB table, ~374 MB distinct rows per step, pool of 8 "
                                 "distinct minibatches cycled",
                    "parallelism": f"replicas x{world} (independent minibatches per rank, no collective)"},
         "hbm_gbs_step": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "sage_tma_kernel<float,1,SUM> hop-2 gather-mean [25600x10x602]",
+        "roofline": {"bound": "hbm", "kernel": "sage_tma_kernel<float,1,SUM>: hop-2 [25600x10x602] + hop-1 [1024x25x602] "
+                                                     "gather-means in one launch",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": k2_bytes, "launch_ms": k2_ms,
                      "l2_flushed": {"launch_ms": k2_cold_ms, "achieved": k2_bytes / (k2_cold_ms * 1e-3) / 1e9,
@@ -268,9 +270,9 @@ def run_sage_b200(args, rank, world, dev):
                                     "note": "same launch, 256 MB written between reps; the timed region does not "
                                             "flush (inputs larger than L2) so ~1/5 of the table stays L2-resident "
                                             "and the no-reuse byte model overcounts there"},
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                     # (profiles/r01_sage_ncu_full.md): 559.3 MB + 56.6 MB per launch
-                     "traffic": 615.8e6},
+                     # dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture (profiles/README.md):
+                     # hop-2 559.3 + 56.6 MB, hop-1 61.1 + 1.1 MB (captured as separate launches of this kernel)
+                     "traffic": 678.0e6},
         "e2e": {"value": world * args.steps * SAGE_EDGES / (e2e_ms * 1e-3), "unit": "edges/s",
                 "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "graphneuralnetwork_b200.layers.CapturedGraphSage(GraphSage.forward_sampled): pinned ids "

@@ -4,12 +4,14 @@
 //   GraphSAGE_Pytorch/models/Aggregator.py:19-24 mean / sum / max over the fanout axis
 //   GraphSAGE/graph_utils.py:6 + GraphSAGE.py:47-49  torch.embedding + torch.mean
 //
-// TMA path (sm_100a): a persistent CTA owns source nodes blockIdx.x, +grid, ...; one
-// producer warp reads the sampled ids and issues one cp.async.bulk (TMA 1-D bulk copy)
-// per gathered feature row into a shared-memory ring, completing on an mbarrier; five
-// consumer warps add the staged rows from shared memory (LDS.128) in fanout order and
-// write the reduced row once.  No feature row touches a register before it is reduced,
-// and ~200 KB of row fetches are in flight per SM.
+// TMA path (sm_100a): persistent CTAs (4 per SM) take source nodes blockIdx.x, +grid, ...;
+// one producer warp reads the sampled ids (next chunk prefetched) and issues one
+// cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) per gathered feature row into a
+// shared-memory ring, completing on an mbarrier; five consumer warps add the staged rows from
+// shared memory (LDS.128) in fanout order and write the reduced row once.  No feature row
+// touches a register before it is reduced.  Up to 4 index blocks with different fanouts (the
+// hops of one minibatch: GraphSage.py:24-27 runs every hop through the same layer) share ONE
+// launch, so the short hop-1 block rides in the shadow of the long hop-2 block.
 // Vector-load path: the row-parallel kernel of rowreduce.cuh with an implicit CSR
 // (rowptr = i*fanout), used when rows are not 16-byte aligned or too short for TMA.
 #include "rowreduce.cuh"
@@ -21,25 +23,28 @@ namespace {
 constexpr int kConsumerWarps = 5;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kSageThreads = 32 + kConsumerThreads;
+constexpr int kMaxBlocks = 4;
 
 template <typename T>
 struct SageArgs {
   const T* table;
   int64_t ld;
-  const int32_t* idx32;
-  const int64_t* idx64;
-  int64_t n_src;
-  int32_t fanout;
   int32_t F;
-  float scale;
-  T* out;
-  int64_t ldo;
-  int32_t* argmax;
-  int32_t row_bytes;  // bytes copied per row (multiple of 16)
-  int32_t kc;         // rows per ring stage
+  int32_t n_blocks;
+  const int32_t* idx32[kMaxBlocks];
+  const int64_t* idx64[kMaxBlocks];
+  int64_t src_off[kMaxBlocks + 1];  // cumulative source counts; a CTA strides over the union
+  int32_t fanout[kMaxBlocks];
+  int32_t kc[kMaxBlocks];            // rows per ring stage for this block
+  float scale[kMaxBlocks];
+  T* out[kMaxBlocks];
+  int64_t ldo[kMaxBlocks];
+  int32_t* argmax[kMaxBlocks];
+  int32_t out_vec16[kMaxBlocks];     // output rows can take 16-byte stores
+  int32_t row_bytes;                 // bytes copied per row (multiple of 16)
+  int32_t stage_rows;                // ring stage capacity in rows (max kc)
   int32_t stages;
-  int32_t nvec;       // 16-byte vectors per row
-  int32_t out_vec16;  // output rows can take 16-byte stores
+  int32_t nvec;                      // 16-byte vectors per row
 };
 
 template <typename T>
@@ -60,12 +65,37 @@ struct Vec16<__nv_bfloat16> {
   }
 };
 
+// position of a CTA in its work list: (global source g -> block b, source within block, chunk)
+struct Cursor {
+  int64_t g;
+  int64_t src;
+  int b, fan, kc, c0;
+};
+template <typename T>
+__device__ __forceinline__ void cursor_set(Cursor& c, const SageArgs<T>& a, int64_t g) {
+  c.g = g;
+  c.c0 = 0;
+  if (g < a.src_off[a.n_blocks]) {
+    int b = 0;
+    while (b + 1 < a.n_blocks && g >= a.src_off[b + 1]) ++b;
+    c.b = b;
+    c.src = g - a.src_off[b];
+    c.fan = a.fanout[b];
+    c.kc = a.kc[b];
+  }
+}
+template <typename T>
+__device__ __forceinline__ void cursor_next(Cursor& c, const SageArgs<T>& a) {
+  c.c0 += c.kc;
+  if (c.c0 >= c.fan) cursor_set(c, a, c.g + gridDim.x);
+}
+
 template <typename T, int NV, int OP>
 __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T> a) {
   constexpr int E = Vec16<T>::E;
   extern __shared__ __align__(128) unsigned char smem[];
   const int S = a.stages;
-  const int stage_bytes = a.kc * a.row_bytes;
+  const int stage_bytes = a.stage_rows * a.row_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty = full + S;
   uint32_t* mask = reinterpret_cast<uint32_t*>(empty + S);
@@ -80,28 +110,27 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
     mbar_fence_init();
   }
   __syncthreads();
-
-  const int nchunk = (a.fanout + a.kc - 1) / a.kc;
-  const int64_t my_src = (a.n_src > (int64_t)blockIdx.x) ? (a.n_src - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t total = my_src * nchunk;
+  const int64_t total_src = a.src_off[a.n_blocks];
 
   if (warp == 0) {
     // ===== producer: sampled ids -> one bulk copy per gathered row =====
-    auto load_id = [&](int64_t it) -> int64_t {
-      if (it >= total) return -1;
-      const int64_t src = blockIdx.x + (it / nchunk) * (int64_t)gridDim.x;
-      const int c0 = (int)(it % nchunk) * a.kc;
-      const int rows = min(a.kc, a.fanout - c0);
+    auto load_id = [&](const Cursor& c) -> int64_t {
+      if (c.g >= total_src) return -1;
+      const int rows = min(c.kc, c.fan - c.c0);
       if (lane >= rows) return -1;
-      const int64_t p = src * a.fanout + c0 + lane;
-      if (a.idx32) return (int64_t)__ldg(a.idx32 + p);
-      if (a.idx64) return __ldg(a.idx64 + p);
-      return p;
+      const int64_t p = c.src * c.fan + c.c0 + lane;
+      if (a.idx32[c.b]) return (int64_t)__ldg(a.idx32[c.b] + p);
+      if (a.idx64[c.b]) return __ldg(a.idx64[c.b] + p);
+      return p;  // identity block
     };
-    int64_t r_next = load_id(0);
-    for (int64_t it = 0; it < total; ++it) {
+    Cursor cur, nxt;
+    cursor_set(cur, a, blockIdx.x);
+    nxt = cur;
+    if (nxt.g < total_src) cursor_next(nxt, a);
+    int64_t r_next = load_id(cur);
+    for (int64_t it = 0; cur.g < total_src; ++it) {
       const int64_t r = r_next;
-      r_next = load_id(it + 1);  // prefetch the next chunk's ids while this one is issued
+      r_next = load_id(nxt);  // prefetch the next chunk's ids while this one is issued
       const int stage = (int)(it % S);
       const uint32_t par = (uint32_t)((it / S) & 1);
       mbar_wait(empty + stage, par ^ 1u);
@@ -115,6 +144,8 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
       if (valid)
         bulk_g2s(smem + (size_t)stage * stage_bytes + (size_t)lane * a.row_bytes, a.table + r * a.ld,
                  (uint32_t)a.row_bytes, full + stage);
+      cur = nxt;
+      if (nxt.g < total_src) cursor_next(nxt, a);
     }
   } else {
     // ===== consumers: reduce the staged rows in fanout order =====
@@ -131,12 +162,13 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
         }
     };
     reset();
-    for (int64_t it = 0; it < total; ++it) {
+    Cursor cur;
+    cursor_set(cur, a, blockIdx.x);
+    for (int64_t it = 0; cur.g < total_src; ++it) {
       const int stage = (int)(it % S);
       const uint32_t par = (uint32_t)((it / S) & 1);
-      const int chunk = (int)(it % nchunk);
-      const int c0 = chunk * a.kc;
-      const int rows = min(a.kc, a.fanout - c0);
+      const int c0 = cur.c0;
+      const int rows = min(cur.kc, cur.fan - c0);
       mbar_wait(full + stage, par);
       const unsigned m = mask[stage];
       const unsigned char* sb = smem + (size_t)stage * stage_bytes;
@@ -166,18 +198,19 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + stage);
-      if (chunk == nchunk - 1) {
-        const int64_t src = blockIdx.x + (it / nchunk) * (int64_t)gridDim.x;
-        T* orow = a.out + src * a.ldo;
+      if (c0 + cur.kc >= cur.fan) {  // last chunk of this source: write the reduced row
+        const int b = cur.b;
+        T* orow = a.out[b] + cur.src * a.ldo[b];
+        const float scale = a.scale[b];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int vi = t + v * kConsumerThreads;
           if (vi < a.nvec) {
             float o[E];
 #pragma unroll
-            for (int i = 0; i < E; ++i) o[i] = (OP == GNN_REDUCE_MAX) ? acc[v][i] : acc[v][i] * a.scale;
+            for (int i = 0; i < E; ++i) o[i] = (OP == GNN_REDUCE_MAX) ? acc[v][i] : acc[v][i] * scale;
             const int col0 = vi * E;
-            if (a.out_vec16) {
+            if (a.out_vec16[b]) {
               VecIO<T, E>::store(orow + col0, o);
             } else {
 #pragma unroll
@@ -187,15 +220,16 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
                   VecIO<T, 1>::store(orow + col0 + i, o1);
                 }
             }
-            if (OP == GNN_REDUCE_MAX && a.argmax) {
+            if (OP == GNN_REDUCE_MAX && a.argmax[b]) {
 #pragma unroll
               for (int i = 0; i < E; ++i)
-                if (col0 + i < a.F) a.argmax[src * a.ldo + col0 + i] = best[v][i];
+                if (col0 + i < a.F) a.argmax[b][cur.src * a.ldo[b] + col0 + i] = best[v][i];
             }
           }
         }
         reset();
       }
+      cursor_next(cur, a);
     }
   }
 }
@@ -228,20 +262,38 @@ int launch_tma(const SageArgs<T>& a, size_t smem_bytes, int grid, cudaStream_t s
 }
 
 template <typename T>
-int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, const void* idx, int idx_bits, int64_t n_src,
-                       int32_t fanout, int32_t F, int reduce, T* out, int64_t ldo, int32_t* argmax, cudaStream_t st) {
-  GNN_REQUIRE(n_src >= 0 && fanout >= 0 && F >= 0, GNN_ERR_BAD_ARG, "negative size");
+struct GatherBlock {
+  const void* idx;
+  int idx_bits;
+  int64_t n_src;
+  int32_t fanout;
+  T* out;
+  int64_t ldo;
+  int32_t* argmax;
+};
+
+template <typename T>
+int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, int32_t F, int reduce,
+                       const GatherBlock<T>* blocks, int n_blocks, cudaStream_t st) {
+  GNN_REQUIRE(F >= 0 && n_blocks >= 0 && n_blocks <= kMaxBlocks, GNN_ERR_BAD_ARG, "bad size (F=%d, blocks=%d, max %d)",
+              F, n_blocks, kMaxBlocks);
   GNN_REQUIRE(reduce == GNN_REDUCE_MEAN || reduce == GNN_REDUCE_SUM || reduce == GNN_REDUCE_MAX, GNN_ERR_BAD_ARG,
               "unknown reduce %d (GraphSAGE_Pytorch/models/Aggregator.py:26 raises ValueError)", reduce);
-  if (n_src == 0 || F == 0) return GNN_OK;
-  GNN_REQUIRE(fanout > 0, GNN_ERR_BAD_ARG, "fanout must be positive");
-  GNN_REQUIRE(table && out, GNN_ERR_BAD_ARG, "null table/out");
-  GNN_REQUIRE(idx == nullptr || idx_bits == 32 || idx_bits == 64, GNN_ERR_BAD_ARG, "idx_bits must be 32 or 64");
-  GNN_REQUIRE(ld >= F && ldo >= F, GNN_ERR_BAD_ARG, "leading dimension smaller than F");
   GNN_REQUIRE(n_table_rows < 0x7fffffffLL, GNN_ERR_UNSUPPORTED, "table rows do not fit int32");
-  GNN_REQUIRE(idx != nullptr || n_src * (int64_t)fanout <= n_table_rows, GNN_ERR_BAD_ARG,
-              "identity block needs n_src*fanout <= n_table_rows");
-  const float scale = (reduce == GNN_REDUCE_MEAN) ? 1.0f / (float)fanout : 1.0f;
+  int64_t total_src = 0;
+  for (int b = 0; b < n_blocks; ++b) {
+    const GatherBlock<T>& k = blocks[b];
+    GNN_REQUIRE(k.n_src >= 0 && k.fanout >= 0, GNN_ERR_BAD_ARG, "negative size");
+    if (k.n_src == 0 || F == 0) continue;
+    GNN_REQUIRE(k.fanout > 0, GNN_ERR_BAD_ARG, "fanout must be positive");
+    GNN_REQUIRE(table && k.out, GNN_ERR_BAD_ARG, "null table/out");
+    GNN_REQUIRE(k.idx == nullptr || k.idx_bits == 32 || k.idx_bits == 64, GNN_ERR_BAD_ARG, "idx_bits must be 32 or 64");
+    GNN_REQUIRE(ld >= F && k.ldo >= F, GNN_ERR_BAD_ARG, "leading dimension smaller than F");
+    GNN_REQUIRE(k.idx != nullptr || k.n_src * (int64_t)k.fanout <= n_table_rows, GNN_ERR_BAD_ARG,
+                "identity block needs n_src*fanout <= n_table_rows");
+    total_src += k.n_src;
+  }
+  if (total_src == 0 || F == 0) return GNN_OK;
 
   const int esz = (int)sizeof(T);
   const int row_bytes = (int)round_up((size_t)F * esz, 16);
@@ -251,62 +303,86 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, const v
     SageArgs<T> a{};
     a.table = table;
     a.ld = ld;
-    a.idx32 = (idx && idx_bits == 32) ? (const int32_t*)idx : nullptr;
-    a.idx64 = (idx && idx_bits == 64) ? (const int64_t*)idx : nullptr;
-    a.n_src = n_src;
-    a.fanout = fanout;
     a.F = F;
-    a.scale = scale;
-    a.out = out;
-    a.ldo = ldo;
-    a.argmax = (reduce == GNN_REDUCE_MAX) ? argmax : nullptr;
     a.row_bytes = row_bytes;
     a.nvec = row_bytes / 16;
     const int E = 16 / esz;
-    a.out_vec16 = aligned_to(out, 16) && ((ldo * esz) % 16 == 0) && ((int64_t)a.nvec * E <= ldo);
-    int kc = tuning("sage.chunk_bytes", 12288) / row_bytes;
-    kc = kc < 1 ? 1 : kc;
-    kc = kc > 32 ? 32 : kc;
-    kc = kc > fanout ? fanout : kc;
-    const int nchunk = (fanout + kc - 1) / kc;
-    kc = (fanout + nchunk - 1) / nchunk;  // balance the chunks of one source
+    int kc0 = tuning("sage.chunk_bytes", 12288) / row_bytes;
+    kc0 = kc0 < 1 ? 1 : kc0;
+    kc0 = kc0 > 32 ? 32 : kc0;
     const size_t budget = (size_t)tuning("sage.smem_kb", 48) * 1024;
-    int stages = (int)(budget / ((size_t)kc * row_bytes));
-    while (stages < 2 && kc > 1) {
-      kc = (kc + 1) / 2;
-      stages = (int)(budget / ((size_t)kc * row_bytes));
+    while (kc0 > 1 && budget / ((size_t)kc0 * row_bytes) < 2) kc0 = (kc0 + 1) / 2;
+    int nb = 0, stage_rows = 1;
+    a.src_off[0] = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+      const GatherBlock<T>& k = blocks[b];
+      if (k.n_src == 0) continue;
+      a.idx32[nb] = (k.idx && k.idx_bits == 32) ? (const int32_t*)k.idx : nullptr;
+      a.idx64[nb] = (k.idx && k.idx_bits == 64) ? (const int64_t*)k.idx : nullptr;
+      a.fanout[nb] = k.fanout;
+      int kc = kc0 > k.fanout ? k.fanout : kc0;
+      const int nchunk = (k.fanout + kc - 1) / kc;
+      kc = (k.fanout + nchunk - 1) / nchunk;  // balance the chunks of one source
+      a.kc[nb] = kc;
+      stage_rows = kc > stage_rows ? kc : stage_rows;
+      a.scale[nb] = (reduce == GNN_REDUCE_MEAN) ? 1.0f / (float)k.fanout : 1.0f;
+      a.out[nb] = k.out;
+      a.ldo[nb] = k.ldo;
+      a.argmax[nb] = (reduce == GNN_REDUCE_MAX) ? k.argmax : nullptr;
+      a.out_vec16[nb] = aligned_to(k.out, 16) && ((k.ldo * esz) % 16 == 0) && ((int64_t)a.nvec * E <= k.ldo);
+      a.src_off[nb + 1] = a.src_off[nb] + k.n_src;
+      ++nb;
     }
+    a.n_blocks = nb;
+    a.stage_rows = stage_rows;
+    int stages = (int)(budget / ((size_t)stage_rows * row_bytes));
     stages = stages > 8 ? 8 : stages;
     GNN_REQUIRE(stages >= 2, GNN_ERR_UNSUPPORTED, "row of %d bytes does not fit the shared-memory ring", row_bytes);
-    a.kc = kc;
     a.stages = stages;
-    const size_t smem_bytes = (size_t)stages * kc * row_bytes + (size_t)stages * (16 + 4) + 16;
+    const size_t smem_bytes = (size_t)stages * stage_rows * row_bytes + (size_t)stages * (16 + 4) + 16;
     int64_t grid = (int64_t)num_sms() * tuning("sage.ctas_per_sm", 4);
-    grid = grid > n_src ? n_src : grid;
+    grid = grid > total_src ? total_src : grid;
     switch (reduce) {
       case GNN_REDUCE_MAX: return launch_tma<T, GNN_REDUCE_MAX>(a, smem_bytes, (int)grid, st);
       default: return launch_tma<T, GNN_REDUCE_SUM>(a, smem_bytes, (int)grid, st);
     }
   }
 
-  RowArgs<T> r{};
-  r.rowptr = nullptr;
-  r.fanout = fanout;
-  r.col32 = (idx && idx_bits == 32) ? (const int32_t*)idx : nullptr;
-  r.col64 = (idx && idx_bits == 64) ? (const int64_t*)idx : nullptr;
-  r.val = nullptr;
-  r.src_div = 0;
-  r.scale = scale;
-  r.X = table;
-  r.ldx = ld;
-  r.Y = out;
-  r.ldy = ldo;
-  r.n_rows = n_src;
-  r.F = F;
-  r.skip_deg_gt = 0;
-  r.argmax = (reduce == GNN_REDUCE_MAX) ? argmax : nullptr;
-  if (reduce == GNN_REDUCE_MAX) return launch_row_reduce<T, 1>(r, st);
-  return launch_row_reduce<T, 0>(r, st);
+  for (int b = 0; b < n_blocks; ++b) {
+    const GatherBlock<T>& k = blocks[b];
+    if (k.n_src == 0) continue;
+    RowArgs<T> r{};
+    r.rowptr = nullptr;
+    r.fanout = k.fanout;
+    r.col32 = (k.idx && k.idx_bits == 32) ? (const int32_t*)k.idx : nullptr;
+    r.col64 = (k.idx && k.idx_bits == 64) ? (const int64_t*)k.idx : nullptr;
+    r.val = nullptr;
+    r.src_div = 0;
+    r.scale = (reduce == GNN_REDUCE_MEAN) ? 1.0f / (float)k.fanout : 1.0f;
+    r.X = table;
+    r.ldx = ld;
+    r.Y = k.out;
+    r.ldy = k.ldo;
+    r.n_rows = k.n_src;
+    r.F = F;
+    r.skip_deg_gt = 0;
+    r.argmax = (reduce == GNN_REDUCE_MAX) ? k.argmax : nullptr;
+    const int rc = (reduce == GNN_REDUCE_MAX) ? launch_row_reduce<T, 1>(r, st) : launch_row_reduce<T, 0>(r, st);
+    if (rc != GNN_OK) return rc;
+  }
+  return GNN_OK;
+}
+
+template <typename T>
+int gather_reduce_multi(const T* table, int64_t ld, int64_t n_table_rows, int32_t F, int reduce, int32_t n_blocks,
+                        const void* const* idx, int idx_bits, const int64_t* n_src, const int32_t* fanout,
+                        void* const* out, const int64_t* ld_out, cudaStream_t st) {
+  GNN_REQUIRE(n_blocks >= 0 && n_blocks <= kMaxBlocks, GNN_ERR_UNSUPPORTED, "at most %d blocks per launch", kMaxBlocks);
+  GNN_REQUIRE(n_blocks == 0 || (idx && n_src && fanout && out && ld_out), GNN_ERR_BAD_ARG, "null block array");
+  GatherBlock<T> blocks[kMaxBlocks];
+  for (int b = 0; b < n_blocks; ++b)
+    blocks[b] = GatherBlock<T>{idx[b], idx_bits, n_src[b], fanout[b], (T*)out[b], ld_out[b], nullptr};
+  return gather_reduce_impl<T>(table, ld, n_table_rows, F, reduce, blocks, n_blocks, st);
 }
 
 __global__ void __launch_bounds__(256) bwd_dense_kernel(const float* __restrict__ d_out, int64_t ld,
@@ -333,16 +409,33 @@ extern "C" {
 int gnn_gather_reduce_f32(const float* table, int64_t ld_table, int64_t n_table_rows, const void* idx, int idx_bits,
                           int64_t n_src, int32_t fanout, int32_t F, int reduce, float* out, int64_t ld_out,
                           int32_t* argmax, gnn_stream_t stream) {
-  return gather_reduce_impl<float>(table, ld_table, n_table_rows, idx, idx_bits, n_src, fanout, F, reduce, out, ld_out,
-                                   argmax, (cudaStream_t)stream);
+  GatherBlock<float> blk{idx, idx_bits, n_src, fanout, out, ld_out, argmax};
+  return gather_reduce_impl<float>(table, ld_table, n_table_rows, F, reduce, &blk, 1, (cudaStream_t)stream);
 }
 
 int gnn_gather_reduce_bf16(const void* table, int64_t ld_table, int64_t n_table_rows, const void* idx, int idx_bits,
                            int64_t n_src, int32_t fanout, int32_t F, int reduce, void* out, int64_t ld_out,
                            int32_t* argmax, gnn_stream_t stream) {
-  return gather_reduce_impl<__nv_bfloat16>((const __nv_bfloat16*)table, ld_table, n_table_rows, idx, idx_bits, n_src,
-                                           fanout, F, reduce, (__nv_bfloat16*)out, ld_out, argmax,
+  GatherBlock<__nv_bfloat16> blk{idx, idx_bits, n_src, fanout, (__nv_bfloat16*)out, ld_out, argmax};
+  return gather_reduce_impl<__nv_bfloat16>((const __nv_bfloat16*)table, ld_table, n_table_rows, F, reduce, &blk, 1,
                                            (cudaStream_t)stream);
+}
+
+int gnn_gather_reduce_multi_f32(const float* table, int64_t ld_table, int64_t n_table_rows, int32_t F, int reduce,
+                                int32_t n_blocks, const void* const* idx_host, int idx_bits,
+                                const int64_t* n_src_host, const int32_t* fanout_host, void* const* out_host,
+                                const int64_t* ld_out_host, gnn_stream_t stream) {
+  return gather_reduce_multi<float>(table, ld_table, n_table_rows, F, reduce, n_blocks, idx_host, idx_bits, n_src_host,
+                                    fanout_host, out_host, ld_out_host, (cudaStream_t)stream);
+}
+
+int gnn_gather_reduce_multi_bf16(const void* table, int64_t ld_table, int64_t n_table_rows, int32_t F, int reduce,
+                                 int32_t n_blocks, const void* const* idx_host, int idx_bits,
+                                 const int64_t* n_src_host, const int32_t* fanout_host, void* const* out_host,
+                                 const int64_t* ld_out_host, gnn_stream_t stream) {
+  return gather_reduce_multi<__nv_bfloat16>((const __nv_bfloat16*)table, ld_table, n_table_rows, F, reduce, n_blocks,
+                                            idx_host, idx_bits, n_src_host, fanout_host, out_host, ld_out_host,
+                                            (cudaStream_t)stream);
 }
 
 int gnn_gather_reduce_bwd_f32(const int64_t* rowptr_t, const int32_t* pos_t, int64_t n_table_rows, int32_t fanout,

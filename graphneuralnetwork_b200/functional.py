@@ -128,6 +128,46 @@ def gather_reduce_raw(table: torch.Tensor, idx: Optional[torch.Tensor], n_src: i
     return out
 
 
+def gather_reduce_multi_raw(table: torch.Tensor, blocks, reduce: str = "mean", outs=None):
+    """Several fixed-fanout id blocks over the SAME table in ONE launch
+    (gnn_gather_reduce_multi_*): `blocks` = [(idx, n_src, fanout), ...] (idx=None: identity).
+    The hops of a GraphSAGE minibatch (GraphSage.py:24-27) are such a set.  No autograd."""
+    import ctypes as C
+    if reduce not in _lib.REDUCE:
+        raise ValueError("Unknown aggr type, expected sum, max, or mean, but got {}".format(reduce))
+    _require_cuda(table, *[b[0] for b in blocks])
+    lib = _lib.load()
+    table = _rowmajor(table)
+    N, F = table.shape
+    nb = len(blocks)
+    idxs, bits = [], None
+    for idx, n_src, fanout in blocks:
+        if idx is not None:
+            idx = idx.contiguous().view(-1)
+            if idx.dtype not in (torch.int32, torch.int64):
+                idx = idx.to(torch.int64)
+            b = 32 if idx.dtype == torch.int32 else 64
+            if bits is not None and b != bits:
+                idx, b = idx.to(torch.int64 if bits == 64 else torch.int32), bits
+            bits = b
+            if idx.numel() != n_src * fanout:
+                raise _lib.GnnError(f"index block has {idx.numel()} ids, expected n_src*fanout = {n_src * fanout}")
+        idxs.append(idx)
+    if outs is None:
+        outs = [_padded_empty(n_src, F, table.dtype, table.device) for _, n_src, _ in blocks]
+    fn = {torch.float32: lib.gnn_gather_reduce_multi_f32, torch.bfloat16: lib.gnn_gather_reduce_multi_bf16}.get(table.dtype)
+    if fn is None:
+        raise _lib.GnnError(f"gather_reduce: unsupported dtype {table.dtype}")
+    idx_arr = (C.c_void_p * nb)(*[_p(i) for i in idxs])
+    nsrc_arr = (C.c_int64 * nb)(*[int(b[1]) for b in blocks])
+    fan_arr = (C.c_int32 * nb)(*[int(b[2]) for b in blocks])
+    out_arr = (C.c_void_p * nb)(*[_p(o) for o in outs])
+    ldo_arr = (C.c_int64 * nb)(*[_ld(o) for o in outs])
+    _lib.check(fn(_p(table), _ld(table), N, F, _lib.REDUCE[reduce], nb, idx_arr, bits or 64, nsrc_arr, fan_arr, out_arr,
+                  ldo_arr, _stream_ptr()), "gnn_gather_reduce_multi")
+    return outs
+
+
 class _GatherReduceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table, idx, n_src, fanout, reduce):

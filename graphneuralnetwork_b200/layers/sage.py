@@ -15,7 +15,7 @@ import torch
 from torch import nn
 import torch.nn.functional as F
 
-from ..functional import gather_reduce, pad_table
+from ..functional import gather_reduce, gather_reduce_multi_raw, pad_table
 
 
 class SampledBlock:
@@ -52,7 +52,10 @@ class NeighborAggregator(nn.Module):
         return gather_reduce(flat, None, n_src, fanout, self.aggr_method)
 
     def forward(self, neighbor_feature):
-        aggr_neighbor = self.aggregate(neighbor_feature)
+        # a tensor that is already [n_src, F] is the aggregate itself (the fused multi-hop launch of
+        # GraphSage.forward_sampled hands those in)
+        aggr_neighbor = neighbor_feature if torch.is_tensor(neighbor_feature) and neighbor_feature.dim() == 2 \
+            else self.aggregate(neighbor_feature)
         neighbor_hidden = torch.matmul(aggr_neighbor, self.weight)
         if self.use_bias:
             neighbor_hidden += self.bias
@@ -135,10 +138,17 @@ class GraphSage(nn.Module):
         assert len(node_id_blocks) == L + 1
         gcn = self.gcn[0]
         hidden = []
+        fused = (not (torch.is_grad_enabled() and table.requires_grad)) and L <= 4 \
+            and gcn.aggr_neighbor_method in ("mean", "sum", "max")
+        if fused:
+            # every hop of layer 0 aggregates from the same table: ONE launch for all of them
+            blocks = [(node_id_blocks[hop + 1], node_id_blocks[hop].numel(), self.num_neighbors_list[hop])
+                      for hop in range(L)]
+            aggs = gather_reduce_multi_raw(table, blocks, gcn.aggr_neighbor_method)
         for hop in range(L):
             src = table.index_select(0, node_id_blocks[hop].to(torch.int64)) if node_id_blocks[hop].dtype != torch.int64 \
                 else table.index_select(0, node_id_blocks[hop])
-            blk = SampledBlock(table, node_id_blocks[hop + 1], self.num_neighbors_list[hop])
+            blk = aggs[hop] if fused else SampledBlock(table, node_id_blocks[hop + 1], self.num_neighbors_list[hop])
             hidden.append(gcn(src, blk))
         for l in range(1, L):
             next_hidden = []

@@ -160,6 +160,18 @@ int gnn_gather_reduce_f32(const float* table, int64_t ld_table, int64_t n_table_
 int gnn_gather_reduce_bf16(const void* table, int64_t ld_table, int64_t n_table_rows,
                            const void* idx, int idx_bits, int64_t n_src, int32_t fanout, int32_t F,
                            int reduce, void* out, int64_t ld_out, int32_t* argmax, gnn_stream_t stream);
+/* Up to 4 index blocks over the SAME table in one launch (the hops of one minibatch:
+ * GraphSAGE_Pytorch/models/GraphSage.py:24-27 sends every hop through the same layer).  The
+ * *_host arrays are host arrays of n_blocks entries: device id pointers (nullable = identity),
+ * source counts, fanouts, device output pointers and their leading dimensions. */
+int gnn_gather_reduce_multi_f32(const float* table, int64_t ld_table, int64_t n_table_rows, int32_t F, int reduce,
+                                int32_t n_blocks, const void* const* idx_host, int idx_bits,
+                                const int64_t* n_src_host, const int32_t* fanout_host,
+                                void* const* out_host, const int64_t* ld_out_host, gnn_stream_t stream);
+int gnn_gather_reduce_multi_bf16(const void* table, int64_t ld_table, int64_t n_table_rows, int32_t F, int reduce,
+                                 int32_t n_blocks, const void* const* idx_host, int idx_bits,
+                                 const int64_t* n_src_host, const int32_t* fanout_host,
+                                 void* const* out_host, const int64_t* ld_out_host, gnn_stream_t stream);
 /* Backward of mean/sum into the table: dTable[r,:] = scale * sum_{p: idx[p]==r} dOut[p/fanout,:]
  * walking the gnn_index_block_transpose structure (ordered, no atomics). */
 int gnn_gather_reduce_bwd_f32(const int64_t* rowptr_t, const int32_t* pos_t, int64_t n_table_rows,

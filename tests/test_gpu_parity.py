@@ -251,6 +251,28 @@ def test_gather_reduce_paths_agree_bitwise(lib):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("reduce", ["mean", "max"])
+def test_gather_reduce_multi_block_launch(lib, dtype, reduce):
+    """The hops of a minibatch (different fanouts) in one launch == one launch per hop, bit for bit."""
+    rng = np.random.default_rng(11)
+    table = Fn.pad_table(cuda(rng.standard_normal((5000, 602)).astype(np.float32)).to(dtype))
+    blocks = [(cuda(rng.integers(0, 5000, 1500 * 10)).to(torch.int32), 1500, 10),
+              (cuda(rng.integers(0, 5000, 64 * 25)).to(torch.int32), 64, 25),
+              (cuda(rng.integers(0, 5000, 7 * 1)).to(torch.int32), 7, 1),
+              (None, 100, 33)]
+    outs = Fn.gather_reduce_multi_raw(table, blocks, reduce)
+    for (idx, n_src, fanout), o in zip(blocks, outs):
+        single = Fn.gather_reduce_raw(table, idx, n_src, fanout, reduce)
+        assert torch.equal(o, single)
+    ref = osage.aggregate(table.float().cpu()[blocks[1][0].long().cpu()].view(64, 25, 602), reduce).numpy()
+    assert rel_err(outs[1].float().cpu().numpy(), ref) < (TOL32 if dtype == torch.float32 else TOLBF)
+    # unaligned table -> per-block vector-load launches behind the same entry point
+    raw = cuda(rng.standard_normal((5000, 602)).astype(np.float32))
+    outs2 = Fn.gather_reduce_multi_raw(raw, blocks[:2], "mean")
+    assert rel_err(outs2[0].cpu().numpy(), raw.cpu()[blocks[0][0].long().cpu()].view(1500, 10, 602).mean(1).numpy()) < TOL32
+
+
 def test_gather_reduce_identity_block_and_skips(lib):
     rng = np.random.default_rng(1)
     n_src, fanout, F = 300, 25, 128
