@@ -42,7 +42,8 @@ static std::map<std::string, int>& tune_map() {
       {"spmm.chunk", 8192},      // edges per long-row chunk
       {"spmm.unroll", 0},        // 0 = heuristic
       {"gat.stage_edges", 128},  // logits staged per warp pass
-      {"gat.coop_min_avg_deg", 48},  // nnz/n at which a whole CTA (not a warp) takes a row
+      {"gat.coop_min_avg_deg", 256},  // nnz/n at which every row gets a whole CTA
+      {"gat.long_row", 1024},        // rows above this get a CTA in the otherwise warp-per-row schedule
       {"halo.ctas_per_sm", 1},
       {"halo.schedule", 0},      // 0 rotated segments, 1 warps interleaved over peers
       {"halo.unroll", 4},        // rows in flight per warp of the push kernel   // footprint of the NVLink push kernel (the rest of the SM runs the SpMM)

@@ -55,7 +55,13 @@ struct GatArgs {
   int64_t ld_dwh;
   float* d_s;
   float* d_t;
+  // schedule: the warp-per-row launch leaves rows longer than skip_deg_gt to the CTA-per-row
+  // launch, which walks row_list (nullable: row = blockIdx.x)
+  const int64_t* row_list;
+  int64_t skip_deg_gt;
 };
+
+__device__ __forceinline__ bool aligned_to_dev(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 __device__ __forceinline__ float act_elu(float x, int elu) {
   if (elu >= 1) x = elu1(x);
@@ -64,24 +70,38 @@ __device__ __forceinline__ float act_elu(float x, int elu) {
 }
 
 // floats of shared memory per warp for the staged chunk
-__host__ __device__ inline int gat_warp_floats(int SE, int H, int HF) { return SE * H + SE + 128 + HF; }
+__host__ __device__ inline int gat_warp_floats(int SE, int H, int HF) { return SE * H + SE + 160 + HF; }
 
-template <int CPL, int W>
-__global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a) {
+// W  = warps that share one row: 1 -> one warp per row (4 rows per CTA); 4 / 16 -> one CTA of W
+//      warps per row, the warps take alternate SE-edge chunks and merge (max, sum, acc) in warp order.
+// HT = compile-time head count (1, 8; must divide 32) or 0 for the generic run-time H.  With HT known
+//      the per-lane head of phase B/B2 is fixed (lane % HT), t rows are loaded as vectors, the row sum
+//      is reduced once per chunk instead of once per edge, and all index arithmetic folds away
+//      (the generic path executed 79 warp instructions per edge, ncu profiles/r01_prof_gat_fwd_raw.csv).
+template <int W>
+struct GatBlock {
+  static constexpr int kWarps = (W == 1) ? kGatWarps : W;
+};
+
+template <int CPL, int W, int HT>
+__global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const GatArgs a) {
+  constexpr int BW = GatBlock<W>::kWarps;
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp : (int64_t)blockIdx.x;
+  const int64_t i = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp
+                             : (a.row_list ? __ldg(a.row_list + blockIdx.x) : (int64_t)blockIdx.x);
   const int wsub = (W == 1) ? 0 : warp;
   if (W == 1 && i >= a.n) return;  // warp-uniform; the W == 1 schedule has no block-wide barrier
-  const int H = a.H, Hp = a.Hp, SE = a.SE;
+  const int H = HT ? HT : a.H, Hp = HT ? HT : a.Hp, SE = a.SE;
   const int PW = gat_warp_floats(SE, H, a.HF);
   float* logit = sm + (size_t)warp * PW;
   int* cols = reinterpret_cast<int*>(logit + SE * H);
-  float* mh = reinterpret_cast<float*>(cols + SE);
-  float* sc = mh + 32;
-  float* marr = sm + (size_t)kGatWarps * PW;      // [W][32]
-  float* larr = marr + kGatWarps * 32;            // [W][CPL*32]
-  float* aarr = larr + kGatWarps * CPL * 32;      // [W][CPL*32]
+  float* mh = reinterpret_cast<float*>(cols + SE);  // [32] running max per head
+  float* sc = mh + 32;                              // [32] rescale factor of this chunk
+  float* lh = sc + 32;                              // [32] running sum per head (HT path)
+  float* marr = sm + (size_t)BW * PW;               // [BW][32]
+  float* larr = marr + BW * 32;                     // [BW][CPL*32]
+  float* aarr = larr + BW * CPL * 32;               // [BW][CPL*32]
 
   int hc[CPL];
   bool cv[CPL];
@@ -96,6 +116,7 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
   }
   const int64_t e0 = __ldg(a.rowptr + i), e1 = __ldg(a.rowptr + i + 1);
   const int64_t d = e1 - e0;
+  if (W == 1 && a.skip_deg_gt > 0 && d > a.skip_deg_gt) return;  // a long row: the CTA-per-row launch owns it
   float* orow = a.out + i * a.ldo;
   if (d == 0) {
     // GAT/models/layers.py:28-30: an all -9e15 row soft-maxes to the uniform 1/N over ALL nodes
@@ -116,10 +137,17 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
   if (lane < Hp) {
     mh[lane] = (a.mode == GNN_GAT_SOFTMAX) ? -INFINITY : 0.f;
     sc[lane] = 1.f;
+    lh[lane] = 0.f;
   }
   __syncwarp();
   const int ngrp = 32 / Hp;
   const int hsub = lane % Hp, g = lane / Hp;
+  float si_reg[HT ? HT : 1];
+  if (HT) {
+#pragma unroll
+    for (int h = 0; h < (HT ? HT : 1); ++h) si_reg[h] = __ldg(a.s + i * H + h);
+  }
+  const bool t_vec4 = HT && (HT % 4 == 0) && aligned_to_dev(a.t, 16);
 
   for (int64_t c0 = (int64_t)wsub * SE; c0 < d; c0 += (int64_t)W * SE) {
     const int ne = (int)((d - c0) < SE ? (d - c0) : SE);
@@ -128,13 +156,34 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
       const int j = __ldg(a.col + e0 + c0 + k);
       cols[k] = j;
       const float* tj = a.t + (int64_t)j * H;
-      const float* si = a.s + i * H;
+      if (HT) {
+        float tv[HT ? HT : 1];
+        if (t_vec4) {
+#pragma unroll
+          for (int q = 0; q < (HT ? HT : 1) / 4; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(tj) + q);
+            tv[4 * q] = v.x; tv[4 * q + 1] = v.y; tv[4 * q + 2] = v.z; tv[4 * q + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < (HT ? HT : 1); ++h) tv[h] = __ldg(tj + h);
+        }
+#pragma unroll
+        for (int h = 0; h < (HT ? HT : 1); ++h) {
+          const float z = si_reg[h] + tv[h];
+          float e = fmaxf(z, 0.f) + a.alpha * fminf(z, 0.f);  // LeakyReLU without a branch
+          if (a.mode == GNN_GAT_EXPNEG) e = -e;
+          logit[k * H + h] = e;
+        }
+      } else {
+        const float* si = a.s + i * H;
 #pragma unroll 4
-      for (int h = 0; h < H; ++h) {
-        const float z = __ldg(si + h) + __ldg(tj + h);
-        float e = z > 0.f ? z : a.alpha * z;
-        if (a.mode == GNN_GAT_EXPNEG) e = -e;
-        logit[k * H + h] = e;
+        for (int h = 0; h < H; ++h) {
+          const float z = __ldg(si + h) + __ldg(tj + h);
+          float e = z > 0.f ? z : a.alpha * z;
+          if (a.mode == GNN_GAT_EXPNEG) e = -e;
+          logit[k * H + h] = e;
+        }
       }
     }
     __syncwarp();
@@ -147,8 +196,10 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
       if (lane < H) {
         const float mo = mh[lane];
         const float mn = fmaxf(mo, mx);
-        sc[lane] = (mo == -INFINITY) ? 0.f : expf(mo - mn);
+        const float f = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+        sc[lane] = f;
         mh[lane] = mn;
+        lh[lane] *= f;
       }
       __syncwarp();
 #pragma unroll
@@ -159,7 +210,20 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
       }
     }
     // B2: logits -> un-normalised probabilities, one exp per (edge, head)
-    for (int idx = lane; idx < ne * H; idx += 32) logit[idx] = expf(logit[idx] - mh[idx % H]);
+    if (HT) {
+      // idx = lane + 32*j  =>  head = lane % HT for every j (HT divides 32)
+      const float mymax = mh[hsub];
+      float ps = 0.f;
+      for (int idx = lane; idx < ne * H; idx += 32) {
+        const float p = __expf(logit[idx] - mymax);
+        logit[idx] = p;
+        ps += p;
+      }
+      for (int o = Hp; o < 32; o <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      if (lane < H) lh[lane] += ps;
+    } else {
+      for (int idx = lane; idx < ne * H; idx += 32) logit[idx] = __expf(logit[idx] - mh[idx % H]);
+    }
     __syncwarp();
     // C: weighted accumulation, one lane per output column, 8 row gathers in flight
     for (int k0 = 0; k0 < ne; k0 += 8) {
@@ -171,14 +235,15 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
 #pragma unroll
         for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? __ldg(wr + lane + 32 * c) : 0.f;
       }
+      const float* pk = logit + k0 * H;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         if (k0 + u < ne) {
 #pragma unroll
           for (int c = 0; c < CPL; ++c)
             if (cv[c]) {
-              const float p = logit[(k0 + u) * H + hc[c]];
-              l[c] += p;
+              const float p = pk[u * H + hc[c]];
+              if (!HT) l[c] += p;
               const float w = a.keep ? p * __ldg(a.keep + (e0 + c0 + k0 + u) * H + hc[c]) : p;
               acc[c] = fmaf(w, x[u][c], acc[c]);
             }
@@ -186,6 +251,10 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
       }
     }
     __syncwarp();
+  }
+  if (HT) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) l[c] = lh[hc[c]];
   }
 
   if (W == 1) {
@@ -215,11 +284,11 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_fwd_kernel(const GatArgs a
       if (cv[c]) {
         const int ci = lane + 32 * c;
         float M = -INFINITY;
-        for (int w = 0; w < kGatWarps; ++w) M = fmaxf(M, marr[w * 32 + hc[c]]);
+        for (int w = 0; w < BW; ++w) M = fmaxf(M, marr[w * 32 + hc[c]]);
         float L = 0.f, A = 0.f;
-        for (int w = 0; w < kGatWarps; ++w) {
+        for (int w = 0; w < BW; ++w) {
           const float mw = marr[w * 32 + hc[c]];
-          const float f = (mw == -INFINITY) ? 0.f : expf(mw - M);
+          const float f = (mw == -INFINITY) ? 0.f : __expf(mw - M);
           L = fmaf(larr[(w * CPL + c) * 32 + lane], f, L);
           A = fmaf(aarr[(w * CPL + c) * 32 + lane], f, A);
         }
@@ -267,33 +336,76 @@ __global__ void __launch_bounds__(256) gat_rowdot_kernel(const float* __restrict
   }
 }
 
+// Phase 1 of backward A for one staged chunk: dots dOut_i . Wh_j per head.  FPT = head width
+// (power of two <= 32: aligned lane groups, segmented xor-shuffle) or 0 (single head: full warp).
+template <int CPL, int FPT>
+__device__ __forceinline__ void bwd_head_dots(const GatArgs& a, const int* cols, int ne, const float (&dcol)[CPL],
+                                              const bool (&cv)[CPL], const bool (&lead)[CPL], const int (&hc)[CPL],
+                                              float* dot_s, int H, int lane) {
+  for (int k0 = 0; k0 < ne; k0 += 4) {
+    float x[4][CPL];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = k0 + u < ne;
+      const float* wr = a.Wh + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? __ldg(wr + lane + 32 * c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k0 + u < ne) {  // uniform
+        if (FPT == 0) {
+          float pr = 0.f;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) pr = fmaf(dcol[c], x[u][c], pr);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
+          if (lane == 0) dot_s[k0 + u] = pr;
+        } else {
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) {
+            float pr = dcol[c] * x[u][c];
+#pragma unroll
+            for (int o = 1; o < FPT; o <<= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
+            if (lead[c]) dot_s[(k0 + u) * H + hc[c]] = pr;
+          }
+        }
+      }
+    }
+  }
+}
+
 // Backward A (forward CSR rows): per-edge attention weight w = keep*alpha_ij, edge gradient dz,
 // and d_s[i,h] = sum_j dz.  SEG == true: Fp is a power of two <= 32 (the head groups of the
 // lane->column map are aligned lane groups, reduced by segmented shuffle) or H == 1 (full-warp
 // reduce).  SEG == false: generic lane-per-edge dot (any H, Fp).
-template <int CPL, int W, bool SEG>
-__global__ void __launch_bounds__(kGatWarps * 32) gat_bwd_rows_kernel(const GatArgs a) {
+template <int CPL, int W, bool SEG, int HT>
+__global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(const GatArgs a) {
+  constexpr int BW = GatBlock<W>::kWarps;
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp : (int64_t)blockIdx.x;
+  const int64_t i = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp
+                             : (a.row_list ? __ldg(a.row_list + blockIdx.x) : (int64_t)blockIdx.x);
   const int wsub = (W == 1) ? 0 : warp;
   if (W == 1 && i >= a.n) return;
-  const int H = a.H, Hp = a.Hp, SE = a.SE, HF = a.HF, Fp = a.Fp;
+  if (W == 1 && a.skip_deg_gt > 0 && __ldg(a.rowptr + i + 1) - __ldg(a.rowptr + i) > a.skip_deg_gt) return;
+  const int H = HT ? HT : a.H, Hp = HT ? HT : a.Hp, SE = a.SE, HF = a.HF, Fp = a.Fp;
   const int PW = gat_warp_floats(SE, H, HF);
   float* dot_s = sm + (size_t)warp * PW;       // [SE*H]: head dots, then dz in place
   int* cols = reinterpret_cast<int*>(dot_s + SE * H);
   float* cst = reinterpret_cast<float*>(cols + SE);  // [4][32]: s_i, m_i, 1/l_i, D_i
   float* dout_s = cst + 128;                    // [HF] (generic path)
-  float* dsarr = sm + (size_t)kGatWarps * PW;   // [W][32]
+  float* dsarr = sm + (size_t)BW * PW;          // [BW][32]
 
   int hc[CPL];
-  bool cv[CPL];
+  bool cv[CPL], lead[CPL];
   float dcol[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
     const int ci = lane + 32 * c;
     cv[c] = ci < HF;
     hc[c] = cv[c] ? ci / Fp : 0;
+    lead[c] = cv[c] && (ci % Fp) == 0;
     dcol[c] = cv[c] ? __ldg(a.d_out + i * a.ldo + ci) : 0.f;
     if (!SEG && cv[c]) dout_s[ci] = dcol[c];
   }
@@ -316,34 +428,16 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_bwd_rows_kernel(const GatA
     __syncwarp();
     // phase 1: per-head dots dOut_i . Wh_j
     if (SEG) {
-      for (int k0 = 0; k0 < ne; k0 += 4) {
-        float x[4][CPL];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool ok = k0 + u < ne;
-          const float* wr = a.Wh + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? __ldg(wr + lane + 32 * c) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (k0 + u < ne) {  // uniform
-            if (H == 1) {
-              float pr = 0.f;
-#pragma unroll
-              for (int c = 0; c < CPL; ++c) pr = fmaf(dcol[c], x[u][c], pr);
-              for (int o = 16; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
-              if (lane == 0) dot_s[k0 + u] = pr;
-            } else {
-#pragma unroll
-              for (int c = 0; c < CPL; ++c) {
-                float pr = dcol[c] * x[u][c];
-                for (int o = 1; o < Fp; o <<= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
-                if (cv[c] && ((lane + 32 * c) % Fp) == 0) dot_s[(k0 + u) * H + hc[c]] = pr;
-              }
-            }
-          }
-        }
+      // the head-group reduction is unrolled for the common widths; `lead` marks the lane that
+      // owns a head's first column (no run-time modulo or loop in the per-edge path)
+      switch (H == 1 ? 0 : Fp) {
+        case 0: bwd_head_dots<CPL, 0>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 1: bwd_head_dots<CPL, 1>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 2: bwd_head_dots<CPL, 2>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 4: bwd_head_dots<CPL, 4>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 8: bwd_head_dots<CPL, 8>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 16: bwd_head_dots<CPL, 16>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        default: bwd_head_dots<CPL, 32>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
       }
     } else {
       for (int k = lane; k < ne; k += 32) {
@@ -358,7 +452,7 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_bwd_rows_kernel(const GatA
     __syncwarp();
     // phase 2: one lane per (edge, head): attention weight and dz, stashed per edge (coalesced)
     for (int idx = lane; idx < ne * H; idx += 32) {
-      const int k = idx / H, h = idx - k * H;
+      const int k = idx / H, h = idx - k * H;  // H is a compile-time constant when HT != 0
       const int64_t e = e0 + c0 + k;
       const float z = cst[h] + __ldg(a.t + (int64_t)cols[k] * H + h);
       float slope = z > 0.f ? 1.f : a.alpha;
@@ -367,7 +461,7 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_bwd_rows_kernel(const GatA
         ee = -ee;
         slope = -slope;
       }
-      const float al = expf(ee - cst[32 + h]) * cst[64 + h];
+      const float al = __expf(ee - cst[32 + h]) * cst[64 + h];
       const float kp = a.keep ? __ldg(a.keep + e * H + h) : 1.f;
       const float dz = al * (kp * dot_s[idx] - cst[96 + h]) * slope;
       a.edge_w[e * H + h] = kp * al;
@@ -388,20 +482,23 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_bwd_rows_kernel(const GatA
   __syncthreads();
   if (warp == 0 && lane < H) {
     float tot = 0.f;
-    for (int w = 0; w < kGatWarps; ++w) tot += dsarr[w * 32 + lane];
+    for (int w = 0; w < BW; ++w) tot += dsarr[w * 32 + lane];
     a.d_s[i * H + lane] = tot;
   }
 }
 
 // Backward B: transposed CSR rows (source node j), sources of the forward edges ascending.
 template <int CPL, int W>
-__global__ void __launch_bounds__(kGatWarps * 32) gat_bwd_cols_kernel(const GatArgs a) {
-  __shared__ float accarr[(W > 1) ? kGatWarps * CPL * 32 : 1];
-  __shared__ float dtarr[(W > 1) ? kGatWarps * 32 : 1];
+__global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_cols_kernel(const GatArgs a) {
+  constexpr int BW = GatBlock<W>::kWarps;
+  __shared__ float accarr[(W > 1) ? BW * CPL * 32 : 1];
+  __shared__ float dtarr[(W > 1) ? BW * 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t j = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp : (int64_t)blockIdx.x;
+  const int64_t j = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp
+                             : (a.row_list ? __ldg(a.row_list + blockIdx.x) : (int64_t)blockIdx.x);
   const int wsub = (W == 1) ? 0 : warp;
   if (W == 1 && j >= a.n) return;
+  if (W == 1 && a.skip_deg_gt > 0 && __ldg(a.rowptr + j + 1) - __ldg(a.rowptr + j) > a.skip_deg_gt) return;
   const int H = a.H, Hp = a.Hp;
   int hc[CPL];
   bool cv[CPL];
@@ -468,12 +565,12 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_bwd_cols_kernel(const GatA
     for (int c = 0; c < CPL; ++c)
       if (cv[c]) {
         float tot = 0.f;
-        for (int w = 0; w < kGatWarps; ++w) tot += accarr[(w * CPL + c) * 32 + lane];
+        for (int w = 0; w < BW; ++w) tot += accarr[(w * CPL + c) * 32 + lane];
         a.d_Wh[j * a.ld_dwh + lane + 32 * c] = tot;
       }
     if (lane < H) {
       float tot = 0.f;
-      for (int w = 0; w < kGatWarps; ++w) tot += dtarr[w * 32 + lane];
+      for (int w = 0; w < BW; ++w) tot += dtarr[w * 32 + lane];
       a.d_t[j * H + lane] = tot;
     }
   }
@@ -499,17 +596,53 @@ int stage_edges(int H) {
   return se < 32 ? 32 : se;
 }
 
-// one CTA per row when rows are long on average
+// one CTA per row for every row when rows are long on average (dense metapath adjacencies);
+// otherwise one warp per row, and only the rows of the caller's long-row list get a CTA
 bool cooperative(int64_t n, int64_t nnz) {
-  const int thr = tuning("gat.coop_min_avg_deg", 48);
+  const int thr = tuning("gat.coop_min_avg_deg", 256);
   return n > 0 && nnz > 0 && nnz / n >= thr;
 }
 
 template <int W>
 size_t gat_smem_bytes(int SE, int H, int HF, int cpl) {
-  size_t f = (size_t)kGatWarps * gat_warp_floats(SE, H, HF);
-  if (W > 1) f += (size_t)kGatWarps * 32 + 2 * (size_t)kGatWarps * cpl * 32;
+  constexpr int BW = GatBlock<W>::kWarps;
+  size_t f = (size_t)BW * gat_warp_floats(SE, H, HF);
+  if (W > 1) f += (size_t)BW * 32 + 2 * (size_t)BW * cpl * 32;
   return f * sizeof(float);
+}
+
+// forward launch: picks the compile-time head count when there is one
+template <int CPL, int W>
+int gat_fwd_launch(const GatArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+  constexpr int thr = GatBlock<W>::kWarps * 32;
+#define GNN_GAT_FWD(HT)                                                                                       \
+  do {                                                                                                        \
+    static size_t configured = 0;                                                                             \
+    if (smem > 48 * 1024 && smem > configured) {                                                              \
+      GNN_CUDA(cudaFuncSetAttribute(gat_fwd_kernel<CPL, W, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    (int)smem));                                                              \
+      configured = smem;                                                                                      \
+    }                                                                                                         \
+    gat_fwd_kernel<CPL, W, HT><<<grid, thr, smem, st>>>(a);                                                   \
+  } while (0)
+  if (a.H == 8) GNN_GAT_FWD(8);
+  else if (a.H == 1) GNN_GAT_FWD(1);
+  else GNN_GAT_FWD(0);
+#undef GNN_GAT_FWD
+  GNN_LAUNCH_CHECK();
+  return GNN_OK;
+}
+
+template <int W>
+int gat_fwd_dispatch(const GatArgs& a, int cpl, unsigned grid, cudaStream_t st) {
+  const int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
+  const size_t smem = gat_smem_bytes<W>(a.SE, a.H, a.HF, cplr);
+  switch (cplr) {
+    case 1: return gat_fwd_launch<1, W>(a, grid, smem, st);
+    case 2: return gat_fwd_launch<2, W>(a, grid, smem, st);
+    case 4: return gat_fwd_launch<4, W>(a, grid, smem, st);
+    default: return gat_fwd_launch<8, W>(a, grid, smem, st);
+  }
 }
 
 #define GNN_GAT_CPL_DISPATCH(KERNEL, ...)               \
@@ -542,7 +675,8 @@ int gnn_gat_scores_f32(const float* Wh, int64_t ldw, const float* a_src, const f
 int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw, const float* s,
                           const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode,
                           int apply_elu, const float* col_mean, const float* edge_keep, float* out, int64_t ldo,
-                          float* row_max, float* row_sum, gnn_stream_t stream) {
+                          float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
+                          int64_t long_threshold, gnn_stream_t stream) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
@@ -575,18 +709,16 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
   a.SE = stage_edges(H);
   cudaStream_t st = (cudaStream_t)stream;
   const int cpl = (HF + 31) / 32;
-  const int thr = kGatWarps * 32;
-  if (cooperative(n, nnz)) {
-    const size_t smem = gat_smem_bytes<kGatWarps>(a.SE, H, HF, cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8);
-    const unsigned grid = (unsigned)n;
-    GNN_GAT_CPL_DISPATCH(gat_fwd_kernel, kGatWarps><<<grid, thr, smem, st>>>(a));
-  } else {
-    const size_t smem = gat_smem_bytes<1>(a.SE, H, HF, 0);
-    const unsigned grid = (unsigned)((n + kGatWarps - 1) / kGatWarps);
-    GNN_GAT_CPL_DISPATCH(gat_fwd_kernel, 1><<<grid, thr, smem, st>>>(a));
+  GNN_REQUIRE(n_long == 0 || (long_rows && long_threshold > 0), GNN_ERR_BAD_ARG, "inconsistent long-row list");
+  if (cooperative(n, nnz)) return gat_fwd_dispatch<kGatWarps>(a, cpl, (unsigned)n, st);
+  if (n_long > 0) {  // hub rows: one 16-warp CTA each, launched first so the short rows fill in behind
+    a.row_list = long_rows;
+    rc = gat_fwd_dispatch<16>(a, cpl, (unsigned)n_long, st);
+    if (rc != GNN_OK) return rc;
+    a.row_list = nullptr;
+    a.skip_deg_gt = long_threshold;
   }
-  GNN_LAUNCH_CHECK();
-  return GNN_OK;
+  return gat_fwd_dispatch<1>(a, cpl, (unsigned)((n + kGatWarps - 1) / kGatWarps), st);
 }
 
 int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
@@ -594,7 +726,9 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64
                           const float* row_max, const float* row_sum, const float* out_pre, const float* d_out,
                           int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
                           const float* edge_keep, float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
-                          float* d_rowdot, float* edge_scratch, int64_t nnz, gnn_stream_t stream) {
+                          float* d_rowdot, float* edge_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
+                          const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
+                          gnn_stream_t stream) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
@@ -642,31 +776,100 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64
   }
   const int cpl = (HF + 31) / 32;
   const int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
-  const int thr = kGatWarps * 32;
   const bool coop = cooperative(n, nnz);
   const bool seg = (H == 1) || (Fp <= 32 && (Fp & (Fp - 1)) == 0);
   const unsigned grid1 = (unsigned)((n + kGatWarps - 1) / kGatWarps);
-  {
-    a.rowptr = rowptr;
-    a.col = col;
-    if (coop) {
-      const size_t smem = gat_smem_bytes<kGatWarps>(a.SE, H, HF, cplr);
-      if (seg) GNN_GAT_CPL_DISPATCH(gat_bwd_rows_kernel, kGatWarps, true><<<(unsigned)n, thr, smem, st>>>(a));
-      else GNN_GAT_CPL_DISPATCH(gat_bwd_rows_kernel, kGatWarps, false><<<(unsigned)n, thr, smem, st>>>(a));
-    } else {
-      const size_t smem = gat_smem_bytes<1>(a.SE, H, HF, 0);
-      if (seg) GNN_GAT_CPL_DISPATCH(gat_bwd_rows_kernel, 1, true><<<grid1, thr, smem, st>>>(a));
-      else GNN_GAT_CPL_DISPATCH(gat_bwd_rows_kernel, 1, false><<<grid1, thr, smem, st>>>(a));
+  GNN_REQUIRE((n_long == 0 || long_rows) && (n_long_t == 0 || long_rows_t) &&
+                  ((n_long == 0 && n_long_t == 0) || long_threshold > 0),
+              GNN_ERR_BAD_ARG, "inconsistent long-row lists");
+  // rows kernel: (CPL, W, SEG, HT) ; cols kernel: (CPL, W).  W: 1 warp per row, 4 = every row a CTA
+  // (dense graphs), 16 = the listed hub rows.
+  auto launch_rows = [&](int W, unsigned grid) -> int {
+#define GNN_ROWS(CPLV, WV)                                                                               \
+  do {                                                                                                   \
+    const size_t smem = gat_smem_bytes<WV>(a.SE, H, HF, CPLV);                                           \
+    constexpr int thrv = GatBlock<WV>::kWarps * 32;                                                      \
+    if (smem > 48 * 1024) {                                                                              \
+      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, true, 8>,                              \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, true, 1>,                              \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, true, 0>,                              \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, false, 0>,                             \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    }                                                                                                    \
+    if (!seg) gat_bwd_rows_kernel<CPLV, WV, false, 0><<<grid, thrv, smem, st>>>(a);                      \
+    else if (H == 8) gat_bwd_rows_kernel<CPLV, WV, true, 8><<<grid, thrv, smem, st>>>(a);                \
+    else if (H == 1) gat_bwd_rows_kernel<CPLV, WV, true, 1><<<grid, thrv, smem, st>>>(a);                \
+    else gat_bwd_rows_kernel<CPLV, WV, true, 0><<<grid, thrv, smem, st>>>(a);                            \
+  } while (0)
+#define GNN_ROWS_W(CPLV)                          \
+  do {                                            \
+    if (W == 1) GNN_ROWS(CPLV, 1);                \
+    else if (W == 4) GNN_ROWS(CPLV, 4);           \
+    else GNN_ROWS(CPLV, 16);                      \
+  } while (0)
+    if (cplr == 1) GNN_ROWS_W(1);
+    else if (cplr == 2) GNN_ROWS_W(2);
+    else if (cplr == 4) GNN_ROWS_W(4);
+    else GNN_ROWS_W(8);
+#undef GNN_ROWS_W
+#undef GNN_ROWS
+    GNN_LAUNCH_CHECK();
+    return GNN_OK;
+  };
+  auto launch_cols = [&](int W, unsigned grid) -> int {
+#define GNN_COLS(CPLV)                                                                                  \
+  do {                                                                                                  \
+    if (W == 1) gat_bwd_cols_kernel<CPLV, 1><<<grid, GatBlock<1>::kWarps * 32, 0, st>>>(a);             \
+    else if (W == 4) gat_bwd_cols_kernel<CPLV, 4><<<grid, GatBlock<4>::kWarps * 32, 0, st>>>(a);        \
+    else gat_bwd_cols_kernel<CPLV, 16><<<grid, GatBlock<16>::kWarps * 32, 0, st>>>(a);                  \
+  } while (0)
+    if (cplr == 1) GNN_COLS(1);
+    else if (cplr == 2) GNN_COLS(2);
+    else if (cplr == 4) GNN_COLS(4);
+    else GNN_COLS(8);
+#undef GNN_COLS
+    GNN_LAUNCH_CHECK();
+    return GNN_OK;
+  };
+  // kernel A over the forward CSR
+  a.rowptr = rowptr;
+  a.col = col;
+  if (coop) {
+    rc = launch_rows(4, (unsigned)n);
+    if (rc != GNN_OK) return rc;
+  } else {
+    if (n_long > 0) {
+      a.row_list = long_rows;
+      rc = launch_rows(16, (unsigned)n_long);
+      if (rc != GNN_OK) return rc;
+      a.row_list = nullptr;
+      a.skip_deg_gt = long_threshold;
     }
-    GNN_LAUNCH_CHECK();
+    rc = launch_rows(1, grid1);
+    if (rc != GNN_OK) return rc;
   }
-  {
-    a.rowptr = rowptr_t;
-    a.col = col_t;
-    a.perm = perm_t;
-    if (coop) GNN_GAT_CPL_DISPATCH(gat_bwd_cols_kernel, kGatWarps><<<(unsigned)n, thr, 0, st>>>(a));
-    else GNN_GAT_CPL_DISPATCH(gat_bwd_cols_kernel, 1><<<grid1, thr, 0, st>>>(a));
-    GNN_LAUNCH_CHECK();
+  // kernel B over the transposed CSR
+  a.rowptr = rowptr_t;
+  a.col = col_t;
+  a.perm = perm_t;
+  a.row_list = nullptr;
+  a.skip_deg_gt = 0;
+  if (coop) {
+    rc = launch_cols(4, (unsigned)n);
+    if (rc != GNN_OK) return rc;
+  } else {
+    if (n_long_t > 0) {
+      a.row_list = long_rows_t;
+      rc = launch_cols(16, (unsigned)n_long_t);
+      if (rc != GNN_OK) return rc;
+      a.row_list = nullptr;
+      a.skip_deg_gt = long_threshold;
+    }
+    rc = launch_cols(1, grid1);
+    if (rc != GNN_OK) return rc;
   }
   return GNN_OK;
 }

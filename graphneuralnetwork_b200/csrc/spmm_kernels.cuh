@@ -34,8 +34,11 @@ struct SpmmArgs {
 
 constexpr int kSpmmThreads = 256;
 
+// One-vector-per-lane variants are held to 64 registers (4 CTAs/SM): next to the 3 CTAs that a
+// concurrently running halo-push CTA leaves room for, this keeps the local-column pass of the
+// partitioned SpMM at full occupancy (at 80 registers it dropped from 3 to 2 CTAs per SM).
 template <typename T, int VEC, int GROUP, int CHUNKS, int U>
-__global__ void __launch_bounds__(kSpmmThreads) spmm_rbs_kernel(const SpmmArgs<T> a) {
+__global__ void __launch_bounds__(kSpmmThreads, (CHUNKS == 1) ? 4 : 1) spmm_rbs_kernel(const SpmmArgs<T> a) {
   const int lane = threadIdx.x & 31;
   const int gl = threadIdx.x % GROUP;
   const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane - gl));

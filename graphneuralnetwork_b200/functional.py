@@ -248,9 +248,10 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
     row_max = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     row_sum = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     col_mean = Wh.mean(dim=0).contiguous() if g.has_empty_rows() else None
+    lr, thr = g.gat_long_rows()
     _lib.check(lib.gnn_gat_fused_fwd_f32(_p(g.rowptr), _p(g.col), _p(Wh), _ld(Wh), _p(s), _p(t), n, g.nnz, H, Fp,
-                                         float(alpha), mode, elu, _p(col_mean), _p(keep), _p(out), _ld(out), _p(row_max), _p(row_sum),
-                                         _stream_ptr()), "gnn_gat_fused_fwd_f32")
+                                         float(alpha), mode, elu, _p(col_mean), _p(keep), _p(out), _ld(out), _p(row_max),
+                                         _p(row_sum), _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd_f32")
     return out, row_max, row_sum
 
 
@@ -280,10 +281,12 @@ class _GatFn(torch.autograd.Function):
         d_t = torch.empty((n, H), dtype=torch.float32, device=dev)
         rowdot = torch.empty((n, H), dtype=torch.float32, device=dev)
         scratch = torch.empty((2, max(g.nnz, 1), H), dtype=torch.float32, device=dev)
+        (lr, thr), (lrt, _) = g.gat_long_rows(), gt.gat_long_rows()
         _lib.check(lib.gnn_gat_fused_bwd_f32(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t), _p(Wh),
                                              _ld(Wh), _p(s), _p(t), _p(row_max), _p(row_sum), _p(out), _p(d_out),
                                              _ld(out), n, H, Fp, alpha, mode, _p(keep), _p(d_Wh), _ld(d_Wh), _p(d_s),
-                                             _p(d_t), _p(rowdot), _p(scratch), g.nnz, _stream_ptr()),
+                                             _p(d_t), _p(rowdot), _p(scratch), g.nnz, _p(lr), lr.numel(), _p(lrt),
+                                             lrt.numel(), thr, _stream_ptr()),
                    "gnn_gat_fused_bwd_f32")
         if g.has_empty_rows():
             # rows without edges output the mean of all Wh rows (GAT/models/layers.py:28-30)

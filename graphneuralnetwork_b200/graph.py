@@ -108,6 +108,15 @@ class CSRGraph:
                 self._plan = (lr, thr, chunk_off, n_chunks, chunk, ws)
         return self._plan or None
 
+    def gat_long_rows(self):
+        """(long_rows int64, threshold): rows the attention kernels hand to a whole CTA (host-side plan,
+        cached)."""
+        if getattr(self, "_gat_long", None) is None:
+            thr = _lib.get_tuning("gat.long_row")
+            deg = self.rowptr[1:] - self.rowptr[:-1]
+            self._gat_long = (torch.nonzero(deg > thr).flatten().contiguous(), thr)
+        return self._gat_long
+
     def has_empty_rows(self) -> bool:
         if self._zero_rows is None:
             deg = self.rowptr[1:] - self.rowptr[:-1]

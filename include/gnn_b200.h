@@ -197,14 +197,18 @@ int gnn_gat_scores_f32(const float* Wh, int64_t ldw, const float* a_src, const f
  * uniform mean over ALL nodes, passed in as col_mean[H*Fp] (nullable if no such row).
  * edge_keep (nullable, fp32 [nnz,H]): post-softmax dropout factor per edge and head
  * (0 or 1/(1-p)), layers.py:31.  row_max/row_sum [n,H] are saved for the backward.
- * Schedule: one warp per row, or one CTA per row (4 warps on alternate 128-edge chunks, merged
- * in warp order) when nnz/n >= the "gat.coop_min_avg_deg" knob. */
+ * Schedule: one warp per row; the rows of long_rows[n_long] (those with more than
+ * long_threshold edges: the caller's plan, CSRGraph.gat_long_rows) get one CTA each (4 warps on
+ * alternate 128-edge chunks, merged in warp order); when nnz/n >= the "gat.coop_min_avg_deg"
+ * knob (dense metapath adjacencies) every row gets a CTA and the list is ignored. */
 int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw,
                           const float* s, const float* t, int64_t n, int64_t nnz /*schedule hint, 0 if unknown*/,
                           int32_t H, int32_t Fp,
                           float alpha, int mode, int apply_elu, const float* col_mean,
                           const float* edge_keep, float* out, int64_t ldo,
-                          float* row_max, float* row_sum, gnn_stream_t stream);
+                          float* row_max, float* row_sum,
+                          const int64_t* long_rows /*nullable*/, int64_t n_long, int64_t long_threshold,
+                          gnn_stream_t stream);
 /* Backward.  d_out is the gradient w.r.t. the PRE-activation aggregate (the wrapper
  * applies the ELU derivative); out_pre is that aggregate.  Produces
  *   d_s [n,H]   (row-parallel over the CSR),
@@ -221,6 +225,8 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
                           const float* edge_keep,
                           float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot /*[n,H] scratch*/,
                           float* edge_scratch /*[2,nnz,H]: per-edge attention weight and dz*/, int64_t nnz,
+                          const int64_t* long_rows, int64_t n_long /*forward CSR*/,
+                          const int64_t* long_rows_t, int64_t n_long_t /*transposed CSR*/, int64_t long_threshold,
                           gnn_stream_t stream);
 
 /* ---- synthetic graphs for the benchmark shapes ---------------- */

@@ -495,6 +495,37 @@ def test_gat_forward_backward_vs_cpu_autograd(lib, nhid, density):
         assert rel_err(p.grad.cpu().numpy(), cpu_params[name].grad.numpy()) < 2e-5, name
 
 
+def test_gat_long_row_schedule(lib):
+    """Warp-per-row launch + CTA-per-row launch for the listed hub rows == the all-warp schedule
+    (forward and all three gradients), and the float64 oracle."""
+    n, H, Fp = 900, 8, 8
+    rng = np.random.default_rng(5)
+    deg = rng.poisson(6, size=n) + 1
+    deg[[3, 400, 899]] = [700, 300, 129]
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    col = rng.integers(0, n, size=rowptr[-1]).astype(np.int32)
+    Wh = rng.standard_normal((n, H, Fp)).astype(np.float32)
+    s = rng.standard_normal((n, H)).astype(np.float32)
+    t = rng.standard_normal((n, H)).astype(np.float32)
+    ref = ogat.edge_attention_f64(rowptr, col, Wh, s, t, 0.2).reshape(n, H * Fp)
+    results = []
+    for thr in (128, 1 << 30):  # 128: rows 3, 400, 899 (and hub columns of the transpose) take the CTA launch
+        _lib.set_tuning("gat.long_row", thr)
+        try:
+            csr = CSRGraph(cuda(rowptr), cuda(col), None, n, n)
+            assert csr.gat_long_rows()[0].numel() == (3 if thr == 128 else 0)
+            Wd = cuda(Wh).view(n, -1).requires_grad_(True)
+            sd, td = cuda(s).requires_grad_(True), cuda(t).requires_grad_(True)
+            out = Fn.gat_aggregate(csr, Wd, sd, td, H, Fp, 0.2)
+            assert rel_err(out.detach().cpu().numpy(), ref) < TOL32
+            out.square().sum().backward()
+            results.append((out.detach(), Wd.grad, sd.grad, td.grad))
+        finally:
+            _lib.set_tuning("gat.long_row", 1024)
+    for a, b in zip(*results):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < TOL32
+
+
 def test_han_small_vs_reference_golden(lib):
     g = load_golden("han_small.npz")
     n = int(g["n"])

@@ -90,6 +90,8 @@ def bench_spmm(args, n, mean_deg, tag):
 
 def bench_gat(args):
     for n, mean_deg, tag in ((2708, 4.9, "cora"), (3025, 730, "acm_dense"), (232_965, 100, "reddit_d100")):
+        if args.graph and tag != args.graph:
+            continue
         # skew=1: uniform targets, so in-degrees stay moderate like in the symmetric adjacencies
         # GAT/HAN are given (the transposed graph the backward walks has no 100k-edge rows)
         csr = S.powerlaw_csr(n, mean_deg, seed=0, device=DEV, with_values=False, max_degree=min(n - 1, 20000),
@@ -123,6 +125,7 @@ if __name__ == "__main__":
     ap.add_argument("--skew", type=float, default=3.0)
     ap.add_argument("--max-degree", type=int, default=1 << 20)
     ap.add_argument("--knobs", type=json.loads, default=[{}])
+    ap.add_argument("--graph", default="")
     a = ap.parse_args()
     if a.what == "sage":
         bench_sage(a)
