@@ -168,6 +168,33 @@ def gather_reduce_multi_raw(table: torch.Tensor, blocks, reduce: str = "mean", o
     return outs
 
 
+def sample_neighbors(g: CSRGraph, src: torch.Tensor, k: int, seed: int, out_dtype=torch.int32,
+                     seed_offset: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """k sampled neighbour ids per source (gnn_sample_neighbors), flat and src-major like
+    GraphSAGE_Pytorch/sample_utils.py:4-17: without replacement when deg >= k, else with."""
+    _require_cuda(src)
+    lib = _lib.load()
+    src = src.contiguous().view(-1)
+    if src.dtype not in (torch.int32, torch.int64):
+        src = src.to(torch.int64)
+    if out is None:
+        out = torch.empty(src.numel() * k, dtype=out_dtype, device=src.device)
+    assert seed_offset is None or (seed_offset.dtype == torch.int64 and seed_offset.is_cuda)
+    _lib.check(lib.gnn_sample_neighbors(_p(g.rowptr), _p(g.col), _p(src), 32 if src.dtype == torch.int32 else 64,
+                                        src.numel(), int(k), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_offset), _p(out),
+                                        32 if out.dtype == torch.int32 else 64, _stream_ptr()), "gnn_sample_neighbors")
+    return out
+
+
+def multihop_sampling(g: CSRGraph, src_nodes: torch.Tensor, sample_nums, seed: int, out_dtype=torch.int32,
+                      seed_offset: Optional[torch.Tensor] = None):
+    """GraphSAGE_Pytorch/sample_utils.py:20-35 on the device: [src, hop-1 ids, hop-2 ids, ...]."""
+    result = [src_nodes.to(out_dtype) if src_nodes.dtype != out_dtype else src_nodes]
+    for hop, k in enumerate(sample_nums):
+        result.append(sample_neighbors(g, result[hop], k, seed + 0x9E3779B9 * (hop + 1), out_dtype, seed_offset))
+    return result
+
+
 class _GatherReduceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table, idx, n_src, fanout, reduce):

@@ -195,32 +195,53 @@ class CapturedGraphSage:
         logits_host = runner(host_id_blocks)        # list of pinned int32/int64 id tensors
     """
 
-    def __init__(self, model: GraphSage, table: torch.Tensor, batch: int, id_dtype=torch.int32):
-        self.model, self.table = model, table
+    def __init__(self, model: GraphSage, table: torch.Tensor, batch: int, id_dtype=torch.int32, adjacency=None,
+                 seed: int = 0):
+        """adjacency (a CSRGraph over the table's nodes, optional): sample the neighbour blocks on the
+        device inside the captured graph (`functional.multihop_sampling`, a fresh draw per replay);
+        then only the batch's node ids cross PCIe."""
+        from .. import _lib
+        from ..functional import multihop_sampling
+        self.model, self.table, self.adjacency = model, table, adjacency
         dev = table.device
         sizes = [batch]
         for f in model.num_neighbors_list:
             sizes.append(sizes[-1] * f)
         self.ids = [torch.zeros(s, dtype=id_dtype, device=dev) for s in sizes]
+        self.replays = torch.zeros(1, dtype=torch.int64, device=dev)  # per-replay RNG stream of the sampler
         self.stream = torch.cuda.Stream(device=dev)
         self.graph = torch.cuda.CUDAGraph()
         self.kernel_launches_per_replay = 0
-        from .. import _lib
+
+        def body():
+            if adjacency is not None:
+                self.replays.add_(1)
+                blocks = multihop_sampling(adjacency, self.ids[0], model.num_neighbors_list, seed, id_dtype,
+                                           seed_offset=self.replays)
+                for dst, src in zip(self.ids[1:], blocks[1:]):
+                    dst.copy_(src)
+            return model.forward_sampled(table, self.ids)
+
         with torch.no_grad(), torch.cuda.stream(self.stream):
             for _ in range(2):  # warm-up outside capture (allocator, cuBLAS handles, smem attributes)
-                model.forward_sampled(table, self.ids)
+                body()
             self.stream.synchronize()
             before = _lib.launch_count()
             with torch.cuda.graph(self.graph, stream=self.stream):
-                self.logits = model.forward_sampled(table, self.ids)
+                self.logits = body()
             self.kernel_launches_per_replay = _lib.launch_count() - before
         self.logits_host = torch.empty(self.logits.shape, dtype=self.logits.dtype).pin_memory()
 
     @torch.no_grad()
     def __call__(self, host_id_blocks):
+        """host_id_blocks: pinned id tensors — every hop's block, or only the batch's node ids when
+        the runner samples on the device."""
+        if torch.is_tensor(host_id_blocks):
+            host_id_blocks = [host_id_blocks]
+        n_in = 1 if self.adjacency is not None else len(self.ids)
         with torch.cuda.stream(self.stream):
-            for dst, src in zip(self.ids, host_id_blocks):
-                dst.copy_(src, non_blocking=True)          # H2D: this minibatch's sampled ids
+            for dst, src in zip(self.ids[:n_in], host_id_blocks[:n_in]):
+                dst.copy_(src, non_blocking=True)          # H2D: this minibatch's ids
             self.graph.replay()
             self.logits_host.copy_(self.logits, non_blocking=True)  # D2H: the result
         self.stream.synchronize()

@@ -183,6 +183,18 @@ int gnn_gather_reduce_bwd_dense_f32(const float* d_out, int64_t ld_dout, const i
                                     int64_t n_src, int32_t fanout, int32_t F, float scale,
                                     float* d_neigh /*[n_src,fanout,F] contiguous*/, gnn_stream_t stream);
 
+/* Fixed-fanout neighbour sampler on the device (semantics of
+ * GraphSAGE_Pytorch/sample_utils.py:4-17): for each source id, k DISTINCT neighbours uniformly at
+ * random if it has at least k (random.sample), else k draws with replacement (random.choices);
+ * out[i*k+j], src-major (sample_utils.py:16).  Counter-based RNG keyed by (seed, i, j):
+ * deterministic for a seed, semantically (not bit-) equal to the Mersenne-Twister reference.
+ * A source without neighbours (or a negative source id) yields -1 ids, which the gather skips.
+ * seed_offset_dev (nullable): a device int64 mixed into the seed at run time, so that a captured
+ * CUDA graph draws a fresh sample on every replay. */
+int gnn_sample_neighbors(const int64_t* rowptr, const int32_t* col, const void* src, int src_bits,
+                         int64_t n_src, int32_t k, uint64_t seed, const int64_t* seed_offset_dev,
+                         void* out, int out_bits, gnn_stream_t stream);
+
 /* ---- GAT / HAN: fused multi-head attention aggregation ---------------------------- */
 /* Per-node, per-head halves of the edge score (GAT/models/layers.py:25-26 decomposes
  * exactly: a·[Wh_i || Wh_j] = a[:F']·Wh_i + a[F':]·Wh_j):

@@ -383,6 +383,85 @@ def test_graphsage_v2_model_vs_reference_golden(lib):
     check_grads(model, g)
 
 
+# ---------------------------------------------------------------- device-side neighbour sampler (§8f)
+def test_sampler_semantics(lib):
+    """Same contract as GraphSAGE_Pytorch/sample_utils.py:4-17: members of the neighbour list; distinct
+    when deg >= k (random.sample), with replacement otherwise (random.choices); src-major layout."""
+    adj = S.adjacency_lists(400, 8, seed=6)
+    ptr = np.cumsum([0] + [len(adj[i]) for i in range(400)]).astype(np.int64)
+    flat = np.concatenate([np.asarray(sorted(adj[i]), dtype=np.int32) for i in range(400)])
+    csr = CSRGraph(cuda(ptr), cuda(flat), None, 400, 400)
+    src = torch.arange(400, device=DEV)
+    for k in (1, 5, 25):
+        for dt in (torch.int32, torch.int64):
+            ids = Fn.sample_neighbors(csr, src, k, seed=123, out_dtype=dt).cpu().numpy().reshape(400, k)
+            for i in range(400):
+                assert set(ids[i].tolist()) <= adj[i]
+                if len(adj[i]) >= k:
+                    assert len(set(ids[i].tolist())) == k  # without replacement
+        again = Fn.sample_neighbors(csr, src, k, seed=123).cpu().numpy()
+        assert np.array_equal(again.reshape(400, k), Fn.sample_neighbors(csr, src, k, seed=123).cpu().numpy().reshape(400, k))
+        other = Fn.sample_neighbors(csr, src, k, seed=124).cpu().numpy()
+        assert not np.array_equal(again, other)
+    blocks = Fn.multihop_sampling(csr, torch.arange(32, device=DEV), [5, 3], seed=7)
+    assert [b.numel() for b in blocks] == [32, 160, 480]
+    b1, b2 = blocks[1].cpu().numpy(), blocks[2].cpu().numpy().reshape(160, 3)
+    for p in range(160):
+        assert set(b2[p].tolist()) <= adj[int(b1[p])]  # neighbours of source p are rows [p*f,(p+1)*f)
+    # isolated / negative sources give -1 ids, which the gather kernels skip
+    csr0 = CSRGraph(cuda(np.array([0, 0, 2], np.int64)), cuda(np.array([1, 0], np.int32)), None, 2, 2)
+    ids = Fn.sample_neighbors(csr0, cuda(np.array([0, 1, -1])), 3, seed=1).cpu().numpy().reshape(3, 3)
+    assert (ids[0] == -1).all() and (ids[2] == -1).all() and set(ids[1].tolist()) <= {0, 1}
+
+
+def test_captured_graphsage_runner(lib):
+    """CUDA-graph runner == eager forward, with host-provided blocks and with device-side sampling."""
+    adj = S.adjacency_lists(600, 8, seed=3)
+    ptr = np.cumsum([0] + [len(adj[i]) for i in range(600)]).astype(np.int64)
+    flat = np.concatenate([np.asarray(sorted(adj[i]), dtype=np.int32) for i in range(600)])
+    csr = CSRGraph(cuda(ptr), cuda(flat), None, 600, 600)
+    table = Fn.pad_table(torch.randn(600, 602, device=DEV))
+    torch.manual_seed(0)
+    model = layers.GraphSage(602, [128, 41], [5, 3]).to(DEV).eval()
+    batch = torch.arange(100, 132, dtype=torch.int32)
+    blocks = Fn.multihop_sampling(csr, batch.to(DEV), [5, 3], seed=11)
+    runner = layers.CapturedGraphSage(model, table, 32)
+    out = runner([b.cpu().pin_memory() for b in blocks]).clone()
+    with torch.no_grad():
+        assert torch.equal(out, model.forward_sampled(table, blocks).cpu())
+    sampling = layers.CapturedGraphSage(model, table, 32, adjacency=csr, seed=5)
+    o1 = sampling(batch.pin_memory()).clone()
+    ids1 = [i.clone() for i in sampling.ids]
+    with torch.no_grad():
+        assert torch.equal(o1, model.forward_sampled(table, ids1).cpu())
+    for p in range(160):
+        assert set(ids1[2].view(160, 3)[p].tolist()) <= adj[int(ids1[1][p])]
+    sampling(batch.pin_memory())
+    assert not torch.equal(ids1[2], sampling.ids[2])  # a fresh draw on every replay
+
+
+def test_sampler_is_uniform(lib):
+    """Marginal frequencies over many independent sources of the same node: both branches."""
+    deg = 50
+    ptr = np.array([0, deg], np.int64)
+    col = np.arange(100, 100 + deg, dtype=np.int32)
+    csr = CSRGraph(cuda(ptr), cuda(col), None, 1, 200)
+    n = 200_000
+    src = torch.zeros(n, dtype=torch.int64, device=DEV)
+    for k in (10, 64):  # 10 <= deg: permutation branch; 64 > deg: with replacement
+        ids = Fn.sample_neighbors(csr, src, k, seed=99).cpu().numpy()
+        counts = np.bincount(ids - 100, minlength=deg).astype(np.float64)
+        expect = n * k / deg
+        assert counts.sum() == n * k
+        assert np.abs(counts - expect).max() < 6 * np.sqrt(expect)  # ~6 sigma of a binomial count
+    # pairs are not correlated either: first two draws of the permutation branch
+    ids = Fn.sample_neighbors(csr, src, 10, seed=5).cpu().numpy().reshape(n, 10) - 100
+    pair = np.bincount(ids[:, 0] * deg + ids[:, 1], minlength=deg * deg).reshape(deg, deg)
+    assert np.trace(pair) == 0
+    off = pair[~np.eye(deg, dtype=bool)]
+    assert np.abs(off - n / (deg * (deg - 1))).max() < 7 * np.sqrt(n / (deg * (deg - 1)))
+
+
 # ---------------------------------------------------------------- GAT / HAN fused attention
 def test_gat_small_vs_reference_golden(lib):
     g = load_golden("gat_small.npz")
