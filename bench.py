@@ -231,6 +231,28 @@ def run_sage_b200(args, rank, world, dev):
     k2_cold_ms = cuda_time(lambda: Fn.gather_reduce_multi_raw(table, [(dev_blocks[0][2], B * f1, f2),
                                                                      (dev_blocks[0][1], B, f1)], "mean",
                                                              outs=[out2, out1]), 20, flush_dev=dev)
+    # SURVEY §8f rank 1 (beyond the reference-facing contract, reported separately): the neighbour blocks
+    # are sampled on the device inside the captured graph, so only the batch's 1024 node ids cross PCIe
+    dev_sampling = None
+    try:
+        from graphneuralnetwork_b200 import synthetic as S
+        adj = S.powerlaw_csr(SAGE["n"], 492.0, seed=0, device=dev, with_values=False)  # Reddit-shaped adjacency
+        runner2 = layers.CapturedGraphSage(model, table, B, adjacency=adj, seed=1)
+        batch_ids = [torch.randint(0, SAGE["n"], (B,), dtype=torch.int32).pin_memory() for _ in range(pool)]
+        for i in range(args.warmup):
+            runner2(batch_ids[i % pool])
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(args.steps):
+            runner2(batch_ids[i % pool])
+        ds_ms = (time.perf_counter() - w0) * 1e3
+        dev_sampling = {"value": args.steps * SAGE_EDGES / (ds_ms * 1e-3), "unit": "edges/s (this rank)",
+                        "ms_per_step": ds_ms / args.steps, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": B * 41 * 4,
+                        "what": "CapturedGraphSage(adjacency=...): gnn_sample_neighbors for both hops + fused "
+                                "gather-means + matmuls in one CUDA graph; Reddit-shaped adjacency, nnz %d" % adj.nnz}
+        del runner2, adj
+    except Exception as e:  # pragma: no cover
+        dev_sampling = {"error": repr(e)}
     # the captured forward must equal the eager drop-in forward on the same ids
     with torch.no_grad():
         eager = model.forward_sampled(table, dev_blocks[(args.warmup + args.steps - 1) % pool])
@@ -279,6 +301,7 @@ def run_sage_b200(args, rank, world, dev):
                        "H2D, aggregation kernels + torch matmuls replayed as one CUDA graph, logits D2H, host sync "
                        "every step; wall-clock",
                 "max_abs_diff_vs_eager": e2e_check},
+        "e2e_device_sampling": dev_sampling,
         "gpu_launches": int(launches) + int(runner.kernel_launches_per_replay) * (args.steps + args.warmup),
         "gpu_launches_detail": {"kernels_only_leg": int(launches),
                                 "e2e_leg_per_step": int(runner.kernel_launches_per_replay)},
