@@ -41,6 +41,8 @@ static std::map<std::string, int>& tune_map() {
       {"spmm.long_row", 2048},   // rows above this nnz go to the CTA-per-chunk path (planned call)
       {"spmm.chunk", 8192},      // edges per long-row chunk
       {"spmm.unroll", 0},        // 0 = heuristic
+      {"spmm.rows_per_team", 0},  // >0 overrides the caller's rows_per_team (tuning sweeps)
+      {"spmm.team_edges", 512},   // host plan: edges one team should hold (graph.py rows_per_team)
       {"gat.stage_edges", 128},  // logits staged per warp pass
       {"gat.coop_min_avg_deg", 256},  // nnz/n at which every row gets a whole CTA
       {"gat.long_row", 1024},        // rows above this get a CTA in the otherwise warp-per-row schedule

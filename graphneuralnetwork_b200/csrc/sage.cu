@@ -24,6 +24,7 @@ constexpr int kConsumerWarps = 5;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kSageThreads = 32 + kConsumerThreads;
 constexpr int kMaxBlocks = 4;
+constexpr int kIdDepth = 4;  // chunks of sampled ids the producer keeps in flight
 
 template <typename T>
 struct SageArgs {
@@ -47,6 +48,16 @@ struct SageArgs {
   int32_t nvec;                      // 16-byte vectors per row
 };
 
+// Two fp32 adds in one instruction (SASS FADD2, sm_100): same round-to-nearest result as two
+// FADDs at half the issue slots.  The bf16 consumer loop was issue-bound (ncu r01: 195 warp
+// instructions per 1.2 KB row, 64 % issue-active with one scheduler idle).
+__device__ __forceinline__ void add2(float& a0, float& a1, float x0, float x1) {
+  asm("{\n\t.reg .b64 ra, rx;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rx, {%2, %3};\n\t"
+      "add.rn.f32x2 ra, ra, rx;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(x0), "f"(x1));
+}
+
 template <typename T>
 struct Vec16;
 template <>
@@ -55,6 +66,10 @@ struct Vec16<float> {
   static __device__ __forceinline__ void unpack(const uint4& w, float (&o)[4]) {
     o[0] = __uint_as_float(w.x); o[1] = __uint_as_float(w.y); o[2] = __uint_as_float(w.z); o[3] = __uint_as_float(w.w);
   }
+  static __device__ __forceinline__ void add(const uint4& w, float (&acc)[4]) {
+    add2(acc[0], acc[1], __uint_as_float(w.x), __uint_as_float(w.y));
+    add2(acc[2], acc[3], __uint_as_float(w.z), __uint_as_float(w.w));
+  }
 };
 template <>
 struct Vec16<__nv_bfloat16> {
@@ -62,6 +77,12 @@ struct Vec16<__nv_bfloat16> {
   static __device__ __forceinline__ void unpack(const uint4& w, float (&o)[8]) {
     bf16x2_to_f32(w.x, o[0], o[1]); bf16x2_to_f32(w.y, o[2], o[3]);
     bf16x2_to_f32(w.z, o[4], o[5]); bf16x2_to_f32(w.w, o[6], o[7]);
+  }
+  static __device__ __forceinline__ void add(const uint4& w, float (&acc)[8]) {
+    float x[8];
+    unpack(w, x);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) add2(acc[i], acc[i + 1], x[i], x[i + 1]);
   }
 };
 
@@ -123,29 +144,44 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
       if (a.idx64[c.b]) return __ldg(a.idx64[c.b] + p);
       return p;  // identity block
     };
-    Cursor cur, nxt;
+    // The ids of the next kIdDepth chunks are always in flight: with a single chunk of lookahead
+    // the producer paid one DRAM round trip per ring stage whenever a source's ids sat in a
+    // sector of their own (fanout 10 = 40 bytes), which capped the 1.2 KB bf16 rows at 0.61.
+    Cursor cur, look;
     cursor_set(cur, a, blockIdx.x);
-    nxt = cur;
-    if (nxt.g < total_src) cursor_next(nxt, a);
-    int64_t r_next = load_id(cur);
-    for (int64_t it = 0; cur.g < total_src; ++it) {
-      const int64_t r = r_next;
-      r_next = load_id(nxt);  // prefetch the next chunk's ids while this one is issued
-      const int stage = (int)(it % S);
-      const uint32_t par = (uint32_t)((it / S) & 1);
-      mbar_wait(empty + stage, par ^ 1u);
-      const bool valid = r >= 0;
-      const unsigned m = __ballot_sync(0xffffffffu, valid);
-      if (lane == 0) {
-        mask[stage] = m;
-        mbar_arrive_expect_tx(full + stage, (uint32_t)__popc(m) * (uint32_t)a.row_bytes);
+    look = cur;
+    int64_t rq[kIdDepth];
+#pragma unroll
+    for (int d = 0; d < kIdDepth; ++d) {
+      rq[d] = load_id(look);
+      if (look.g < total_src) cursor_next(look, a);
+    }
+    int stage = 0;
+    uint32_t par = 0;
+    while (cur.g < total_src) {
+#pragma unroll
+      for (int d = 0; d < kIdDepth; ++d) {
+        if (cur.g >= total_src) break;
+        const int64_t r = rq[d];
+        rq[d] = load_id(look);
+        if (look.g < total_src) cursor_next(look, a);
+        mbar_wait(empty + stage, par ^ 1u);
+        const bool valid = r >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) {
+          mask[stage] = m;
+          mbar_arrive_expect_tx(full + stage, (uint32_t)__popc(m) * (uint32_t)a.row_bytes);
+        }
+        __syncwarp();
+        if (valid)
+          bulk_g2s(smem + (size_t)stage * stage_bytes + (size_t)lane * a.row_bytes, a.table + r * a.ld,
+                   (uint32_t)a.row_bytes, full + stage);
+        cursor_next(cur, a);
+        if (++stage == S) {
+          stage = 0;
+          par ^= 1u;
+        }
       }
-      __syncwarp();
-      if (valid)
-        bulk_g2s(smem + (size_t)stage * stage_bytes + (size_t)lane * a.row_bytes, a.table + r * a.ld,
-                 (uint32_t)a.row_bytes, full + stage);
-      cur = nxt;
-      if (nxt.g < total_src) cursor_next(nxt, a);
     }
   } else {
     // ===== consumers: reduce the staged rows in fanout order =====
@@ -164,33 +200,48 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
     reset();
     Cursor cur;
     cursor_set(cur, a, blockIdx.x);
-    for (int64_t it = 0; cur.g < total_src; ++it) {
-      const int stage = (int)(it % S);
-      const uint32_t par = (uint32_t)((it / S) & 1);
+    int stage = 0;
+    uint32_t par = 0;
+    for (; cur.g < total_src; cursor_next(cur, a)) {
       const int c0 = cur.c0;
       const int rows = min(cur.kc, cur.fan - c0);
       mbar_wait(full + stage, par);
       const unsigned m = mask[stage];
       const unsigned char* sb = smem + (size_t)stage * stage_bytes;
+      const unsigned all_rows = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
+      if (OP != GNN_REDUCE_MAX && m == all_rows) {
+        // every id of the chunk is valid (the sampled blocks of GraphSAGE_Pytorch always are):
+        // no per-row mask test, packed adds
+#pragma unroll 5
+        for (int k = 0; k < rows; ++k) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int vi = t + v * kConsumerThreads;
+            if (vi < a.nvec)
+              Vec16<T>::add(*reinterpret_cast<const uint4*>(sb + (size_t)k * a.row_bytes + (size_t)vi * 16), acc[v]);
+          }
+        }
+      } else {
 #pragma unroll 4
-      for (int k = 0; k < rows; ++k) {
-        if (!((m >> k) & 1u)) continue;
+        for (int k = 0; k < rows; ++k) {
+          if (!((m >> k) & 1u)) continue;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int vi = t + v * kConsumerThreads;
-          if (vi < a.nvec) {
-            const uint4 w = *reinterpret_cast<const uint4*>(sb + (size_t)k * a.row_bytes + (size_t)vi * 16);
-            float x[E];
-            Vec16<T>::unpack(w, x);
+          for (int v = 0; v < NV; ++v) {
+            const int vi = t + v * kConsumerThreads;
+            if (vi < a.nvec) {
+              const uint4 w = *reinterpret_cast<const uint4*>(sb + (size_t)k * a.row_bytes + (size_t)vi * 16);
+              float x[E];
+              Vec16<T>::unpack(w, x);
 #pragma unroll
-            for (int i = 0; i < E; ++i) {
-              if (OP == GNN_REDUCE_MAX) {
-                if (x[i] > acc[v][i]) {
-                  acc[v][i] = x[i];
-                  best[v][i] = c0 + k;
+              for (int i = 0; i < E; ++i) {
+                if (OP == GNN_REDUCE_MAX) {
+                  if (x[i] > acc[v][i]) {
+                    acc[v][i] = x[i];
+                    best[v][i] = c0 + k;
+                  }
+                } else {
+                  acc[v][i] += x[i];
                 }
-              } else {
-                acc[v][i] += x[i];
               }
             }
           }
@@ -229,7 +280,10 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
         }
         reset();
       }
-      cursor_next(cur, a);
+      if (++stage == S) {
+        stage = 0;
+        par ^= 1u;
+      }
     }
   }
 }

@@ -30,6 +30,7 @@ struct SpmmArgs {
   int32_t F;
   int64_t skip_deg_gt;  // >0: rows with more edges belong to the long-row kernels
   int32_t accumulate;   // 1: Y += Â·X (second pass of the partitioned SpMM), 0: Y = Â·X
+  int32_t rows_per_team;  // rows a team of GROUP lanes owns (1..GROUP); 0 = GROUP
 };
 
 constexpr int kSpmmThreads = 256;
@@ -42,13 +43,18 @@ __global__ void __launch_bounds__(kSpmmThreads, (CHUNKS == 1) ? 4 : 1) spmm_rbs_
   const int lane = threadIdx.x & 31;
   const int gl = threadIdx.x % GROUP;
   const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane - gl));
+  // A team owns rpt consecutive rows.  rpt = GROUP suits sparse rows (papers100M: 14 edges per
+  // row, 460 per team); on dense graphs (Reddit: 490 per row) 32 rows per team left 7,288 warps
+  // for the whole graph, each walking 15,000 edges at one DRAM round trip per U of them, so the
+  // host lowers rpt until a team holds a few hundred edges.
+  const int rpt = (a.rows_per_team > 0 && a.rows_per_team < GROUP) ? a.rows_per_team : GROUP;
   const int64_t team = ((int64_t)blockIdx.x * kSpmmThreads + threadIdx.x) / GROUP;
-  const int64_t r0 = team * GROUP;
+  const int64_t r0 = team * rpt;
   if (r0 >= a.n_rows) return;
-  const int64_t rlo = (r0 + gl < a.n_rows) ? r0 + gl : a.n_rows;
-  const int64_t rhi = (r0 + gl + 1 < a.n_rows) ? r0 + gl + 1 : a.n_rows;
+  const int nr = (int)((a.n_rows - r0) < (int64_t)rpt ? (a.n_rows - r0) : (int64_t)rpt);
+  const int64_t rlo = r0 + (gl < nr ? gl : nr);          // lanes past the team's rows hold an
+  const int64_t rhi = r0 + (gl + 1 < nr ? gl + 1 : nr);  // empty range at the team's end
   const int64_t lo = __ldg(a.rowptr + rlo), hi = __ldg(a.rowptr + rhi);
-  const int nr = (int)((a.n_rows - r0) < (int64_t)GROUP ? (a.n_rows - r0) : (int64_t)GROUP);
   const bool is_long = a.skip_deg_gt > 0 && (hi - lo) > a.skip_deg_gt;
   const unsigned longs = __ballot_sync(gmask, is_long) & gmask;
 
@@ -319,7 +325,9 @@ inline void spmm_rbs_launch(const SpmmArgs<T>& a, cudaStream_t st) {
   constexpr int WORDS = CHUNKS * VecRaw<T, VEC>::W;
   constexpr int U0 = (WORDS <= 4) ? 8 : (WORDS <= 12 ? 4 : 2);
   constexpr int U = U0 < GROUP ? U0 : GROUP;
-  const int64_t grid = (a.n_rows + kSpmmThreads - 1) / kSpmmThreads;  // 256 rows per CTA for every GROUP
+  const int rpt = (a.rows_per_team > 0 && a.rows_per_team < GROUP) ? a.rows_per_team : GROUP;
+  const int64_t teams = (a.n_rows + rpt - 1) / rpt;
+  const int64_t grid = (teams * GROUP + kSpmmThreads - 1) / kSpmmThreads;
   spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U><<<(unsigned)grid, kSpmmThreads, 0, st>>>(a);
 }
 
@@ -349,7 +357,7 @@ inline int spmm_main_vec(const SpmmArgs<T>& a0, cudaStream_t st) {
 
 template <typename T>
 inline int spmm_main(const SpmmArgs<T>& a, cudaStream_t st) {
-  GNN_REQUIRE((a.n_rows + kSpmmThreads - 1) / kSpmmThreads < 0x7fffffffLL, GNN_ERR_UNSUPPORTED, "too many rows");
+  GNN_REQUIRE(a.n_rows < (1LL << 33), GNN_ERR_UNSUPPORTED, "too many rows");  // grid <= n_rows / 8
   const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F);
   if (sizeof(T) == 2 && vec == 8) return spmm_main_vec<T, (sizeof(T) == 2 ? 8 : 4)>(a, st);
   if (vec >= 4) return spmm_main_vec<T, 4>(a, st);

@@ -55,12 +55,13 @@ def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, p
         raise _lib.GnnError(f"spmm: unsupported dtype {X.dtype} (fp32 and bf16 only)")
     f32 = X.dtype == torch.float32
     plan = g.long_row_plan() if planned else None
-    if plan is not None or accumulate:
+    if planned or accumulate:
         lr, thr, chunk_off, n_chunks, chunk, ws = plan if plan is not None else (None, 0, None, 0, 0, None)
         fn = lib.gnn_spmm_csr_planned_f32 if f32 else lib.gnn_spmm_csr_planned_bf16
         _lib.check(fn(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F, _ld(X), _ld(out),
                       _p(lr), 0 if lr is None else lr.numel(), thr, _p(chunk_off), n_chunks, chunk,
-                      1 if accumulate else 0, _p(ws), 0 if ws is None else ws.numel(), st),
+                      1 if accumulate else 0, g.rows_per_team() if planned else 0, _p(ws),
+                      0 if ws is None else ws.numel(), st),
                    "gnn_spmm_csr_planned")
     else:
         fn = lib.gnn_spmm_csr_f32 if f32 else lib.gnn_spmm_csr_bf16

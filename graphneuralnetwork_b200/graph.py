@@ -108,6 +108,20 @@ class CSRGraph:
                 self._plan = (lr, thr, chunk_off, n_chunks, chunk, ws)
         return self._plan or None
 
+    def rows_per_team(self) -> int:
+        """Host-side plan for the row-block streaming SpMM: how many consecutive rows one
+        sub-warp team streams, chosen so that a team holds about `spmm.team_edges` edges of
+        the rows that are not long (1..32; the kernel clamps to its team width)."""
+        if getattr(self, "_rpt", None) is None:
+            lr = self.long_rows()
+            short_nnz = self.nnz
+            if lr.numel() > 0:
+                short_nnz -= int((self.rowptr[lr + 1] - self.rowptr[lr]).sum().item())
+            mean = short_nnz / max(self.n_rows - lr.numel(), 1)
+            target = _lib.get_tuning("spmm.team_edges")
+            self._rpt = int(min(32, max(1, -(-target // max(int(mean + 0.5), 1)))))
+        return self._rpt
+
     def gat_long_rows(self):
         """(long_rows int64, threshold): rows the attention kernels hand to a whole CTA (host-side plan,
         cached)."""

@@ -126,22 +126,25 @@ int gnn_spmm_csr_bf16(const int64_t* rowptr, const int32_t* col, const float* va
  * (gnn_spmm_csr_workspace_size) and are added per row in chunk order: deterministic.
  * All other rows take the row-block streaming kernel.  n_long may be 0 (no plan arrays
  * needed); accumulate=1 adds into Y (the remote-column pass of the partitioned SpMM,
- * SURVEY.md §8e).  The plan is host logic computed once
- * per graph (graphneuralnetwork_b200/graph.py CSRGraph.long_row_plan). */
+ * SURVEY.md §8e).  rows_per_team (0 = default) is how many consecutive rows one sub-warp
+ * team streams: the default suits sparse rows (papers100M-shaped, 14 edges per row); the
+ * host lowers it on dense graphs (Reddit-shaped, 490 per row) so that a team holds a few
+ * hundred edges and the grid has enough warps.  The plan is host logic computed once
+ * per graph (graphneuralnetwork_b200/graph.py CSRGraph.long_row_plan / rows_per_team). */
 size_t gnn_spmm_csr_workspace_size(int64_t n_chunks, int32_t elem_size);
 int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const float* val,
                              const float* X, float* Y, int64_t n_rows, int64_t n_cols, int32_t F,
                              int64_t ldx, int64_t ldy,
                              const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
-                             int accumulate /*1: Y += A*X*/,
+                             int accumulate /*1: Y += A*X*/, int32_t rows_per_team,
                              void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const float* val,
                               const void* X, void* Y, int64_t n_rows, int64_t n_cols, int32_t F,
                               int64_t ldx, int64_t ldy,
                               const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                               const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
-                              int accumulate,
+                              int accumulate, int32_t rows_per_team,
                               void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 
 /* ---- GraphSAGE: fused gather + reduce over fixed-fanout index blocks ----------- */

@@ -167,6 +167,31 @@ def test_spmm_long_rows_chunked(lib, F):
     assert rel_err(Yb.float().cpu().numpy(), ogcn.spmm_f64(rowptr, col, val, Xb.float().cpu().numpy())) < TOLBF
 
 
+@pytest.mark.parametrize("F", [16, 128, 602])
+def test_spmm_rows_per_team(lib, F):
+    """Dense rows: the host plan gives a team fewer rows than its lanes (CSRGraph.rows_per_team);
+    every team height gives the same bits (rows are always added in CSR order)."""
+    n_rows, n_cols = 1003, 1500
+    rowptr, col, val = random_csr(n_rows, n_cols, 300, seed=F)
+    X = np.random.default_rng(F + 5).standard_normal((n_cols, F)).astype(np.float32)
+    csr = CSRGraph(cuda(rowptr), cuda(col), cuda(val), n_rows, n_cols)
+    assert csr.rows_per_team() == 2  # ceil(512 / 300)
+    ref = ogcn.spmm_f64(rowptr, col, val, X)
+    Y = Fn.spmm_raw(csr, cuda(X))
+    assert rel_err(Y.cpu().numpy(), ref) < TOL32
+    Yacc = Fn.spmm_raw(csr, cuda(X), out=Y.clone(), accumulate=True)
+    assert rel_err(Yacc.cpu().numpy(), 2 * ref) < TOL32
+    try:
+        for rpt in (1, 3, 5, 31, 32, 64):
+            _lib.set_tuning("spmm.rows_per_team", rpt)
+            assert torch.equal(Fn.spmm_raw(csr, cuda(X)), Y), rpt
+    finally:
+        _lib.set_tuning("spmm.rows_per_team", 0)
+    Xb = cuda(X).to(torch.bfloat16)
+    refb = ogcn.spmm_f64(rowptr, col, val, Xb.float().cpu().numpy())
+    assert rel_err(Fn.spmm_raw(csr, Xb).float().cpu().numpy(), refb) < TOLBF
+
+
 def test_spmm_strided_and_empty(lib):
     rowptr, col, val = random_csr(100, 100, 5, seed=9)
     csr = CSRGraph(cuda(rowptr), cuda(col), cuda(val), 100, 100)

@@ -73,7 +73,7 @@ def bench_spmm(args, n, mean_deg, tag):
     deg = csr.rowptr[1:] - csr.rowptr[:-1]
     emit(bench=tag + "_graph", n=n, nnz=csr.nnz, max_deg=int(deg.max()), long_rows=int(csr.long_rows().numel()))
     for F in args.Fs:
-        for dt in ([torch.float32, torch.bfloat16] if args.bf16 else [torch.float32]):
+        for dt in ([torch.bfloat16] if args.only_bf16 else [torch.float32, torch.bfloat16] if args.bf16 else [torch.float32]):
             # 16-byte rows, as bench.py and the drop-in layers allocate them (602 -> ld 604 / 608)
             X = Fn.pad_table(torch.randn(n, F, device=DEV).to(dt))
             Y = Fn._padded_empty(n, F, dt, DEV)
@@ -81,10 +81,13 @@ def bench_spmm(args, n, mean_deg, tag):
             B = csr.nnz * 8 + csr.nnz * F * es + n * F * es + (n + 1) * 8
             comp = csr.nnz * 8 + 2 * n * F * es + (n + 1) * 8
             for planned in ([True, False] if args.both else [True]):
-                med, best = timeit(lambda: Fn.spmm_raw(csr, X, out=Y, planned=planned), reps=args.reps)
-                emit(bench=tag, F=F, dtype=str(dt), planned=planned, ms=med, ms_best=best, gather_gbs=B / med / 1e6,
-                     gather_frac=B / med / 1e6 / PEAK, compulsory_gbs=comp / med / 1e6,
-                     edges_per_s=csr.nnz / med * 1e3, X_mb=n * F * es / 1e6)
+                for knobs in args.knobs:
+                    for k, v in knobs.items():
+                        _lib.set_tuning(k, v)
+                    med, best = timeit(lambda: Fn.spmm_raw(csr, X, out=Y, planned=planned), reps=args.reps)
+                    emit(bench=tag, F=F, dtype=str(dt), planned=planned, knobs=knobs, rows_per_team=csr.rows_per_team(),
+                         ms=med, ms_best=best, gather_gbs=B / med / 1e6, gather_frac=B / med / 1e6 / PEAK,
+                         compulsory_gbs=comp / med / 1e6, edges_per_s=csr.nnz / med * 1e3, X_mb=n * F * es / 1e6)
             del X, Y
 
 
@@ -117,6 +120,7 @@ if __name__ == "__main__":
     ap.add_argument("--F", type=int, default=602)
     ap.add_argument("--Fs", type=int, nargs="+", default=[16, 64, 128, 602])
     ap.add_argument("--bf16", action="store_true")
+    ap.add_argument("--only-bf16", action="store_true")
     ap.add_argument("--both", action="store_true")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--n", type=int, default=0)
