@@ -38,6 +38,7 @@ static std::map<std::string, int>& tune_map() {
       {"sage.chunk_bytes", 12288},  // bytes per ring stage
       {"sage.force_ldg", 0},     // 1: never take the TMA path
       {"sage.ctas_per_sm", 4},
+      {"sage.packed_add", -1},   // FADD2 in the consumers: -1 = bf16 only, 0 never, 1 always
       {"spmm.long_row", 2048},   // rows above this nnz go to the CTA-per-chunk path (planned call)
       {"spmm.chunk", 8192},      // edges per long-row chunk
       {"spmm.unroll", 0},        // 0 = heuristic

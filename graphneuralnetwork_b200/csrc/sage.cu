@@ -111,7 +111,7 @@ __device__ __forceinline__ void cursor_next(Cursor& c, const SageArgs<T>& a) {
   if (c.c0 >= c.fan) cursor_set(c, a, c.g + gridDim.x);
 }
 
-template <typename T, int NV, int OP>
+template <typename T, int NV, int OP, bool PK = true>
 __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T> a) {
   constexpr int E = Vec16<T>::E;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -217,8 +217,17 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
             const int vi = t + v * kConsumerThreads;
-            if (vi < a.nvec)
-              Vec16<T>::add(*reinterpret_cast<const uint4*>(sb + (size_t)k * a.row_bytes + (size_t)vi * 16), acc[v]);
+            if (vi < a.nvec) {
+              const uint4 w = *reinterpret_cast<const uint4*>(sb + (size_t)k * a.row_bytes + (size_t)vi * 16);
+              if (PK) {
+                Vec16<T>::add(w, acc[v]);
+              } else {
+                float x[E];
+                Vec16<T>::unpack(w, x);
+#pragma unroll
+                for (int i = 0; i < E; ++i) acc[v][i] += x[i];
+              }
+            }
           }
         }
       } else {
@@ -288,17 +297,27 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
   }
 }
 
-template <typename T, int NV, int OP>
-int launch_tma_inst(const SageArgs<T>& a, size_t smem_bytes, int grid, cudaStream_t st) {
+template <typename T, int NV, int OP, bool PK>
+int launch_tma_pk(const SageArgs<T>& a, size_t smem_bytes, int grid, cudaStream_t st) {
   static size_t configured = 0;  // benign race: attribute set is idempotent
   if (smem_bytes > configured) {
-    GNN_CUDA(cudaFuncSetAttribute(sage_tma_kernel<T, NV, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GNN_CUDA(cudaFuncSetAttribute(sage_tma_kernel<T, NV, OP, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_bytes));
     configured = smem_bytes;
   }
-  sage_tma_kernel<T, NV, OP><<<grid, kSageThreads, smem_bytes, st>>>(a);
+  sage_tma_kernel<T, NV, OP, PK><<<grid, kSageThreads, smem_bytes, st>>>(a);
   GNN_LAUNCH_CHECK();
   return GNN_OK;
+}
+
+template <typename T, int NV, int OP>
+int launch_tma_inst(const SageArgs<T>& a, size_t smem_bytes, int grid, cudaStream_t st) {
+  // packed adds pay where the consumers are issue-bound (bf16: 8 unpack + 8 add per 16 bytes);
+  // "sage.packed_add": -1 = by dtype, 0 / 1 = force
+  const int knob = tuning("sage.packed_add", -1);
+  const bool pk = (OP != GNN_REDUCE_MAX) && (knob < 0 ? sizeof(T) == 2 : knob != 0);
+  if (pk) return launch_tma_pk<T, NV, OP, true>(a, smem_bytes, grid, st);
+  return launch_tma_pk<T, NV, OP, false>(a, smem_bytes, grid, st);
 }
 
 template <typename T, int OP>

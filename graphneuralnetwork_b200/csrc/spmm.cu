@@ -11,7 +11,8 @@ template <typename T>
 int spmm_impl(const int64_t* rowptr, const int32_t* col, const float* val, const T* X, T* Y, int64_t n_rows,
               int64_t n_cols, int32_t F, int64_t ldx, int64_t ldy, const int64_t* long_rows, int64_t n_long,
               int64_t long_threshold, const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges, int accumulate,
-              int32_t rows_per_team, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+              int32_t rows_per_team, const float* bias, int32_t relu, void* workspace, size_t workspace_bytes,
+              cudaStream_t st) {
   GNN_REQUIRE(n_rows >= 0 && n_cols >= 0 && F >= 0, GNN_ERR_BAD_ARG, "negative size");
   if (n_rows == 0 || F == 0) return GNN_OK;
   // col may be null only for a graph without edges (nnz lives on the device; rowptr decides)
@@ -33,6 +34,9 @@ int spmm_impl(const int64_t* rowptr, const int32_t* col, const float* val, const
   a.skip_deg_gt = 0;
   a.accumulate = accumulate ? 1 : 0;
   GNN_REQUIRE(rows_per_team >= 0, GNN_ERR_BAD_ARG, "rows_per_team must be >= 0");
+  GNN_REQUIRE(!(accumulate && (bias || relu)), GNN_ERR_BAD_ARG, "the bias/ReLU epilogue belongs to the final pass");
+  a.bias = bias;
+  a.relu = relu ? 1 : 0;
   a.rows_per_team = tuning("spmm.rows_per_team", 0) > 0 ? tuning("spmm.rows_per_team", 0) : rows_per_team;
   if (n_long > 0) {
     GNN_REQUIRE(long_rows && chunk_off && long_threshold > 0 && chunk_edges > 0 && n_chunks >= n_long, GNN_ERR_BAD_ARG,
@@ -60,22 +64,23 @@ size_t gnn_spmm_csr_workspace_size(int64_t n_chunks, int32_t elem_size) {
 int gnn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, const float* X, float* Y,
                      int64_t n_rows, int64_t n_cols, int32_t F, int64_t ldx, int64_t ldy, gnn_stream_t stream) {
   return spmm_impl<float>(rowptr, col, val, X, Y, n_rows, n_cols, F, ldx, ldy, nullptr, 0, 0, nullptr, 0, 0, 0, 0,
-                          nullptr, 0, (cudaStream_t)stream);
+                          nullptr, 0, nullptr, 0, (cudaStream_t)stream);
 }
 
 int gnn_spmm_csr_bf16(const int64_t* rowptr, const int32_t* col, const float* val, const void* X, void* Y,
                       int64_t n_rows, int64_t n_cols, int32_t F, int64_t ldx, int64_t ldy, gnn_stream_t stream) {
   return spmm_impl<__nv_bfloat16>(rowptr, col, val, (const __nv_bfloat16*)X, (__nv_bfloat16*)Y, n_rows, n_cols, F, ldx,
-                                  ldy, nullptr, 0, 0, nullptr, 0, 0, 0, 0, nullptr, 0, (cudaStream_t)stream);
+                                  ldy, nullptr, 0, 0, nullptr, 0, 0, 0, 0, nullptr, 0, nullptr, 0, (cudaStream_t)stream);
 }
 
 int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const float* val, const float* X, float* Y,
                              int64_t n_rows, int64_t n_cols, int32_t F, int64_t ldx, int64_t ldy,
                              const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges, int accumulate,
-                             int32_t rows_per_team, void* workspace, size_t workspace_bytes, gnn_stream_t stream) {
+                             int32_t rows_per_team, const float* bias, int32_t relu, void* workspace,
+                             size_t workspace_bytes, gnn_stream_t stream) {
   return spmm_impl<float>(rowptr, col, val, X, Y, n_rows, n_cols, F, ldx, ldy, long_rows, n_long, long_threshold,
-                          chunk_off, n_chunks, chunk_edges, accumulate, rows_per_team, workspace, workspace_bytes,
+                          chunk_off, n_chunks, chunk_edges, accumulate, rows_per_team, bias, relu, workspace, workspace_bytes,
                           (cudaStream_t)stream);
 }
 
@@ -83,10 +88,11 @@ int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const f
                               int64_t n_rows, int64_t n_cols, int32_t F, int64_t ldx, int64_t ldy,
                               const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                               const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges, int accumulate,
-                              int32_t rows_per_team, void* workspace, size_t workspace_bytes, gnn_stream_t stream) {
+                              int32_t rows_per_team, const float* bias, int32_t relu, void* workspace,
+                              size_t workspace_bytes, gnn_stream_t stream) {
   return spmm_impl<__nv_bfloat16>(rowptr, col, val, (const __nv_bfloat16*)X, (__nv_bfloat16*)Y, n_rows, n_cols, F, ldx,
                                   ldy, long_rows, n_long, long_threshold, chunk_off, n_chunks, chunk_edges, accumulate,
-                                  rows_per_team, workspace, workspace_bytes, (cudaStream_t)stream);
+                                  rows_per_team, bias, relu, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -31,14 +31,31 @@ struct SpmmArgs {
   int64_t skip_deg_gt;  // >0: rows with more edges belong to the long-row kernels
   int32_t accumulate;   // 1: Y += Â·X (second pass of the partitioned SpMM), 0: Y = Â·X
   int32_t rows_per_team;  // rows a team of GROUP lanes owns (1..GROUP); 0 = GROUP
+  // fused epilogue of the GCN layer (GCN/GCN.py:44-45 `output + self.bias`, GCN.py:12 nn.ReLU):
+  const float* bias;      // nullable, [F] fp32, added to every row
+  int32_t relu;           // 1: max(., 0) after the bias
 };
+
+// y = relu?(acc + bias[col0..]) for the VEC columns starting at col0 (columns >= F are padding)
+template <int VEC>
+__device__ __forceinline__ void spmm_epilogue(float (&acc)[VEC], const float* bias, int relu, int col0, int F) {
+  if (bias) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      if (col0 + i < F) acc[i] += __ldg(bias + col0 + i);
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = fmaxf(acc[i], 0.f);
+  }
+}
 
 constexpr int kSpmmThreads = 256;
 
 // One-vector-per-lane variants are held to 64 registers (4 CTAs/SM): next to the 3 CTAs that a
 // concurrently running halo-push CTA leaves room for, this keeps the local-column pass of the
 // partitioned SpMM at full occupancy (at 80 registers it dropped from 3 to 2 CTAs per SM).
-template <typename T, int VEC, int GROUP, int CHUNKS, int U>
+template <typename T, int VEC, int GROUP, int CHUNKS, int U, bool EPI>
 __global__ void __launch_bounds__(kSpmmThreads, (CHUNKS == 1) ? 4 : 1) spmm_rbs_kernel(const SpmmArgs<T> a) {
   const int lane = threadIdx.x & 31;
   const int gl = threadIdx.x % GROUP;
@@ -76,6 +93,7 @@ __global__ void __launch_bounds__(kSpmmThreads, (CHUNKS == 1) ? 4 : 1) spmm_rbs_
 #pragma unroll
           for (int i = 0; i < VEC; ++i) acc[ch][i] += prev[i];
         }
+        if (EPI) spmm_epilogue<VEC>(acc[ch], a.bias, a.relu, col0, a.F);
         VecIO<T, VEC>::store(yr + col0, acc[ch]);
       }
 #pragma unroll
@@ -290,7 +308,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     spmm_long_finalize_kernel(const int64_t* __restrict__ long_rows, const int64_t* __restrict__ chunk_off,
                               const float* __restrict__ partial, int ldp, int col_base, int Ftile, T* __restrict__ Y,
-                              int64_t ldy, int accumulate) {
+                              int64_t ldy, int accumulate, const float* __restrict__ bias, int relu) {
   const int64_t r = blockIdx.x;
   const int64_t row = __ldg(long_rows + r);
   const int64_t c0 = __ldg(chunk_off + r), c1 = __ldg(chunk_off + r + 1);
@@ -302,6 +320,8 @@ __global__ void __launch_bounds__(256)
       VecIO<T, 1>::load(Y + row * ldy + col_base + f, prev);
       sum += prev[0];
     }
+    if (bias) sum += __ldg(bias + col_base + f);
+    if (relu) sum = fmaxf(sum, 0.f);
     float o[1] = {sum};
     VecIO<T, 1>::store(Y + row * ldy + col_base + f, o);
   }
@@ -328,7 +348,9 @@ inline void spmm_rbs_launch(const SpmmArgs<T>& a, cudaStream_t st) {
   const int rpt = (a.rows_per_team > 0 && a.rows_per_team < GROUP) ? a.rows_per_team : GROUP;
   const int64_t teams = (a.n_rows + rpt - 1) / rpt;
   const int64_t grid = (teams * GROUP + kSpmmThreads - 1) / kSpmmThreads;
-  spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U><<<(unsigned)grid, kSpmmThreads, 0, st>>>(a);
+  // the bias/ReLU epilogue is a separate instantiation: the plain one keeps its register budget
+  if (a.bias || a.relu) spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, true><<<(unsigned)grid, kSpmmThreads, 0, st>>>(a);
+  else spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false><<<(unsigned)grid, kSpmmThreads, 0, st>>>(a);
 }
 
 template <typename T, int VEC>
@@ -338,6 +360,7 @@ inline int spmm_main_vec(const SpmmArgs<T>& a0, cudaStream_t st) {
     SpmmArgs<T> a = a0;
     a.X = a0.X + c0;
     a.Y = a0.Y + c0;
+    a.bias = a0.bias ? a0.bias + c0 : nullptr;
     a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
     const int nvec = (a.F + VEC - 1) / VEC;
     if (nvec <= 4) spmm_rbs_launch<T, VEC, 4, 1>(a, st);
@@ -388,7 +411,7 @@ inline int spmm_long_vec(const SpmmArgs<T>& a0, const int64_t* long_rows, int64_
 #undef GNN_LONG
     GNN_LAUNCH_CHECK();
     spmm_long_finalize_kernel<T><<<(unsigned)n_long, 256, 0, st>>>(long_rows, chunk_off, partial, ldp, c0, a.F, a0.Y,
-                                                                   a0.ldy, a0.accumulate);
+                                                                   a0.ldy, a0.accumulate, a0.bias, a0.relu);
     GNN_LAUNCH_CHECK();
   }
   return GNN_OK;

@@ -40,8 +40,9 @@ def _padded_empty(rows: int, F: int, dtype, device) -> torch.Tensor:
 # GCN: Y = Â·X
 # --------------------------------------------------------------------------------------
 def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, planned: bool = True,
-             accumulate: bool = False) -> torch.Tensor:
-    """Y = Â·X (or Y += Â·X into `out`) through gnn_spmm_csr_* (no autograd)."""
+             accumulate: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """Y = Â·X (or Y += Â·X into `out`) through gnn_spmm_csr_* (no autograd).
+    bias / relu: fused epilogue Y = relu?(Â·X + bias) of the planned entry point."""
     _require_cuda(X)
     lib = _lib.load()
     X = _rowmajor(X)
@@ -55,13 +56,18 @@ def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, p
         raise _lib.GnnError(f"spmm: unsupported dtype {X.dtype} (fp32 and bf16 only)")
     f32 = X.dtype == torch.float32
     plan = g.long_row_plan() if planned else None
-    if planned or accumulate:
+    if bias is not None:
+        _require_cuda(bias)
+        if bias.dtype != torch.float32 or bias.numel() != F:
+            raise _lib.GnnError(f"spmm: bias must be fp32 with {F} entries")
+        bias = bias.contiguous()
+    if planned or accumulate or bias is not None or relu:
         lr, thr, chunk_off, n_chunks, chunk, ws = plan if plan is not None else (None, 0, None, 0, 0, None)
         fn = lib.gnn_spmm_csr_planned_f32 if f32 else lib.gnn_spmm_csr_planned_bf16
         _lib.check(fn(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, g.n_cols, F, _ld(X), _ld(out),
                       _p(lr), 0 if lr is None else lr.numel(), thr, _p(chunk_off), n_chunks, chunk,
-                      1 if accumulate else 0, g.rows_per_team() if planned else 0, _p(ws),
-                      0 if ws is None else ws.numel(), st),
+                      1 if accumulate else 0, g.rows_per_team() if planned else 0, _p(bias), 1 if relu else 0,
+                      _p(ws), 0 if ws is None else ws.numel(), st),
                    "gnn_spmm_csr_planned")
     else:
         fn = lib.gnn_spmm_csr_f32 if f32 else lib.gnn_spmm_csr_bf16
@@ -86,6 +92,37 @@ class _SpmmFn(torch.autograd.Function):
 def spmm(g: CSRGraph, X: torch.Tensor) -> torch.Tensor:
     """Y = Â·X with autograd (replaces torch.spmm(adj, support), GCN/GCN.py:43)."""
     return _SpmmFn.apply(X, g)
+
+
+class _GcnAggregateFn(torch.autograd.Function):
+    """Y = relu?(Â·S + b) in ONE launch: the aggregation (GCN/GCN.py:43), the bias add
+    (GCN.py:44-45) and the ReLU that follows every hidden layer (GCN.py:12,19) fused into the
+    row flush of the SpMM.  Backward: dZ = dY ⊙ [Y > 0];  dS = Âᵀ·dZ;  db = Σ_rows dZ."""
+
+    @staticmethod
+    def forward(ctx, S, bias, g: CSRGraph, relu: bool):
+        Y = spmm_raw(g, S, bias=bias, relu=relu)
+        ctx.g, ctx.relu, ctx.has_bias = g, relu, bias is not None
+        if relu:
+            ctx.save_for_backward(Y)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        dZ = dY
+        if ctx.relu:
+            (Y,) = ctx.saved_tensors
+            dZ = dY * (Y > 0).to(dY.dtype)
+        dS = spmm_raw(ctx.g.transpose(), dZ.contiguous()) if ctx.needs_input_grad[0] else None
+        db = dZ.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        return dS, db, None, None
+
+
+def gcn_aggregate(g: CSRGraph, S: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """relu?(Â·S + bias) with autograd into S and bias (fp32 bias; S fp32 or bf16)."""
+    if bias is not None and bias.dtype != torch.float32:
+        bias = bias.float()
+    return _GcnAggregateFn.apply(S, bias, g, relu)
 
 
 # --------------------------------------------------------------------------------------
@@ -263,7 +300,8 @@ def gat_scores_raw(Wh: torch.Tensor, a_src: torch.Tensor, a_dst: torch.Tensor, H
     return s, t
 
 
-def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=0, keep=None, save_stats=False):
+def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=0, keep=None, save_stats=False,
+                out=None):
     _require_cuda(Wh, s, t, keep)
     lib = _lib.load()
     Wh = _rowmajor(Wh)
@@ -272,7 +310,10 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
     n = g.n_rows
     if Wh.shape != (n, H * Fp) or g.n_cols != n:
         raise _lib.GnnError(f"gat: Wh {tuple(Wh.shape)} does not match graph n={n}, H*Fp={H * Fp}")
-    out = torch.empty((n, H * Fp), dtype=torch.float32, device=Wh.device)
+    if out is None:
+        out = torch.empty((n, H * Fp), dtype=torch.float32, device=Wh.device)
+    elif out.shape != (n, H * Fp) or out.dtype != torch.float32 or out.stride(1) != 1 or not out.is_cuda:
+        raise _lib.GnnError("gat: `out` must be a CUDA fp32 [n, H*Fp] view with unit column stride")
     row_max = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     row_sum = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     col_mean = Wh.mean(dim=0).contiguous() if g.has_empty_rows() else None
@@ -324,7 +365,8 @@ class _GatFn(torch.autograd.Function):
 
 
 def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tensor, H: int, Fp: int, alpha: float,
-                  mode: int = _lib.GAT_SOFTMAX, elu: int = 0, keep: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  mode: int = _lib.GAT_SOFTMAX, elu: int = 0, keep: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused edge-score + LeakyReLU + edge-softmax + weighted aggregation over all H heads.
 
     With gradients enabled the kernel returns the pre-activation aggregate and the ELU(s)
@@ -332,11 +374,15 @@ def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tenso
     them; without gradients the ELU is fused into the kernel's epilogue."""
     need_grad = torch.is_grad_enabled() and (Wh.requires_grad or s.requires_grad or t.requires_grad)
     if not need_grad:
-        return gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep)[0]
-    out = _GatFn.apply(Wh, s, t, g, H, Fp, alpha, mode, keep)
+        # `out` (optional): a strided [n, H*Fp] view the kernel writes in place, e.g. one metapath's
+        # slice of HAN's [N, M, H*Fp] semantic stack
+        return gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep, out=out)[0]
+    res = _GatFn.apply(Wh, s, t, g, H, Fp, alpha, mode, keep)
     for _ in range(elu):
-        out = torch.nn.functional.elu(out)
-    return out
+        res = torch.nn.functional.elu(res)
+    if out is not None:
+        raise _lib.GnnError("gat_aggregate: `out` is only supported without autograd")
+    return res
 
 
 def attention_keep_mask(g: CSRGraph, H: int, p: float, generator: Optional[torch.Generator] = None) -> torch.Tensor:

@@ -17,7 +17,7 @@ from ..functional import attention_keep_mask, gat_aggregate
 from ..graph import adj_cache
 
 
-def _fused_heads(x, adj, Ws, a_srcs, a_dsts, alpha, mode, elu, dropout, training):
+def _fused_heads(x, adj, Ws, a_srcs, a_dsts, alpha, mode, elu, dropout, training, out=None):
     """All heads of one attention layer: x [N,in]; Ws list of [in,F']; a_* list of [F']."""
     g = adj_cache.get(adj)
     H = len(Ws)
@@ -32,7 +32,7 @@ def _fused_heads(x, adj, Ws, a_srcs, a_dsts, alpha, mode, elu, dropout, training
     keep = None
     if training and dropout > 0.0:
         keep = attention_keep_mask(g, H, dropout)  # post-softmax dropout, layers.py:31
-    return gat_aggregate(g, Wh, s, t, H, Fp, alpha, mode=mode, elu=elu, keep=keep)
+    return gat_aggregate(g, Wh, s, t, H, Fp, alpha, mode=mode, elu=elu, keep=keep, out=out)
 
 
 class GraphAttentionLayer(nn.Module):
@@ -95,52 +95,54 @@ class SpGraphAttentionLayer(nn.Module):
 
 
 class GATBase(nn.Module):
-    """GAT/models/GAT.py:7-18.  All heads in `self.attentions` run in one fused launch."""
+    """Two-layer GAT skeleton (GAT/models/GAT.py:7-18): `attentions` = the first layer's heads
+    (state_dict `attentions.AttentionHead{k}.{W,a}`), `out_att` = the single-head output layer.
+    `_head_cls` / `_mode` select the masked-softmax (dense) or exp(-LeakyReLU) (edge-list) scores.
+    The heads never run one by one: `forward` hands all of them to one fused launch, whose
+    column block k is head k — the reference's `torch.cat(..., dim=1)`."""
 
+    _head_cls = None
     _mode = _lib.GAT_SOFTMAX
 
     def __init__(self, dropout, **kwargs):
-        super(GATBase, self).__init__(**kwargs)
+        super().__init__(**kwargs)
         self.dropout = dropout
         self.attentions = nn.ModuleList()
         self.out_att = None
 
-    def _heads(self, x, adj):
-        atts = list(self.attentions)
-        halves = [att._halves() for att in atts]
-        head0 = atts[0]
-        p = head0.dropout.p if isinstance(head0.dropout, nn.Dropout) else head0.dropout
-        # concat=True heads apply ELU (layers.py:35); cat over heads == column blocks k*F'..(k+1)*F'
-        return _fused_heads(x, adj, [att.W for att in atts], [h[0] for h in halves], [h[1] for h in halves],
-                            head0.alpha, self._mode, 1 if head0.concat else 0, p, self.training)
+    def _build(self, nfeat, nhid, nclass, alpha, nheads):
+        for k in range(nheads):
+            self.attentions.add_module(f'AttentionHead{k}', self._head_cls(nfeat, nhid, self.dropout, alpha, True))
+        self.out_att = self._head_cls(nhid * nheads, nclass, self.dropout, alpha, False)
 
     def forward(self, x, adj):
-        adj = adj_cache.get(adj)
+        graph = adj_cache.get(adj)  # CSR of adj > 0, built once per adjacency tensor
+        heads = list(self.attentions)
+        halves = [head._halves() for head in heads]
+        p_att = heads[0].dropout.p if isinstance(heads[0].dropout, nn.Dropout) else heads[0].dropout
         x = F.dropout(x, self.dropout, training=self.training)
-        x = self._heads(x, adj)
+        x = _fused_heads(x, graph, [head.W for head in heads], [h[0] for h in halves], [h[1] for h in halves],
+                         heads[0].alpha, self._mode, 1 if heads[0].concat else 0, p_att, self.training)
         x = F.dropout(x, self.dropout, training=self.training)
-        return F.elu(self.out_att(x, adj))
+        return F.elu(self.out_att(x, graph))
 
 
 class GAT(GATBase):
-    """Dense-adjacency GAT (GAT/models/GAT.py:21-28)."""
+    """Dense-adjacency GAT (GAT/models/GAT.py:21-28): `adj` is used only as the mask `adj > 0`."""
+
+    _head_cls = GraphAttentionLayer
 
     def __init__(self, nfeat, nhid, nclass, dropout, alpha, nheads, **kwargs):
-        super(GAT, self).__init__(dropout, **kwargs)
-        for i in range(nheads):
-            self.attentions.add_module(f'AttentionHead{i}',
-                                       GraphAttentionLayer(nfeat, nhid, dropout=dropout, alpha=alpha, concat=True))
-        self.out_att = GraphAttentionLayer(nhid * nheads, nclass, dropout=dropout, alpha=alpha, concat=False)
+        super().__init__(dropout, **kwargs)
+        self._build(nfeat, nhid, nclass, alpha, nheads)
 
 
 class SpGAT(GATBase):
     """Edge-list GAT (GAT/models/GAT.py:31-38)."""
 
+    _head_cls = SpGraphAttentionLayer
     _mode = _lib.GAT_EXPNEG
 
     def __init__(self, nfeat, nhid, nclass, dropout, alpha, nheads, **kwargs):
-        super(SpGAT, self).__init__(dropout, **kwargs)
-        for i in range(nheads):
-            self.attentions.add_module(f'AttentionHead{i}',
-                                       SpGraphAttentionLayer(nfeat, nhid, dropout=dropout, alpha=alpha, concat=True))
-        self.out_att = SpGraphAttentionLayer(nhid * nheads, nclass, dropout=dropout, alpha=alpha, concat=False)
+        super().__init__(dropout, **kwargs)
+        self._build(nfeat, nhid, nclass, alpha, nheads)

@@ -1,11 +1,20 @@
-"""Drop-in HAN node-level attention, semantic attention and model (class names, ctor
-signatures, parameter names and forward signatures of /root/reference
-HAN/models/NodeAttention.py, SemanticAttention.py and HAN.py).
+"""Drop-in HAN node-level attention, semantic attention and model for /root/reference
+HAN/models/NodeAttention.py:44-62, SemanticAttention.py:5-20 and HAN.py:7-41.
 
-Each metapath's `GATConv` (HAN/models/NodeAttention.py:44-62) runs its 8 heads in one fused
-launch over the CSR of that metapath's float64 0/1 adjacency (`adj > 0`); the second
-`F.elu` the reference applies when `num_class is None` (NodeAttention.py:62) is kept and
-fused as a double ELU.  `SemanticAttention` is a small dense reduce and stays torch.
+Fixed by the reference: class names, constructor / forward signatures and the state_dict keys
+(`layers.{l}.gat_layers.meta_path_model{m}.attentions.AttentionHead{k}.{W,a}`,
+`layers.{l}.semantic_attention.project.{0,2}.*`, `predict.*`).
+
+Re-designed for the device:
+  * each metapath's `GATConv` runs all its heads in ONE fused launch over the CSR of that
+    metapath's float64 0/1 adjacency (`adj > 0`, converted once and cached);
+  * the second `F.elu` the reference applies when `num_class is None` (NodeAttention.py:62) is
+    fused into the same kernel's epilogue (double ELU) whenever no dropout sits between them;
+  * without autograd the M metapath kernels write straight into their `[:, m, :]` slice of the
+    `[N, M, H·F']` semantic stack — `torch.stack` (HAN.py:21) never copies;
+  * semantic attention (SemanticAttention.py:15-20) reduces the `[N·M, ·]` projection to M scores
+    and applies `softmax_M` as one `[M] x [N, M, D]` contraction instead of broadcasting β to
+    `[N, M, 1]` and materialising `β·z`.
 """
 import torch
 from torch import nn
@@ -17,82 +26,90 @@ from .gat import GraphAttentionLayer, _fused_heads
 
 
 class GATConv(nn.Module):
+    """Multi-head node attention over one metapath graph (NodeAttention.py:44-62)."""
+
     def __init__(self, feat_size, hidden_size, dropout, num_heads, alpha=0.2, num_class=None, **kwargs):
-        super(GATConv, self).__init__(**kwargs)
-        self.dropout = dropout
+        super().__init__(**kwargs)
+        self.dropout, self.num_class = dropout, num_class
         self.attentions = nn.ModuleList()
-        for i in range(num_heads):
-            self.attentions.add_module(f'AttentionHead{i}',
-                                       GraphAttentionLayer(feat_size, hidden_size, dropout=dropout, alpha=alpha,
-                                                           concat=True))
-        self.num_class = num_class
-        if self.num_class is not None:
+        for k in range(num_heads):
+            self.attentions.add_module(f'AttentionHead{k}', GraphAttentionLayer(feat_size, hidden_size, dropout=dropout,
+                                                                                alpha=alpha, concat=True))
+        if num_class is not None:
             self.out_att = GraphAttentionLayer(hidden_size * num_heads, num_class, dropout=dropout, alpha=alpha,
                                                concat=False)
 
-    def forward(self, x, adj):
-        adj = adj_cache.get(adj)
+    def forward(self, x, adj, out=None):
+        """`out` (optional, no autograd): a `[N, H·F']` strided view the kernel fills in place."""
+        graph = adj_cache.get(adj)
+        heads = list(self.attentions)
+        halves = [head._halves() for head in heads]
+        drop_active = self.training and self.dropout > 0.0
+        # heads are concat=True => ELU (NodeAttention.py:35); with num_class None the concatenation gets
+        # a second ELU (NodeAttention.py:62), fused as elu=2 unless a dropout separates the two
+        double_elu = self.num_class is None and not drop_active
         x = F.dropout(x, self.dropout, training=self.training)
-        atts = list(self.attentions)
-        halves = [att._halves() for att in atts]
-        # heads are concat=True (ELU, NodeAttention.py:35); with num_class None the reference
-        # applies F.elu once more to the concatenation (NodeAttention.py:62) => elu=2.  The
-        # F.dropout between them is the identity in eval mode and is applied by torch in training.
-        fuse_second = self.num_class is None and not (self.training and self.dropout > 0.0)
-        x = _fused_heads(x, adj, [att.W for att in atts], [h[0] for h in halves], [h[1] for h in halves],
-                         atts[0].alpha, _lib.GAT_SOFTMAX, 2 if fuse_second else 1, self.dropout, self.training)
-        if fuse_second:
-            return x
-        x = F.dropout(x, self.dropout, training=self.training)
-        return F.elu(self.out_att(x, adj)) if self.num_class is not None else F.elu(x)
+        y = _fused_heads(x, graph, [head.W for head in heads], [h[0] for h in halves], [h[1] for h in halves],
+                         heads[0].alpha, _lib.GAT_SOFTMAX, 2 if double_elu else 1, self.dropout, self.training,
+                         out=out if double_elu else None)
+        if double_elu:
+            return y
+        y = F.dropout(y, self.dropout, training=self.training)
+        y = F.elu(y if self.num_class is None else self.out_att(y, graph))
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
 
 class SemanticAttention(nn.Module):
-    """HAN/models/SemanticAttention.py:5-20 (tiny dense reduce; stays torch)."""
+    """β = softmax_M(mean_N(q·tanh(W z + b)));  out = Σ_m β_m z_m  (SemanticAttention.py:5-20)."""
 
     def __init__(self, in_size, hidden_size=128):
-        super(SemanticAttention, self).__init__()
-        self.project = nn.Sequential(
-            nn.Linear(in_size, hidden_size),
-            nn.Tanh(),
-            nn.Linear(hidden_size, 1, bias=False)
-        )
+        super().__init__()
+        self.project = nn.Sequential(nn.Linear(in_size, hidden_size), nn.Tanh(), nn.Linear(hidden_size, 1, bias=False))
 
     def forward(self, z):
-        w = self.project(z).mean(0)  # (M, 1)
-        beta = torch.softmax(w, dim=0)  # (M, 1)
-        beta = beta.expand((z.shape[0],) + beta.shape)  # (N, M, 1)
-        return (beta * z).sum(1)  # (N, D * K)
+        n, m, d = z.shape
+        scores = self.project(z.reshape(n * m, d)).view(n, m).mean(dim=0)  # [M]
+        beta = torch.softmax(scores, dim=0)
+        return torch.einsum('m,nmd->nd', beta, z)
 
 
 class HANLayer(nn.Module):
+    """M metapath GATs over the same node features + semantic attention (HAN.py:7-23)."""
+
     def __init__(self, num_meta_paths, in_size, out_size, layer_num_heads, dropout, **kwargs):
-        super(HANLayer, self).__init__(**kwargs)
+        super().__init__(**kwargs)
         self.gat_layers = nn.ModuleList()
-        for i in range(num_meta_paths):
-            self.gat_layers.add_module(f'meta_path_model{i}', GATConv(in_size, out_size, dropout, layer_num_heads))
+        for m in range(num_meta_paths):
+            self.gat_layers.add_module(f'meta_path_model{m}', GATConv(in_size, out_size, dropout, layer_num_heads))
         self.semantic_attention = SemanticAttention(in_size=out_size * layer_num_heads)
+        self._width = out_size * layer_num_heads
 
     def forward(self, gs, h):
-        semantic_embeddings = []
-        for g, gat_layer in zip(gs, self.gat_layers):
-            semantic_embeddings.append(gat_layer(h, g).flatten(1))
-        semantic_embeddings = torch.stack(semantic_embeddings, dim=1)  # (N, M, D * K)
-        return self.semantic_attention(semantic_embeddings)
+        convs = list(self.gat_layers)
+        if torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in self.parameters())):
+            z = torch.stack([conv(h, g).flatten(1) for g, conv in zip(gs, convs)], dim=1)  # (N, M, H·F')
+        else:
+            z = h.new_empty(h.shape[0], len(convs), self._width, dtype=torch.float32)
+            for m, (g, conv) in enumerate(zip(gs, convs)):
+                conv(h, g, out=z[:, m, :])
+        return self.semantic_attention(z)
 
 
 class HANModel(nn.Module):
+    """Stack of HANLayers + linear classifier (HAN.py:26-41)."""
+
     def __init__(self, num_mate_paths, in_size, hidden_size, out_size, num_heads, dropout, **kwargs):
-        super(HANModel, self).__init__(**kwargs)
-        self.layers = nn.ModuleList()
-        self.layers.append(HANLayer(num_mate_paths, in_size, hidden_size, num_heads[0], dropout))
-        for l in range(1, len(num_heads)):
-            self.layers.append(
-                HANLayer(num_mate_paths, hidden_size * num_heads[l - 1], hidden_size, num_heads[l], dropout))
-        self.predict = nn.Linear(hidden_size * num_heads[-1], out_size)
+        super().__init__(**kwargs)
+        widths = [in_size] + [hidden_size * k for k in num_heads]
+        self.layers = nn.ModuleList(HANLayer(num_mate_paths, widths[l], hidden_size, num_heads[l], dropout)
+                                    for l in range(len(num_heads)))
+        self.predict = nn.Linear(widths[-1], out_size)
 
     def forward(self, g, h):
-        g = [adj_cache.get(a) for a in g]  # dense float64 masks -> CSR once
-        for gnn in self.layers:
-            h = gnn(g, h)
+        graphs = [adj_cache.get(a) for a in g]  # dense float64 masks -> CSR, once per graph
+        for layer in self.layers:
+            h = layer(graphs, h)
         return self.predict(h)

@@ -28,105 +28,110 @@ class SampledBlock:
 
 
 class NeighborAggregator(nn.Module):
+    """reduce_k(neighbours)·W (+ b) — GraphSAGE_Pytorch/models/Aggregator.py:5-37.
+    state_dict: `weight [in,out]` (+ `bias [out]` with use_bias)."""
+
     def __init__(self, input_dim, output_dim, use_bias=False, aggr_method="mean", **kwargs):
-        super(NeighborAggregator, self).__init__(*kwargs)
-        self.input_dim = input_dim
-        self.output_dim = output_dim
-        self.use_bias = use_bias
-        self.aggr_method = aggr_method
-        self.weight = nn.Parameter(torch.Tensor(input_dim, output_dim))
-        nn.init.xavier_uniform_(self.weight)
-        if self.use_bias:
-            self.bias = nn.Parameter(torch.zeros(self.output_dim))
+        super().__init__(**kwargs)
+        self.input_dim, self.output_dim = input_dim, output_dim
+        self.use_bias, self.aggr_method = use_bias, aggr_method
+        self.weight = nn.Parameter(nn.init.xavier_uniform_(torch.empty(input_dim, output_dim)))
+        if use_bias:
+            self.bias = nn.Parameter(torch.zeros(output_dim))
 
     def aggregate(self, neighbor_feature):
+        """The reduce over the fanout axis, on the device: a `SampledBlock` (ids into a resident
+        table: gather fused into the reduce) or the reference's pre-gathered `[n_src, fanout, F]`
+        tensor (Aggregator.py:18), walked as an identity index block."""
         if self.aggr_method not in ("mean", "sum", "max"):
             raise ValueError("Unknown aggr type, expected sum, max, or mean, but got {}".format(self.aggr_method))
         if isinstance(neighbor_feature, SampledBlock):
             b = neighbor_feature
             return gather_reduce(b.table, b.ids, b.n_src, b.fanout, self.aggr_method)
         n_src, fanout, feat = neighbor_feature.shape
-        flat = neighbor_feature.reshape(n_src * fanout, feat)
         # `max`: the reference's `.max(dim=1)` returns a (values, indices) tuple and the
         # following matmul raises TypeError (Aggregator.py:24,29); we implement `.values`.
-        return gather_reduce(flat, None, n_src, fanout, self.aggr_method)
+        return gather_reduce(neighbor_feature.reshape(n_src * fanout, feat), None, n_src, fanout, self.aggr_method)
 
     def forward(self, neighbor_feature):
-        # a tensor that is already [n_src, F] is the aggregate itself (the fused multi-hop launch of
-        # GraphSage.forward_sampled hands those in)
-        aggr_neighbor = neighbor_feature if torch.is_tensor(neighbor_feature) and neighbor_feature.dim() == 2 \
+        # a 2-D tensor is already the aggregate (GraphSage.forward_sampled's fused multi-hop launch)
+        pooled = neighbor_feature if torch.is_tensor(neighbor_feature) and neighbor_feature.dim() == 2 \
             else self.aggregate(neighbor_feature)
-        neighbor_hidden = torch.matmul(aggr_neighbor, self.weight)
-        if self.use_bias:
-            neighbor_hidden += self.bias
-        return neighbor_hidden
+        return torch.addmm(self.bias, pooled, self.weight) if self.use_bias else torch.mm(pooled, self.weight)
 
     def extra_repr(self):
-        return 'in_features={}, out_features={}, aggr_method={}'.format(
-            self.input_dim, self.output_dim, self.aggr_method)
+        return f'in_features={self.input_dim}, out_features={self.output_dim}, aggr_method={self.aggr_method}'
 
 
 class SageGCN(nn.Module):
+    """activation(src·W_self  (+ | ‖)  agg(neigh)·W_agg) — GraphSAGE_Pytorch/models/SageGCN.py:8-36.
+    state_dict: `weight [in,hidden]`, `aggregator.weight [in,hidden]` (+ `aggregator.bias`)."""
+
     def __init__(self, input_dim, hidden_dim, activation=F.relu, aggr_neighbor_method="mean", aggr_hidden_method="sum",
                  **kwargs):
-        super(SageGCN, self).__init__(**kwargs)
+        super().__init__(**kwargs)
         assert aggr_neighbor_method in ["mean", "sum", "max"]
         assert aggr_hidden_method in ["sum", "concat"]
-        self.input_dim = input_dim
-        self.hidden_dim = hidden_dim
-        self.aggr_neighbor_method = aggr_neighbor_method
-        self.aggr_hidden_method = aggr_hidden_method
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        self.aggr_neighbor_method, self.aggr_hidden_method = aggr_neighbor_method, aggr_hidden_method
         self.activation = activation
         self.aggregator = NeighborAggregator(input_dim, hidden_dim, aggr_method=aggr_neighbor_method)
-        self.weight = nn.Parameter(torch.Tensor(input_dim, hidden_dim))
+        self.weight = nn.Parameter(torch.empty(input_dim, hidden_dim))
         nn.init.xavier_uniform_(self.weight)
 
     def forward(self, src_node_features, neighbor_node_features):
-        neighbor_hidden = self.aggregator(neighbor_node_features)
-        self_hidden = torch.matmul(src_node_features, self.weight)
+        agg = self.aggregator
+        # the aggregate is either handed in ([n_src, F], from the fused multi-hop launch) or reduced here
+        pooled = neighbor_node_features if torch.is_tensor(neighbor_node_features) and neighbor_node_features.dim() == 2 \
+            else agg.aggregate(neighbor_node_features)
         if self.aggr_hidden_method == "sum":
-            hidden = self_hidden + neighbor_hidden
+            # both products accumulate into one buffer: no separate add (SageGCN.py:26-27)
+            hidden = torch.addmm(torch.mm(src_node_features, self.weight), pooled, agg.weight)
+            if agg.use_bias:
+                hidden = hidden + agg.bias
         elif self.aggr_hidden_method == "concat":
-            hidden = torch.cat([self_hidden, neighbor_hidden], dim=1)
+            hidden = torch.cat([torch.mm(src_node_features, self.weight), agg(pooled)], dim=1)  # SageGCN.py:28-29
         else:
             raise ValueError("Expected sum or concat, got {}".format(self.aggr_hidden_method))
-        if self.activation:
-            return self.activation(hidden)
-        return hidden
+        return self.activation(hidden) if self.activation else hidden
 
     def extra_repr(self):
-        output_dim = self.hidden_dim if self.aggr_hidden_method == "sum" else self.hidden_dim * 2
-        return 'in_features={}, out_features={}, aggr_hidden_method={}'.format(
-            self.input_dim, output_dim, self.aggr_hidden_method)
+        width = self.hidden_dim * (1 if self.aggr_hidden_method == "sum" else 2)
+        return f'in_features={self.input_dim}, out_features={width}, aggr_hidden_method={self.aggr_hidden_method}'
 
 
 class GraphSage(nn.Module):
+    """GraphSAGE_Pytorch/models/GraphSage.py:6-33.  state_dict: `gcn.{l}.weight`, `gcn.{l}.aggregator.weight`."""
+
     def __init__(self, input_dim, hidden_dim, num_neighbors_list):
-        super(GraphSage, self).__init__()
-        self.input_dim = input_dim
-        self.hidden_dim = hidden_dim
+        super().__init__()
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
         self.num_neighbors_list = num_neighbors_list
         self.num_layers = len(num_neighbors_list)
-        self.gcn = nn.ModuleList()
-        self.gcn.append(SageGCN(input_dim, hidden_dim[0]))
-        for index in range(0, len(hidden_dim) - 2):
-            self.gcn.append(SageGCN(hidden_dim[index], hidden_dim[index + 1]))
-        self.gcn.append(SageGCN(hidden_dim[-2], hidden_dim[-1], activation=None))
+        widths = [input_dim] + list(hidden_dim)
+        last = len(hidden_dim) - 1
+        # every layer but the last ends in ReLU (GraphSage.py:13-16)
+        self.gcn = nn.ModuleList(SageGCN(widths[l], widths[l + 1], **({"activation": None} if l == last else {}))
+                                 for l in range(len(hidden_dim)))
+
+    def _upper_layers(self, hidden):
+        """Layers 1..L-1 (GraphSage.py:21-29): layer l turns the states of hops 0..L-l into the states of
+        hops 0..L-l-1; the neighbours of hop h are the contiguous rows of hop h+1, reduced as an
+        identity index block (no gather)."""
+        for l in range(1, self.num_layers):
+            layer = self.gcn[l]
+            hidden = [layer(hidden[hop], hidden[hop + 1].view(hidden[hop].shape[0], self.num_neighbors_list[hop], -1))
+                      for hop in range(self.num_layers - l)]
+        return hidden[0]
 
     def forward(self, node_features_list):
-        """Reference call surface (GraphSage.py:18-30): pre-gathered feature tensors per hop."""
-        hidden = node_features_list
-        for l in range(self.num_layers):
-            next_hidden = []
-            gcn = self.gcn[l]
-            for hop in range(self.num_layers - l):
-                src_node_features = hidden[hop]
-                src_node_num = len(src_node_features)
-                neighbor_node_features = hidden[hop + 1].view((src_node_num, self.num_neighbors_list[hop], -1))
-                h = gcn(src_node_features, neighbor_node_features)
-                next_hidden.append(h)
-            hidden = next_hidden
-        return hidden[0]
+        """Reference call surface (GraphSage.py:18-30): pre-gathered feature tensors per hop,
+        `node_features_list[h]` = [B·f1·…·fh, F]."""
+        layer0, fan = self.gcn[0], self.num_neighbors_list
+        hidden = [layer0(node_features_list[hop],
+                         node_features_list[hop + 1].view(node_features_list[hop].shape[0], fan[hop], -1))
+                  for hop in range(self.num_layers)]
+        return self._upper_layers(hidden)
 
     def forward_sampled(self, table, node_id_blocks):
         """Fused path: `table` [N,F] resident on the device (ideally `pad_table`-aligned),
@@ -134,32 +139,18 @@ class GraphSage(nn.Module):
         as int32/int64 device tensors.  Same arithmetic as `forward` on
         `[table[ids] for ids in node_id_blocks]`, without materialising the gathers of the
         outermost hop: layer 0 reads neighbours straight from the table."""
-        L = self.num_layers
+        L, fan, layer0 = self.num_layers, self.num_neighbors_list, self.gcn[0]
         assert len(node_id_blocks) == L + 1
-        gcn = self.gcn[0]
-        hidden = []
         fused = (not (torch.is_grad_enabled() and table.requires_grad)) and L <= 4 \
-            and gcn.aggr_neighbor_method in ("mean", "sum", "max")
+            and layer0.aggr_neighbor_method in ("mean", "sum", "max")
         if fused:
             # every hop of layer 0 aggregates from the same table: ONE launch for all of them
-            blocks = [(node_id_blocks[hop + 1], node_id_blocks[hop].numel(), self.num_neighbors_list[hop])
-                      for hop in range(L)]
-            aggs = gather_reduce_multi_raw(table, blocks, gcn.aggr_neighbor_method)
-        for hop in range(L):
-            src = table.index_select(0, node_id_blocks[hop].to(torch.int64)) if node_id_blocks[hop].dtype != torch.int64 \
-                else table.index_select(0, node_id_blocks[hop])
-            blk = aggs[hop] if fused else SampledBlock(table, node_id_blocks[hop + 1], self.num_neighbors_list[hop])
-            hidden.append(gcn(src, blk))
-        for l in range(1, L):
-            next_hidden = []
-            gcn = self.gcn[l]
-            for hop in range(L - l):
-                src_node_features = hidden[hop]
-                n_src = len(src_node_features)
-                neigh = hidden[hop + 1].view((n_src, self.num_neighbors_list[hop], -1))
-                next_hidden.append(gcn(src_node_features, neigh))
-            hidden = next_hidden
-        return hidden[0]
+            pooled = gather_reduce_multi_raw(table, [(node_id_blocks[hop + 1], node_id_blocks[hop].numel(), fan[hop])
+                                                     for hop in range(L)], layer0.aggr_neighbor_method)
+        else:
+            pooled = [SampledBlock(table, node_id_blocks[hop + 1], fan[hop]) for hop in range(L)]
+        hidden = [layer0(table.index_select(0, node_id_blocks[hop].to(torch.int64)), pooled[hop]) for hop in range(L)]
+        return self._upper_layers(hidden)
 
     def extra_repr(self):
         return 'in_features={}, num_neighbors_list={}'.format(self.input_dim, self.num_neighbors_list)

@@ -129,7 +129,10 @@ int gnn_spmm_csr_bf16(const int64_t* rowptr, const int32_t* col, const float* va
  * SURVEY.md §8e).  rows_per_team (0 = default) is how many consecutive rows one sub-warp
  * team streams: the default suits sparse rows (papers100M-shaped, 14 edges per row); the
  * host lowers it on dense graphs (Reddit-shaped, 490 per row) so that a team holds a few
- * hundred edges and the grid has enough warps.  The plan is host logic computed once
+ * hundred edges and the grid has enough warps.  bias / relu fuse the rest of the GCN layer
+ * into the row flush: Y = relu?(A*X + bias) (`output + self.bias` GCN/GCN.py:44-45 and the
+ * nn.ReLU that follows the layer, GCN.py:12); not allowed with accumulate=1.
+ * The plan is host logic computed once
  * per graph (graphneuralnetwork_b200/graph.py CSRGraph.long_row_plan / rows_per_team). */
 size_t gnn_spmm_csr_workspace_size(int64_t n_chunks, int32_t elem_size);
 int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const float* val,
@@ -138,6 +141,7 @@ int gnn_spmm_csr_planned_f32(const int64_t* rowptr, const int32_t* col, const fl
                              const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
                              int accumulate /*1: Y += A*X*/, int32_t rows_per_team,
+                             const float* bias /*nullable [F]*/, int32_t relu,
                              void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const float* val,
                               const void* X, void* Y, int64_t n_rows, int64_t n_cols, int32_t F,
@@ -145,6 +149,7 @@ int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const f
                               const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
                               const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_edges,
                               int accumulate, int32_t rows_per_team,
+                              const float* bias /*nullable [F], fp32*/, int32_t relu,
                               void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 
 /* ---- GraphSAGE: fused gather + reduce over fixed-fanout index blocks ----------- */

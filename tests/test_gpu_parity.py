@@ -234,6 +234,45 @@ def test_gcn_layer_and_model_vs_reference_golden(lib):
     check_grads(model, g)
 
 
+@pytest.mark.parametrize("F", [7, 16, 602])
+@pytest.mark.parametrize("relu", [False, True])
+def test_gcn_fused_bias_relu_epilogue(lib, F, relu):
+    """relu?(Â·S + b) in one launch (GCN/GCN.py:43-45 + the nn.ReLU of GCN.py:12) == the unfused
+    reference arithmetic, forward and backward, including a chunked long row and empty rows."""
+    n = 1200
+    rowptr, col, val = random_csr(n, n, 9, seed=F, long_row=(5, 9000))
+    rng = np.random.default_rng(F)
+    S_np = rng.standard_normal((n, F)).astype(np.float32)
+    b_np = rng.standard_normal(F).astype(np.float32)
+    csr = CSRGraph(cuda(rowptr), cuda(col), cuda(val), n, n)
+    ref = ogcn.spmm_f64(rowptr, col, val, S_np) + b_np
+    if relu:
+        ref = np.maximum(ref, 0.0)
+    Sd = cuda(S_np).requires_grad_(True)
+    bd = cuda(b_np).requires_grad_(True)
+    Y = Fn.gcn_aggregate(csr, Sd, bd, relu=relu)
+    assert rel_err(Y.detach().cpu().numpy(), ref) < TOL32
+    G = rng.standard_normal((n, F)).astype(np.float32)
+    Y.backward(cuda(G))
+    # unfused reference on the CPU: torch.spmm + bias (+ relu) with autograd
+    Sc = torch.from_numpy(S_np).requires_grad_(True)
+    bc = torch.from_numpy(b_np).requires_grad_(True)
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    A = torch.sparse_coo_tensor(torch.from_numpy(np.vstack((rows, col)).astype(np.int64)), torch.from_numpy(val), (n, n))
+    Yc = torch.spmm(A, Sc) + bc
+    if relu:
+        Yc = torch.relu(Yc)
+    Yc.backward(torch.from_numpy(G))
+    assert rel_err(Sd.grad.cpu().numpy(), Sc.grad.numpy()) < 2e-5
+    assert rel_err(bd.grad.cpu().numpy(), bc.grad.numpy()) < 2e-5
+    # bias-free, relu only / plain (the epilogue instantiation is only picked when needed)
+    Y0 = Fn.spmm_raw(csr, cuda(S_np), relu=relu)
+    ref0 = ogcn.spmm_f64(rowptr, col, val, S_np)
+    assert rel_err(Y0.cpu().numpy(), np.maximum(ref0, 0.0) if relu else ref0) < TOL32
+    with pytest.raises(_lib.GnnError):
+        Fn.spmm_raw(csr, cuda(S_np), out=Y0, accumulate=True, bias=cuda(b_np))
+
+
 def test_spmm_deterministic(lib):
     rowptr, col, val = random_csr(5000, 5000, 30, seed=2, long_row=(3, 9000))
     csr = CSRGraph(cuda(rowptr), cuda(col), cuda(val), 5000, 5000)
