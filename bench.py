@@ -407,6 +407,23 @@ def run_other_configs_b200(dev, reps=20):
             torch.nn.functional.cross_entropy(o, labels if idx is None else labels[idx]).backward()
         return fn
 
+    def captured_epoch_ms(model, inputs, labels, idx=None):
+        """The same epoch + an Adam update replayed as ONE CUDA graph (runtime.CapturedTrainStep)."""
+        from graphneuralnetwork_b200.runtime import CapturedTrainStep
+        try:
+            opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=5e-4, capturable=True)
+
+            def closure():
+                o = model(*inputs)
+                return torch.nn.functional.cross_entropy(o if idx is None else o[idx],
+                                                         labels if idx is None else labels[idx])
+            step = CapturedTrainStep(model, closure, opt)
+            return {"epoch_ms_captured": cuda_time(step, reps),
+                    "captured": "forward + loss + backward + Adam update replayed as one CUDA graph",
+                    "our_launches_per_captured_epoch": int(step.kernel_launches_per_replay)}
+        except Exception as e:  # pragma: no cover
+            return {"epoch_ms_captured": None, "captured_error": repr(e)[:300]}
+
     # configs[0]: GCN 2-layer (16 hidden) on the Cora-shaped graph
     n, (row, col, val), X, labels = cora_inputs()
     adj = torch.sparse_coo_tensor(torch.from_numpy(np.vstack((row, col))), torch.from_numpy(val), (n, n)).to(dev)
@@ -422,6 +439,7 @@ def run_other_configs_b200(dev, reps=20):
                        "epoch_ms": ms, "spmm_per_epoch": 4, "edges_per_s": 4 * nnz / ms * 1e3,
                        "roofline": "n/a (L2-resident, launch-bound)",
                        "our_launches_per_epoch": (lib.gnn_launch_count() - l0) // (reps + 3)}
+    out["gcn_cora"].update(captured_epoch_ms(gcn, (Xd, adj), yd, idx))
     # configs[1]: GAT 8x8 + 1x7 on the same graph (dense normalised adjacency used as a mask)
     dense = np.zeros((n, n), np.float32)
     dense[row, col] = val
@@ -430,6 +448,8 @@ def run_other_configs_b200(dev, reps=20):
     gat = layers.GAT(S.CORA["feats"], 8, S.CORA["classes"], 0.6, 0.2, 8).to(dev).train()
     l0 = lib.gnn_launch_count()
     ms = cuda_time(epoch_fn(gat, (Xd, dense_d), yd, idx), reps)
+    gat_launches = (lib.gnn_launch_count() - l0) // (reps + 3)
+    cap = captured_epoch_ms(gat, (Xd, dense_d), yd, idx)
     gat.eval()
     with torch.no_grad():
         ms_eval = cuda_time(lambda: gat(Xd, dense_d), reps)
@@ -437,7 +457,8 @@ def run_other_configs_b200(dev, reps=20):
                                  "forward+backward epoch through layers.GAT",
                        "epoch_ms": ms, "eval_forward_ms": ms_eval, "edges_per_s": 2 * nnz / ms * 1e3,
                        "roofline": "n/a (L2-resident, launch-bound)",
-                       "our_launches_per_epoch": (lib.gnn_launch_count() - l0) // (2 * (reps + 3))}
+                       "our_launches_per_epoch": gat_launches}
+    out["gat_cora"].update(cap)
     del dense_d, gat, gcn
     # configs[3]: HAN, 3 metapaths, 8 heads x 8, ACM-shaped
     n, gs, X, labels = acm_inputs()
@@ -451,6 +472,7 @@ def run_other_configs_b200(dev, reps=20):
                                 "semantic attention, ACM-shaped, forward+backward epoch through layers.HANModel"
                                 % [int((g > 0).sum()) for g in gs],
                       "epoch_ms": ms, "edges_per_s": tot / ms * 1e3, "roofline": "n/a (Wh table L2-resident)"}
+    out["han_acm"].update(captured_epoch_ms(han, (gs_d, Xd), yd))
     del gs_d, han, Xd
     torch.cuda.empty_cache()
     # Reddit-shaped full-graph GCN aggregation at F=602 (north_star: >=70% of HBM roofline)
