@@ -34,8 +34,16 @@ struct PushArgs {
 // which cost 2.5x at 8 GPUs):
 //   SCHED 0  rotated: rank r walks its segments in the order r+1, r+2, ... (one receiver at a time)
 //   SCHED 1  interleaved: warp w serves peer first_peer + w % n_peers (all receivers at once)
-template <int VEC, int UNROLL, int SCHED>
-__global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a) {
+//
+// SM partition ("halo.dedicated_sms" = N > 0): instead of one small CTA on every SM — where the 8
+// push warps compete with 24 SpMM warps for the same load/store unit and the overlapped exchange
+// ran at ~420 GB/s instead of 610 — the push runs as N CTAs of 1024 threads that each claim
+// "halo.exclusion_smem_kb" of shared memory.  One such CTA fills an SM's shared memory, and the
+// concurrently launched local-column SpMM asks for a token amount of dynamic shared memory
+// ("spmm.exclusion_smem_kb") that no longer fits next to it: the block scheduler itself keeps the
+// two kernels on disjoint SMs (N for the NVLink stores, 148 - N for the HBM-bound SpMM).
+template <int VEC, int UNROLL, int SCHED, int THREADS>
+__global__ void __launch_bounds__(THREADS) halo_push_kernel(const PushArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -169,14 +177,26 @@ int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* sen
   const int unroll = tuning("halo.unroll", 4);
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = (unsigned)grid;
-  if (vec4) {
-    if (sched == 1 && unroll >= 8) halo_push_kernel<4, 8, 1><<<g, 256, 0, st>>>(a);
-    else if (sched == 1) halo_push_kernel<4, 4, 1><<<g, 256, 0, st>>>(a);
-    else if (unroll >= 8) halo_push_kernel<4, 8, 0><<<g, 256, 0, st>>>(a);
-    else halo_push_kernel<4, 4, 0><<<g, 256, 0, st>>>(a);
+  const int dedicated = tuning("halo.dedicated_sms", 0);
+  if (dedicated > 0 && vec4) {
+    const size_t smem = (size_t)tuning("halo.exclusion_smem_kb", 200) * 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+      GNN_CUDA(cudaFuncSetAttribute(halo_push_kernel<4, 4, 0, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GNN_CUDA(cudaFuncSetAttribute(halo_push_kernel<4, 8, 0, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    const unsigned gd = (unsigned)(dedicated < num_sms() ? dedicated : num_sms());
+    if (unroll >= 8) halo_push_kernel<4, 8, 0, 1024><<<gd, 1024, smem, st>>>(a);
+    else halo_push_kernel<4, 4, 0, 1024><<<gd, 1024, smem, st>>>(a);
+  } else if (vec4) {
+    if (sched == 1 && unroll >= 8) halo_push_kernel<4, 8, 1, 256><<<g, 256, 0, st>>>(a);
+    else if (sched == 1) halo_push_kernel<4, 4, 1, 256><<<g, 256, 0, st>>>(a);
+    else if (unroll >= 8) halo_push_kernel<4, 8, 0, 256><<<g, 256, 0, st>>>(a);
+    else halo_push_kernel<4, 4, 0, 256><<<g, 256, 0, st>>>(a);
   } else {
-    if (sched == 1) halo_push_kernel<1, 4, 1><<<g, 256, 0, st>>>(a);
-    else halo_push_kernel<1, 4, 0><<<g, 256, 0, st>>>(a);
+    if (sched == 1) halo_push_kernel<1, 4, 1, 256><<<g, 256, 0, st>>>(a);
+    else halo_push_kernel<1, 4, 0, 256><<<g, 256, 0, st>>>(a);
   }
   GNN_LAUNCH_CHECK();
   return GNN_OK;

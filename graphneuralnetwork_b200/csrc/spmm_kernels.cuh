@@ -349,8 +349,11 @@ inline void spmm_rbs_launch(const SpmmArgs<T>& a, cudaStream_t st) {
   const int64_t teams = (a.n_rows + rpt - 1) / rpt;
   const int64_t grid = (teams * GROUP + kSpmmThreads - 1) / kSpmmThreads;
   // the bias/ReLU epilogue is a separate instantiation: the plain one keeps its register budget
-  if (a.bias || a.relu) spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, true><<<(unsigned)grid, kSpmmThreads, 0, st>>>(a);
-  else spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false><<<(unsigned)grid, kSpmmThreads, 0, st>>>(a);
+  // token dynamic shared memory (<= 48 KB, unused by the kernel) keeps these CTAs off the SMs a
+  // dedicated halo push has claimed (peer.cu); 0 outside the partitioned SpMM's local pass
+  const size_t sm = (size_t)tuning("spmm.exclusion_smem_kb", 0) * 1024;
+  if (a.bias || a.relu) spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, true><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
+  else spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
 }
 
 template <typename T, int VEC>

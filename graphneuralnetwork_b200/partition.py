@@ -134,10 +134,16 @@ class _RawCudaBuffer:
 class PartitionedSpmm:
     """Executes Y_local = (Â·X)[own rows] for one rank.  fp32."""
 
-    def __init__(self, plan: HaloPlan, F: int, device, group=None, transport: str = "p2p"):
+    def __init__(self, plan: HaloPlan, F: int, device, group=None, transport: str = "p2p",
+                 dedicated_sms: Optional[int] = None):
+        """dedicated_sms: SMs the fused NVLink push gets to itself while the local-column pass runs on
+        the rest (peer.cu).  None = measured default: 48 at 8 GPUs, where the exchange is the critical
+        path (r01, papers100M-shaped: 34.9 ms shared SMs -> 33.5 / 32.8 ms with 32 / 48 dedicated; 16
+        SMs cannot feed NVLink: 53 ms); 0 (one small push CTA on every SM) below that."""
         from .graph import CSRGraph
         self.plan, self.F, self.dev, self.group = plan, int(F), torch.device(device), group
         self.transport = transport if plan.world > 1 else "none"
+        self.dedicated = (48 if plan.world >= 8 else 0) if dedicated_sms is None else int(dedicated_sms)
         n_loc, n_halo = plan.n_local, max(plan.n_halo, 1)
         self.A_loc = CSRGraph(plan.rowptr_loc, plan.col_loc, plan.val_loc, n_loc, n_loc)
         self.A_rem = CSRGraph(plan.rowptr_rem, plan.col_rem, plan.val_rem, n_loc, n_halo)
@@ -192,6 +198,7 @@ class PartitionedSpmm:
         if self.transport == "p2p":
             b = self._step & 1
             ptrs = (C.c_void_p * plan.world)(*self._peer_ptrs[b])
+            _lib.set_tuning("halo.dedicated_sms", self.dedicated)
             _lib.check(lib.gnn_halo_push_f32(X.data_ptr(), X.stride(0), self.F, plan.send_rows.data_ptr(), self._send_off,
                                              ptrs, self._dst_off, self.ld, plan.world, (plan.rank + 1) % plan.world,
                                              torch.cuda.current_stream().cuda_stream), "gnn_halo_push_f32")
@@ -221,7 +228,16 @@ class PartitionedSpmm:
                 self.comm.wait_event(self._ev_x)          # X is ready (and the previous remote pass is done)
                 halo = self._exchange(X)
                 self._ev_halo.record(self.comm)
-            spmm_raw(self.A_loc, X, out=out)              # local columns while the halo is in flight
+            # local columns while the halo is in flight; with a dedicated push (halo.dedicated_sms) this
+            # pass asks for token shared memory so the scheduler keeps it off the push's SMs
+            excl = 28 if (self.transport == "p2p" and self.dedicated > 0) else 0
+            if excl:
+                _lib.set_tuning("spmm.exclusion_smem_kb", excl)
+            try:
+                spmm_raw(self.A_loc, X, out=out)
+            finally:
+                if excl:
+                    _lib.set_tuning("spmm.exclusion_smem_kb", 0)
             main.wait_event(self._ev_halo)
         else:
             halo = self._exchange(X)

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--halo-sched", type=int, default=0)
     ap.add_argument("--halo-unroll", type=int, default=8)
     ap.add_argument("--overlap-only", action="store_true")
+    ap.add_argument("--dedicated", type=int, nargs="+", default=[0], help="PartitionedSpmm.dedicated values to sweep")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
@@ -78,7 +79,9 @@ def main():
     for transport in (a.transports if world > 1 else ["none"]):
         op = PartitionedSpmm(plan, a.F, dev, transport=transport)
         Y = torch.empty(n_loc, a.F, device=dev)
-        for overlap in ([True] if (a.overlap_only or world == 1) else [True, False]):
+        for overlap, dedicated in [(o, d) for d in (a.dedicated if transport == "p2p" else [0])
+                                   for o in ([True] if (a.overlap_only or world == 1) else [True, False])]:
+            op.dedicated = dedicated
             for _ in range(a.warmup):
                 op.forward(X, out=Y, overlap=overlap)
             torch.cuda.synchronize()
@@ -96,7 +99,7 @@ def main():
             if rank == 0:
                 hal = [int(s[0]) for s in allstats]
                 print(json.dumps({"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F,
-                                  "transport": transport, "overlap": overlap, "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": a.halo_unroll, "ms": ms.item(),
+                                  "transport": transport, "overlap": overlap, "dedicated_sms": dedicated, "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": a.halo_unroll, "ms": ms.item(),
                                   "edges_per_s": nnz_total / ms.item() * 1e3, "p_local": a.p_local, "window": a.window, "scatter": a.scatter, "skew": a.skew,
                                   "halo_rows_max": max(hal), "halo_rows_mean": sum(hal) / world,
                                   "halo_gb_recv_max": max(hal) * a.F * 4 / 1e9,
