@@ -23,6 +23,8 @@ struct RowArgs {
   const int64_t* col64;  // int64 index block; both null => identity (source row = slot)
   const float* val;      // nullptr => 1
   int32_t src_div;       // >0: source row = col / src_div (gather backward: flat position -> source)
+  int32_t src_mul;       // >0: typed table [N, src_mul, F]: source row = col * src_mul + (row % src_mul)
+                         //     (GATNE's edge-type axis: output row b*T+t reads type-t embeddings)
   float scale;           // result multiplier (1/fanout for mean)
   const T* X;
   int64_t ldx;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kRowReduceThreads) row_reduce_kernel(const Row
       else if (a.col64) c = (int32_t)__ldg(a.col64 + k);
       else c = (int32_t)k;
       if (a.src_div > 0 && c >= 0) c /= a.src_div;
+      if (a.src_mul > 0 && c >= 0) c = c * a.src_mul + (int32_t)(row % a.src_mul);
       v = a.val ? __ldg(a.val + k) : 1.f;
     }
     const int cnt = (int)((e - base) < (int64_t)GROUP ? (e - base) : (int64_t)GROUP);

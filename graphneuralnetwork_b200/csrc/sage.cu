@@ -511,6 +511,38 @@ int gnn_gather_reduce_multi_bf16(const void* table, int64_t ld_table, int64_t n_
                                             (cudaStream_t)stream);
 }
 
+int gnn_gather_reduce_typed_f32(const float* table, int64_t ld_row, int64_t n_nodes, int32_t n_types, const void* idx,
+                                int idx_bits, int64_t n_src, int32_t fanout, int32_t F, int reduce, float* out,
+                                int64_t ld_out, gnn_stream_t stream) {
+  GNN_REQUIRE(n_src >= 0 && n_nodes >= 0 && F >= 0, GNN_ERR_BAD_ARG, "negative size");
+  GNN_REQUIRE(n_types > 0 && fanout > 0, GNN_ERR_BAD_ARG, "n_types and fanout must be positive");
+  GNN_REQUIRE(reduce == GNN_REDUCE_MEAN || reduce == GNN_REDUCE_SUM, GNN_ERR_BAD_ARG,
+              "typed gather supports sum and mean (GATNE_Pytorch/models/GATNE.py:72-77 raises otherwise)");
+  if (n_src == 0 || F == 0) return GNN_OK;
+  GNN_REQUIRE(table && idx && out, GNN_ERR_BAD_ARG, "null pointer");
+  GNN_REQUIRE(idx_bits == 32 || idx_bits == 64, GNN_ERR_BAD_ARG, "idx_bits must be 32 or 64");
+  GNN_REQUIRE(ld_row >= F && ld_out >= F, GNN_ERR_BAD_ARG, "leading dimension smaller than F");
+  GNN_REQUIRE(n_nodes * (int64_t)n_types < 0x7fffffffLL, GNN_ERR_UNSUPPORTED, "n_nodes * n_types does not fit int32");
+  RowArgs<float> r{};
+  r.rowptr = nullptr;
+  r.fanout = fanout;
+  r.col32 = idx_bits == 32 ? (const int32_t*)idx : nullptr;
+  r.col64 = idx_bits == 64 ? (const int64_t*)idx : nullptr;
+  r.val = nullptr;
+  r.src_div = 0;
+  r.src_mul = n_types;
+  r.scale = (reduce == GNN_REDUCE_MEAN) ? 1.0f / (float)fanout : 1.0f;
+  r.X = table;
+  r.ldx = ld_row;
+  r.Y = out;
+  r.ldy = ld_out;
+  r.n_rows = n_src * (int64_t)n_types;
+  r.F = F;
+  r.skip_deg_gt = 0;
+  r.argmax = nullptr;
+  return launch_row_reduce<float, 0>(r, (cudaStream_t)stream);
+}
+
 int gnn_gather_reduce_bwd_f32(const int64_t* rowptr_t, const int32_t* pos_t, int64_t n_table_rows, int32_t fanout,
                               float scale, const float* d_out, int64_t ld_dout, float* d_table, int64_t ld_dtable,
                               int32_t F, gnn_stream_t stream) {

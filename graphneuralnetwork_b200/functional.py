@@ -285,6 +285,57 @@ def gather_reduce(table: torch.Tensor, idx: Optional[torch.Tensor], n_src: int, 
     return _GatherReduceFn.apply(table, idx, n_src, fanout, reduce)
 
 
+class _TypedGatherFn(torch.autograd.Function):
+    """out[b,t,:] = reduce_k table[idx[b,t,k], t, :] (gnn_gather_reduce_typed_f32).  Backward into the
+    table walks the transposed index block of the flat (node*T + t) ids: ordered, no atomics."""
+
+    @staticmethod
+    def forward(ctx, table, idx, reduce):
+        N, T, U = table.shape
+        B, T2, K = idx.shape
+        out = torch.empty((B, T, U), dtype=torch.float32, device=table.device)
+        lib = _lib.load()
+        _lib.check(lib.gnn_gather_reduce_typed_f32(_p(table), table.stride(1), N, T, _p(idx),
+                                                   32 if idx.dtype == torch.int32 else 64, B, K, U,
+                                                   _lib.REDUCE[reduce], _p(out), U, _stream_ptr()),
+                   "gnn_gather_reduce_typed_f32")
+        ctx.save_for_backward(idx)
+        ctx.meta = (N, T, U, K, reduce)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (idx,) = ctx.saved_tensors
+        N, T, U, K, reduce = ctx.meta
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        lib = _lib.load()
+        flat = (idx.to(torch.int64) * T + torch.arange(T, device=idx.device).view(1, T, 1)).reshape(-1)
+        rowptr_t, pos_t = index_block_transpose(flat, N * T)
+        d_out = d_out.contiguous().view(-1, U)
+        d_table = torch.empty((N, T, U), dtype=torch.float32, device=d_out.device)
+        _lib.check(lib.gnn_gather_reduce_bwd_f32(_p(rowptr_t), _p(pos_t), N * T, K, 1.0 / K if reduce == "mean" else 1.0,
+                                                 _p(d_out), U, _p(d_table), U, U, _stream_ptr()),
+                   "gnn_gather_reduce_bwd_f32")
+        return d_table, None, None
+
+
+def typed_gather_reduce(table: torch.Tensor, idx: torch.Tensor, reduce: str = "sum") -> torch.Tensor:
+    """GATNE's per-edge-type neighbour aggregation: `table` [N, T, U] fp32 (node_type_embeddings),
+    `idx` [B, T, K] int32/int64 neighbour ids per edge type -> [B, T, U]; reduce 'sum' | 'mean'
+    (GATNE_Pytorch/models/GATNE.py:57-77, GATNE/models/GATNE.py:50-58)."""
+    if reduce not in ("sum", "mean"):
+        raise ValueError("please choice else aggregator!")  # the reference's message (GATNE.py:77)
+    _require_cuda(table, idx)
+    if table.dim() != 3 or idx.dim() != 3 or idx.shape[1] != table.shape[1]:
+        raise _lib.GnnError(f"typed_gather_reduce: table {tuple(table.shape)} / idx {tuple(idx.shape)} do not agree")
+    if table.dtype != torch.float32:
+        raise _lib.GnnError("typed_gather_reduce: fp32 table only")
+    if idx.dtype not in (torch.int32, torch.int64):
+        idx = idx.to(torch.int64)
+    return _TypedGatherFn.apply(table.contiguous(), idx.contiguous(), reduce)
+
+
 # --------------------------------------------------------------------------------------
 # GAT / HAN: fused multi-head attention aggregation
 # --------------------------------------------------------------------------------------

@@ -5,9 +5,10 @@ from .sage import (Aggregator, CapturedGraphSage, GraphSage, NeighborAggregator,
                    gather_mean)
 
 from .sage_v2 import GraphSAGE, SageLayer
+from .gatne import GATNEModel, GATNEModelV1, GraphDecoder, GraphEncoder
 
 __all__ = [
-    "GraphSAGE", "SageLayer",
+    "GraphSAGE", "SageLayer", "GATNEModel", "GATNEModelV1", "GraphDecoder", "GraphEncoder",
     "GCN_Model", "Graph_conv_layer", "GAT", "GATBase", "GraphAttentionLayer", "SpGAT", "SpGraphAttentionLayer",
     "GATConv", "HANLayer", "HANModel", "SemanticAttention", "Aggregator", "GraphSage", "NeighborAggregator",
     "SageGCN", "SampledBlock", "gather_mean", "CapturedGraphSage",

@@ -180,6 +180,15 @@ int gnn_gather_reduce_multi_bf16(const void* table, int64_t ld_table, int64_t n_
                                  int32_t n_blocks, const void* const* idx_host, int idx_bits,
                                  const int64_t* n_src_host, const int32_t* fanout_host,
                                  void* const* out_host, const int64_t* ld_out_host, gnn_stream_t stream);
+/* Edge-type axis (GATNE): table [n_nodes, n_types, F] (ld_row = stride between (node,type)
+ * rows), idx [n_src, n_types, fanout]; out[(b*n_types+t), :] = reduce_k table[idx[b,t,k], t, :]
+ * — the per-type neighbour aggregation of GATNE_Pytorch/models/GATNE.py:57-77 (`torch.cat` of T
+ * per-type gathers, then sum/mean over dim 2) and GATNE/models/GATNE.py:50-58 (gather of all T
+ * embeddings of every neighbour + `torch.diagonal` + sum), without the [B,T,K,(T,)U]
+ * intermediates.  reduce: sum or mean. */
+int gnn_gather_reduce_typed_f32(const float* table, int64_t ld_row, int64_t n_nodes, int32_t n_types,
+                                const void* idx, int idx_bits, int64_t n_src, int32_t fanout, int32_t F,
+                                int reduce, float* out, int64_t ld_out, gnn_stream_t stream);
 /* Backward of mean/sum into the table: dTable[r,:] = scale * sum_{p: idx[p]==r} dOut[p/fanout,:]
  * walking the gnn_index_block_transpose structure (ordered, no atomics). */
 int gnn_gather_reduce_bwd_f32(const int64_t* rowptr_t, const int32_t* pos_t, int64_t n_table_rows,

@@ -99,3 +99,8 @@ def han():
         sa = importlib.import_module("models.SemanticAttention")
         hm = importlib.import_module("models.HAN")
         return {"NodeAttention": na, "SemanticAttention": sa, "HAN": hm}
+
+
+def gatne():
+    """(GATNE_Pytorch/models/GATNE.py, GATNE/models/GATNE.py) — both files import torch only."""
+    return load_file("GATNE_Pytorch/models/GATNE.py", "ref_gatne_pytorch"), load_file("GATNE/models/GATNE.py", "ref_gatne_v1")

@@ -185,6 +185,36 @@ def make_han():
          out=out.detach().numpy(), loss=np.float64(loss.item()), **params_np(model), **grads_np(model))
 
 
+def make_gatne():
+    """GATNE per-edge-type neighbour aggregation: both reference variants, with
+    learned embeddings (GATNE-T) and with node features (GATNE-I), forward + gradients."""
+    ref_pt, ref_v1 = R.gatne()
+    N, T, K, B, E, U, A, Fd = 300, 3, 10, 64, 32, 10, 20, 24
+    rng = np.random.default_rng(21)
+    inputs = torch.from_numpy(rng.integers(0, N, B))
+    types = torch.from_numpy(rng.integers(0, T, B))
+    neigh = torch.from_numpy(rng.integers(0, N, (B, T, K)))
+    feats = torch.from_numpy(rng.standard_normal((N, Fd)).astype(np.float32))
+    target = torch.from_numpy(rng.standard_normal((B, E)).astype(np.float32))
+    out = {"inputs": inputs.numpy(), "types": types.numpy(), "neigh": neigh.numpy(), "features": feats.numpy(),
+           "target": target.numpy()}
+    for tag, ctor in (("pt_t_sum", lambda: ref_pt.GraphEncoder(N, E, U, T, A, None, agg_func="SUM")),
+                      ("pt_t_mean", lambda: ref_pt.GraphEncoder(N, E, U, T, A, None, agg_func="MEAN")),
+                      ("pt_i_sum", lambda: ref_pt.GraphEncoder(N, E, U, T, A, feats, agg_func="SUM")),
+                      ("v1_t", lambda: ref_v1.GATNEModel(N, E, U, T, A, None)),
+                      ("v1_i", lambda: ref_v1.GATNEModel(N, E, U, T, A, feats))):
+        torch.manual_seed(7)
+        model = ctor()
+        emb = model(inputs, types, neigh)
+        loss = ((emb - target) ** 2).sum()
+        loss.backward()
+        out[f"{tag}.out"] = emb.detach().numpy()
+        out[f"{tag}.loss"] = np.float64(loss.item())
+        out.update({f"{tag}.{k}": v for k, v in params_np(model).items()})
+        out.update({f"{tag}.{k}": v for k, v in grads_np(model).items()})
+    save("gatne_small.npz", **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "reference not found"
     torch.set_num_threads(8)
@@ -194,3 +224,4 @@ if __name__ == "__main__":
     make_sage()
     make_sage_v2()
     make_han()
+    make_gatne()

@@ -743,6 +743,47 @@ def test_spmm_powerlaw_properties(lib):
     assert Yt.shape == (200_000, 128)
 
 
+# ---------------------------------------------------------------- GATNE
+def test_typed_gather_reduce_vs_oracle(lib):
+    from oracle import gatne as ogatne
+    rng = np.random.default_rng(4)
+    N, T, U, B, K = 500, 3, 10, 77, 7
+    table = rng.standard_normal((N, T, U)).astype(np.float32)
+    idx = rng.integers(0, N, (B, T, K))
+    for reduce, agg in (("sum", "SUM"), ("mean", "MEAN")):
+        ref = ogatne.neighbour_aggregate(torch.from_numpy(table), torch.from_numpy(idx), agg).numpy()
+        for dt in (torch.int64, torch.int32):
+            out = Fn.typed_gather_reduce(cuda(table), cuda(idx).to(dt), reduce)
+            assert rel_err(out.cpu().numpy(), ref) < TOL32
+    # backward into the [N,T,U] table == autograd of the reference formulation
+    td = cuda(table).requires_grad_(True)
+    G = rng.standard_normal((B, T, U)).astype(np.float32)
+    Fn.typed_gather_reduce(td, cuda(idx), "mean").backward(cuda(G))
+    tc = torch.from_numpy(table).requires_grad_(True)
+    ogatne.neighbour_aggregate(tc, torch.from_numpy(idx), "MEAN").backward(torch.from_numpy(G))
+    assert rel_err(td.grad.cpu().numpy(), tc.grad.numpy()) < TOL32
+    with pytest.raises(ValueError):
+        Fn.typed_gather_reduce(cuda(table), cuda(idx), "max")
+
+
+@pytest.mark.parametrize("tag", ["pt_t_sum", "pt_t_mean", "pt_i_sum", "v1_t", "v1_i"])
+def test_gatne_encoders_vs_reference_golden(lib, tag):
+    g = load_golden("gatne_small.npz")
+    N, T, K, B, E, U, A = 300, 3, 10, 64, 32, 10, 20
+    feats = cuda(g["features"]) if "_i" in tag else None
+    if tag.startswith("pt"):
+        model = layers.GraphEncoder(N, E, U, T, A, feats, agg_func="MEAN" if tag.endswith("mean") else "SUM")
+    else:
+        model = layers.GATNEModelV1(N, E, U, T, A, feats)
+    model = load_params(model, g, prefix=tag + ".")
+    emb = model(cuda(g["inputs"]), cuda(g["types"]), cuda(g["neigh"]))
+    assert rel_err(emb.detach().cpu().numpy(), g[f"{tag}.out"]) < TOL32
+    loss = ((emb - cuda(g["target"])) ** 2).sum()
+    assert abs(loss.item() - float(g[f"{tag}.loss"])) < 1e-4 * max(1.0, float(g[f"{tag}.loss"]))
+    loss.backward()
+    check_grads(model, g, prefix=tag + ".", tol=2e-5)
+
+
 @pytest.mark.parametrize("which", ["gcn", "gat", "han"])
 def test_captured_train_step_matches_eager(lib, which):
     """runtime.CapturedTrainStep: a whole epoch (forward, loss, backward, Adam update) replayed as one

@@ -122,3 +122,16 @@ def test_edge_attention_f64_matches_dense_oracle():
     t = np.stack([(X @ W @ a[8:]).numpy()[:, 0] for W, a in zip(Ws, As)], 1)
     out = ogat.edge_attention_f64(rowptr, col, Wh, s, t, 0.2).reshape(300, 64)
     assert rel_err(out, dense) < TOL
+
+
+def test_gatne_encoders():
+    """oracle/gatne.py vs the unmodified GATNE_Pytorch GraphEncoder and GATNE GATNEModel."""
+    from oracle import gatne as ogatne
+    g = load_golden("gatne_small.npz")
+    inputs, types, neigh = (torch.from_numpy(g[k]) for k in ("inputs", "types", "neigh"))
+    feats = torch.from_numpy(g["features"])
+    for tag, use_feats, agg in (("pt_t_sum", False, "SUM"), ("pt_t_mean", False, "MEAN"), ("pt_i_sum", True, "SUM"),
+                                ("v1_t", False, "SUM"), ("v1_i", True, "SUM")):
+        params = _params(g, tag + ".")
+        out = ogatne.encoder_forward(params, inputs, types, neigh, feats if use_feats else None, agg)
+        assert rel_err(out.numpy(), g[f"{tag}.out"]) < TOL, tag
