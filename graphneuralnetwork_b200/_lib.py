@@ -40,6 +40,7 @@ SIGNATURES = {
                                         cint, i32, ptr, i32, ptr, size_t, ptr]),
     "gnn_spmm_csr_planned_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr, i64, i64, ptr, i64, i32,
                                          cint, i32, ptr, i32, ptr, size_t, ptr]),
+    "gnn_sddmm_coo_f32": (cint, [ptr, ptr, cint, i64, ptr, i64, ptr, i64, i32, ptr, ptr]),
     "gnn_gather_reduce_f32": (cint, [ptr, i64, i64, ptr, cint, i64, i32, i32, cint, ptr, i64, ptr, ptr]),
     "gnn_gather_reduce_bf16": (cint, [ptr, i64, i64, ptr, cint, i64, i32, i32, cint, ptr, i64, ptr, ptr]),
     "gnn_gather_reduce_multi_f32": (cint, [ptr, i64, i64, i32, cint, i32, ptr, cint, ptr, ptr, ptr, ptr, ptr]),

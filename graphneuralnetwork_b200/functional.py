@@ -94,6 +94,58 @@ def spmm(g: CSRGraph, X: torch.Tensor) -> torch.Tensor:
     return _SpmmFn.apply(X, g)
 
 
+def sddmm(rows: torch.Tensor, cols: torch.Tensor, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """out[e] = <A[rows[e]], B[cols[e]]> (gnn_sddmm_coo_f32): the edge-gradient contraction, nnz dot
+    products instead of the dense `A @ B.T` of GAT/models/layers.py:59-61.  No autograd."""
+    _require_cuda(rows, cols, A, B)
+    lib = _lib.load()
+    A, B = _rowmajor(A), _rowmajor(B)
+    if A.dtype != torch.float32 or B.dtype != torch.float32 or A.shape[1] != B.shape[1]:
+        raise _lib.GnnError(f"sddmm: fp32 operands with equal widths expected, got {tuple(A.shape)} {tuple(B.shape)}")
+    if rows.dtype != cols.dtype or rows.dtype not in (torch.int32, torch.int64) or rows.numel() != cols.numel():
+        raise _lib.GnnError("sddmm: rows / cols must be int32 or int64 arrays of equal length")
+    rows, cols = rows.contiguous(), cols.contiguous()
+    out = torch.empty(rows.numel(), dtype=torch.float32, device=A.device)
+    _lib.check(lib.gnn_sddmm_coo_f32(_p(rows), _p(cols), 32 if rows.dtype == torch.int32 else 64, rows.numel(), _p(A),
+                                     _ld(A), _p(B), _ld(B), A.shape[1], _p(out), _stream_ptr()), "gnn_sddmm_coo_f32")
+    return out
+
+
+class _SpmmValuesFn(torch.autograd.Function):
+    """Y = S·X where the VALUES of S are an autograd input (pattern fixed, CSR order).
+    Backward: dX = Sᵀ·dY (transpose SpMM on the cached transposed pattern),
+              dval[e] = <dY[row(e)], X[col(e)]> (edge-gradient SDDMM)."""
+
+    @staticmethod
+    def forward(ctx, val, X, pattern: CSRGraph):
+        ctx.pattern = pattern
+        ctx.save_for_backward(val, X)
+        return spmm_raw(pattern.with_values(val), X)
+
+    @staticmethod
+    def backward(ctx, dY):
+        val, X = ctx.saved_tensors
+        g = ctx.pattern
+        dY = dY.contiguous()
+        dval = dX = None
+        if ctx.needs_input_grad[0]:
+            dval = sddmm(g.edge_rows(), g.col, dY, X)
+        if ctx.needs_input_grad[1]:
+            gt = g.transpose()  # pattern transpose + permutation, cached on the pattern graph
+            dX = spmm_raw(gt.with_values(val.detach()[g.perm_t]), dY)
+        return dval, dX, None
+
+
+def spmm_values(pattern: CSRGraph, val: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """Y = S·X with autograd into BOTH the edge values `val` (CSR order of `pattern`) and X:
+    the sparse product of GAT/models/layers.py:43-64 (SpecialSpmmFunction) and of a GCN over a
+    learned adjacency (GTN/models/GTN.py:49-52)."""
+    _require_cuda(val, X)
+    if val.dtype != torch.float32 or val.numel() != pattern.nnz:
+        raise _lib.GnnError(f"spmm_values: {pattern.nnz} fp32 edge values expected")
+    return _SpmmValuesFn.apply(val, X, pattern)
+
+
 class _GcnAggregateFn(torch.autograd.Function):
     """Y = relu?(Â·S + b) in ONE launch: the aggregation (GCN/GCN.py:43), the bias add
     (GCN.py:44-45) and the ReLU that follows every hidden layer (GCN.py:12,19) fused into the

@@ -53,6 +53,25 @@ class CSRGraph:
     def device(self):
         return self.rowptr.device
 
+    def with_values(self, val: Optional[torch.Tensor]) -> "CSRGraph":
+        """Same pattern, other edge values (learned / per-step weights): shares rowptr, col and every
+        host-side plan that depends on the pattern only, so nothing is re-planned or re-synchronised."""
+        self.long_row_plan()  # plans are cached on the pattern owner before the copy shares them
+        self.rows_per_team()
+        g = CSRGraph.__new__(CSRGraph)
+        g.__dict__.update(self.__dict__)
+        g.val = None if val is None else val.contiguous()
+        g._t = None  # the transpose carries values: rebuilt (from the cached permutation) on demand
+        return g
+
+    def edge_rows(self) -> torch.Tensor:
+        """int32 row id of every CSR slot (rowptr expanded once; cached with the pattern)."""
+        if getattr(self, "_edge_rows", None) is None:
+            counts = self.rowptr[1:] - self.rowptr[:-1]
+            self._edge_rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device, dtype=torch.int32),
+                                                      counts, output_size=self.nnz)
+        return self._edge_rows
+
     # -- plans ---------------------------------------------------------------------
     def transpose(self) -> "CSRGraph":
         """CSR of the transpose, stable in source order (gnn_csr_transpose); cached."""
@@ -139,8 +158,10 @@ class CSRGraph:
 
     # -- builders --------------------------------------------------------------------
     @staticmethod
-    def from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int) -> "CSRGraph":
-        """COO -> CSR, stable in row (gnn_build_csr_from_coo)."""
+    def from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int,
+                 return_perm: bool = False):
+        """COO -> CSR, stable in row (gnn_build_csr_from_coo).  return_perm: also return the int64
+        input position of every CSR slot (values given in COO order are `val[perm]` in CSR order)."""
         _require_cuda(row, col, val)
         lib = _lib.load()
         dev = row.device
@@ -154,10 +175,12 @@ class CSRGraph:
         val32 = None if val is None else torch.empty(nnz, dtype=torch.float32, device=dev)
         ws_bytes = lib.gnn_build_csr_from_coo_workspace_size(nnz, n_rows)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        perm = torch.empty(nnz, dtype=torch.int64, device=dev) if return_perm else None
         _lib.check(lib.gnn_build_csr_from_coo(_p(row), _p(col), _p(val), nnz, n_rows, n_cols, _p(rowptr), _p(col32),
-                                              _p(val32), None, _p(ws), ws_bytes, _stream_ptr()),
+                                              _p(val32), _p(perm), _p(ws), ws_bytes, _stream_ptr()),
                    "gnn_build_csr_from_coo")
-        return CSRGraph(rowptr, col32, val32, n_rows, n_cols)
+        g = CSRGraph(rowptr, col32, val32, n_rows, n_cols)
+        return (g, perm) if return_perm else g
 
     @staticmethod
     def from_torch_sparse(adj: torch.Tensor) -> "CSRGraph":

@@ -1,5 +1,6 @@
 from .gcn import GCN_Model, Graph_conv_layer
-from .gat import GAT, GATBase, GraphAttentionLayer, SpGAT, SpGraphAttentionLayer
+from .gat import (GAT, GATBase, GraphAttentionLayer, SpecialSpmm, SpecialSpmmFunction, SpGAT,
+                  SpGraphAttentionLayer)
 from .han import GATConv, HANLayer, HANModel, SemanticAttention
 from .sage import (Aggregator, CapturedGraphSage, GraphSage, NeighborAggregator, SageGCN, SampledBlock,
                    gather_mean)
@@ -9,7 +10,7 @@ from .gatne import GATNEModel, GATNEModelV1, GraphDecoder, GraphEncoder
 
 __all__ = [
     "GraphSAGE", "SageLayer", "GATNEModel", "GATNEModelV1", "GraphDecoder", "GraphEncoder",
-    "GCN_Model", "Graph_conv_layer", "GAT", "GATBase", "GraphAttentionLayer", "SpGAT", "SpGraphAttentionLayer",
+    "GCN_Model", "Graph_conv_layer", "SpecialSpmm", "SpecialSpmmFunction", "GAT", "GATBase", "GraphAttentionLayer", "SpGAT", "SpGraphAttentionLayer",
     "GATConv", "HANLayer", "HANModel", "SemanticAttention", "Aggregator", "GraphSage", "NeighborAggregator",
     "SageGCN", "SampledBlock", "gather_mean", "CapturedGraphSage",
 ]

@@ -13,8 +13,40 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from ..functional import attention_keep_mask, gat_aggregate
-from ..graph import adj_cache
+from ..functional import attention_keep_mask, gat_aggregate, spmm_values
+from ..graph import CSRGraph, adj_cache
+
+_pattern_cache = {}
+
+
+def _coo_pattern(indices, shape):
+    """CSR pattern + COO->CSR permutation of an `indices [2, nnz]` tensor, built once per tensor."""
+    key = (indices.data_ptr(), indices._version, tuple(indices.shape), tuple(shape))
+    hit = _pattern_cache.get(key)
+    if hit is None:
+        if len(_pattern_cache) >= 16:
+            _pattern_cache.pop(next(iter(_pattern_cache)))
+        hit = CSRGraph.from_coo(indices[0], indices[1], None, int(shape[0]), int(shape[1]), return_perm=True)
+        _pattern_cache[key] = hit
+    return hit
+
+
+class SpecialSpmmFunction:
+    """`SpecialSpmmFunction.apply(indices, values, shape, b)` of GAT/models/layers.py:43-64: the product
+    of a sparse matrix given as COO (indices, values) with a dense matrix, differentiable in `values`
+    and `b` only.  Forward = CSR SpMM; backward = edge-gradient SDDMM + transpose SpMM — the
+    reference's backward goes through a dense N x N `grad_output @ b.T` (layers.py:59-61)."""
+
+    @staticmethod
+    def apply(indices, values, shape, b):
+        assert not indices.requires_grad
+        pattern, perm = _coo_pattern(indices, shape)
+        return spmm_values(pattern, values[perm], b)
+
+
+class SpecialSpmm(nn.Module):
+    def forward(self, indices, values, shape, b):
+        return SpecialSpmmFunction.apply(indices, values, shape, b)
 
 
 def _fused_heads(x, adj, Ws, a_srcs, a_dsts, alpha, mode, elu, dropout, training, out=None):

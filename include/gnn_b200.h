@@ -152,6 +152,16 @@ int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const f
                               const float* bias /*nullable [F], fp32*/, int32_t relu,
                               void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 
+/* Edge-gradient SDDMM: out[e] = <A[row[e], 0:F], B[col[e], 0:F]> for e in [0, nnz).
+ * The gradient of Y = S·B with respect to the VALUES of S is dY_i · B_j on the pattern of S:
+ * GAT/models/layers.py:55-61 (SpecialSpmmFunction.backward) forms the dense N x N product
+ * `grad_output.matmul(b.t())` and indexes it with row*N+col; this forms only the nnz dots.
+ * row / col: device id arrays of idx_bits (32|64) bits in any edge order (COO); edge-parallel,
+ * deterministic. */
+int gnn_sddmm_coo_f32(const void* row, const void* col, int idx_bits, int64_t nnz,
+                      const float* A, int64_t lda, const float* B, int64_t ldb, int32_t F,
+                      float* out /*[nnz]*/, gnn_stream_t stream);
+
 /* ---- GraphSAGE: fused gather + reduce over fixed-fanout index blocks ----------- */
 /* out[i,:] = reduce_k table[idx[i*fanout+k], :]
  * (replaces the CPU gather GraphSAGE_Pytorch/data_utils.py:64 + .mean/.sum/.max(dim=1)

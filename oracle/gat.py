@@ -98,3 +98,22 @@ def edge_attention_f64(rowptr, col, Wh, s, t, alpha, mode=0, keep=None):
             att = att * keep[rowptr[i]:rowptr[i + 1]]
         out[i] = np.einsum("eh,ehf->hf", att, Wh[js])
     return out
+
+
+def special_spmm(indices, values, shape, b, grad_output=None):
+    """GAT/models/layers.py:43-64 restated in float64 numpy: out = S·b for the COO matrix
+    (indices, values) — duplicates add — and, given grad_output, the two gradients of
+    `SpecialSpmmFunction.backward`: grad_values[e] = <grad_output[row_e], b[col_e]> (layers.py:59-61
+    picks these out of a dense N x N product) and grad_b = Sᵀ·grad_output (layers.py:63)."""
+    import numpy as np
+    rows, cols = np.asarray(indices[0]), np.asarray(indices[1])
+    v, bb = np.asarray(values, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    out = np.zeros((int(shape[0]), bb.shape[1]))
+    np.add.at(out, rows, v[:, None] * bb[cols])
+    if grad_output is None:
+        return out
+    g = np.asarray(grad_output, dtype=np.float64)
+    grad_values = np.einsum("ef,ef->e", g[rows], bb[cols])
+    grad_b = np.zeros_like(bb)
+    np.add.at(grad_b, cols, v[:, None] * g[rows])
+    return out, grad_values, grad_b

@@ -215,6 +215,24 @@ def make_gatne():
     save("gatne_small.npz", **out)
 
 
+def make_special_spmm():
+    """GAT/models/layers.py:43-64 SpecialSpmmFunction on an UNSORTED COO pattern with one duplicated
+    entry: output, gradient w.r.t. the values (the edge-gradient SDDMM contract) and w.r.t. b."""
+    layers = R.gat_layers()
+    rng = np.random.default_rng(31)
+    n, m, F, nnz = 90, 90, 24, 900  # square: the reference indexes its dense gradient with row*N+col (layers.py:60)
+    rows, cols = rng.integers(0, n, nnz), rng.integers(0, m, nnz)
+    rows[-1], cols[-1] = rows[0], cols[0]  # a duplicate: two separate values on the same position
+    indices = torch.from_numpy(np.vstack((rows, cols)).astype(np.int64))
+    values = torch.from_numpy(rng.standard_normal(nnz).astype(np.float32)).requires_grad_(True)
+    b = torch.from_numpy(rng.standard_normal((m, F)).astype(np.float32)).requires_grad_(True)
+    G = torch.from_numpy(rng.standard_normal((n, F)).astype(np.float32))
+    out = layers.SpecialSpmmFunction.apply(indices, values, torch.Size([n, m]), b)
+    out.backward(G)
+    save("special_spmm.npz", indices=indices.numpy(), values=values.detach().numpy(), b=b.detach().numpy(), G=G.numpy(),
+         out=out.detach().numpy(), grad_values=values.grad.numpy(), grad_b=b.grad.numpy(), shape=np.array([n, m]))
+
+
 if __name__ == "__main__":
     assert R.available(), "reference not found"
     torch.set_num_threads(8)
@@ -225,3 +243,4 @@ if __name__ == "__main__":
     make_sage_v2()
     make_han()
     make_gatne()
+    make_special_spmm()

@@ -743,6 +743,67 @@ def test_spmm_powerlaw_properties(lib):
     assert Yt.shape == (200_000, 128)
 
 
+# ---------------------------------------------------------------- edge-gradient SDDMM / SpecialSpmm (a6)
+@pytest.mark.parametrize("F", [1, 3, 8, 24, 64, 128, 130, 602])
+def test_sddmm_vs_f64(lib, F):
+    rng = np.random.default_rng(F)
+    n, m, nnz = 700, 900, 20011
+    rows, cols = rng.integers(0, n, nnz), rng.integers(0, m, nnz)
+    A = rng.standard_normal((n, F)).astype(np.float32)
+    B = rng.standard_normal((m, F)).astype(np.float32)
+    ref = np.einsum("ef,ef->e", A[rows].astype(np.float64), B[cols].astype(np.float64))
+    for dt in (torch.int64, torch.int32):
+        out = Fn.sddmm(cuda(rows).to(dt), cuda(cols).to(dt), cuda(A), cuda(B))
+        assert rel_err(out.cpu().numpy(), ref) < TOL32
+    assert torch.equal(Fn.sddmm(cuda(rows), cuda(cols), cuda(A), cuda(B)), out.to(out.dtype))  # deterministic
+    # strided operands (row stride > F)
+    Ap = torch.zeros(n, F + 5, device=DEV)
+    Ap[:, :F] = cuda(A)
+    assert rel_err(Fn.sddmm(cuda(rows), cuda(cols), Ap[:, :F], cuda(B)).cpu().numpy(), ref) < TOL32
+
+
+def test_special_spmm_vs_reference_golden(lib):
+    """layers.SpecialSpmm == GAT/models/layers.py:43-70 on an unsorted COO with a duplicate: forward,
+    gradient w.r.t. the values (SDDMM) and w.r.t. b (transpose SpMM)."""
+    g = load_golden("special_spmm.npz")
+    indices = cuda(g["indices"])
+    values = cuda(g["values"]).requires_grad_(True)
+    b = cuda(g["b"]).requires_grad_(True)
+    shape = torch.Size(g["shape"].tolist())
+    out = layers.SpecialSpmm()(indices, values, shape, b)
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < TOL32
+    out.backward(cuda(g["G"]))
+    assert rel_err(values.grad.cpu().numpy(), g["grad_values"]) < TOL32
+    assert rel_err(b.grad.cpu().numpy(), g["grad_b"]) < TOL32
+    ref = ogat.special_spmm(g["indices"], g["values"], g["shape"], g["b"], g["G"])
+    assert rel_err(out.detach().cpu().numpy(), ref[0]) < TOL32 and rel_err(values.grad.cpu().numpy(), ref[1]) < TOL32
+    # second call reuses the cached pattern; values may change between calls
+    v2 = (cuda(g["values"]) * 2).requires_grad_(True)
+    out2 = layers.SpecialSpmmFunction.apply(indices, v2, shape, b.detach())
+    assert rel_err(out2.detach().cpu().numpy(), 2 * g["out"]) < TOL32
+
+
+def test_spmm_values_learned_adjacency(lib):
+    """A GCN over a LEARNED sparse adjacency (GTN/models/GTN.py:49-52 `gcn_conv`): gradients reach the
+    edge values through the SDDMM and the features through the transpose SpMM; power-law rows
+    included (one row is long enough for the chunked path)."""
+    n = 3000
+    rowptr, col, val = random_csr(n, n, 8, seed=5, long_row=(17, 6000))
+    pattern = CSRGraph(cuda(rowptr), cuda(col), None, n, n)
+    rng = np.random.default_rng(6)
+    X = rng.standard_normal((n, 48)).astype(np.float32)
+    G = rng.standard_normal((n, 48)).astype(np.float32)
+    vd = cuda(val).requires_grad_(True)
+    Xd = cuda(X).requires_grad_(True)
+    Y = Fn.spmm_values(pattern, vd, Xd)
+    Y.backward(cuda(G))
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    ref = ogat.special_spmm(np.vstack((rows, col)), val, (n, n), X, G)
+    assert rel_err(Y.detach().cpu().numpy(), ref[0]) < TOL32
+    assert rel_err(vd.grad.cpu().numpy(), ref[1]) < TOL32
+    assert rel_err(Xd.grad.cpu().numpy(), ref[2]) < TOL32
+
+
 # ---------------------------------------------------------------- GATNE (SURVEY §8f rank 3)
 def test_typed_gather_reduce_vs_oracle(lib):
     from oracle import gatne as ogatne

@@ -135,3 +135,10 @@ def test_gatne_encoders():
         params = _params(g, tag + ".")
         out = ogatne.encoder_forward(params, inputs, types, neigh, feats if use_feats else None, agg)
         assert rel_err(out.numpy(), g[f"{tag}.out"]) < TOL, tag
+
+
+def test_special_spmm_forward_and_edge_gradients():
+    """oracle/gat.special_spmm vs the unmodified SpecialSpmmFunction (unsorted COO, one duplicate)."""
+    g = load_golden("special_spmm.npz")
+    out, gv, gb = ogat.special_spmm(g["indices"], g["values"], g["shape"], g["b"], g["G"])
+    assert rel_err(out, g["out"]) < TOL and rel_err(gv, g["grad_values"]) < TOL and rel_err(gb, g["grad_b"]) < TOL
