@@ -221,19 +221,64 @@ class CapturedGraphSage:
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.logits = body()
             self.kernel_launches_per_replay = _lib.launch_count() - before
-        self.logits_host = torch.empty(self.logits.shape, dtype=self.logits.dtype).pin_memory()
+        # two-slot pipeline around the captured graph: ids of minibatch i+1 cross PCIe while minibatch i
+        # computes, logits of minibatch i-1 travel back meanwhile (submit / collect below)
+        n_in = 1 if adjacency is not None else len(self.ids)
+        self._n_in = n_in
+        self._h2d, self._d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._slots = []
+        for _ in range(2):
+            self._slots.append({
+                "stage": [torch.zeros_like(t) for t in self.ids[:n_in]],
+                "out": torch.empty_like(self.logits),
+                "host": torch.empty(self.logits.shape, dtype=self.logits.dtype).pin_memory(),
+                "ev_in": torch.cuda.Event(), "ev_free": torch.cuda.Event(), "ev_done": torch.cuda.Event(),
+                "ev_out": torch.cuda.Event(),
+            })
+        self._submitted = self._collected = 0
+        self.logits_host = self._slots[0]["host"]
 
     @torch.no_grad()
-    def __call__(self, host_id_blocks):
-        """host_id_blocks: pinned id tensors — every hop's block, or only the batch's node ids when
-        the runner samples on the device."""
+    def submit(self, host_id_blocks) -> int:
+        """Queue one minibatch (pinned id tensors: every hop's block, or only the batch's node ids when
+        the runner samples on the device).  At most two minibatches may be in flight: call `collect`
+        before the third `submit`.  Returns the ticket number."""
+        if self._submitted - self._collected >= 2:
+            raise RuntimeError("CapturedGraphSage: two minibatches already in flight; collect() first")
         if torch.is_tensor(host_id_blocks):
             host_id_blocks = [host_id_blocks]
-        n_in = 1 if self.adjacency is not None else len(self.ids)
+        slot = self._slots[self._submitted & 1]
+        with torch.cuda.stream(self._h2d):
+            self._h2d.wait_event(slot["ev_free"])            # the staging buffers were consumed
+            for dst, src in zip(slot["stage"], host_id_blocks[:self._n_in]):
+                dst.copy_(src, non_blocking=True)            # H2D: this minibatch's ids
+            slot["ev_in"].record(self._h2d)
         with torch.cuda.stream(self.stream):
-            for dst, src in zip(self.ids[:n_in], host_id_blocks[:n_in]):
-                dst.copy_(src, non_blocking=True)          # H2D: this minibatch's ids
+            self.stream.wait_event(slot["ev_in"])
+            for dst, src in zip(self.ids[:self._n_in], slot["stage"]):
+                dst.copy_(src)                               # device copy into the graph's static inputs
+            slot["ev_free"].record(self.stream)
             self.graph.replay()
-            self.logits_host.copy_(self.logits, non_blocking=True)  # D2H: the result
-        self.stream.synchronize()
-        return self.logits_host
+            slot["out"].copy_(self.logits)
+            slot["ev_done"].record(self.stream)
+        with torch.cuda.stream(self._d2h):
+            self._d2h.wait_event(slot["ev_done"])
+            slot["host"].copy_(slot["out"], non_blocking=True)  # D2H: the result
+            slot["ev_out"].record(self._d2h)
+        self._submitted += 1
+        return self._submitted - 1
+
+    def collect(self) -> torch.Tensor:
+        """Logits of the oldest minibatch in flight (pinned host tensor, valid until two more submits)."""
+        if self._collected >= self._submitted:
+            raise RuntimeError("CapturedGraphSage: nothing in flight")
+        slot = self._slots[self._collected & 1]
+        slot["ev_out"].synchronize()
+        self._collected += 1
+        self.logits_host = slot["host"]
+        return slot["host"]
+
+    def __call__(self, host_id_blocks):
+        """Synchronous form: submit one minibatch and wait for its logits."""
+        self.submit(host_id_blocks)
+        return self.collect()

@@ -493,6 +493,24 @@ def test_captured_graphsage_runner(lib):
     out = runner([b.cpu().pin_memory() for b in blocks]).clone()
     with torch.no_grad():
         assert torch.equal(out, model.forward_sampled(table, blocks).cpu())
+    # two minibatches in flight (submit / collect): same logits as one at a time, in submission order
+    batches = [torch.arange(s, s + 32, dtype=torch.int32) for s in (0, 50, 200, 333, 568)]
+    host = [[b.cpu().pin_memory() for b in Fn.multihop_sampling(csr, bt.to(DEV), [5, 3], seed=20 + k)]
+            for k, bt in enumerate(batches)]
+    sync = [runner(h).clone() for h in host]
+    piped = []
+    for k, h in enumerate(host):
+        runner.submit(h)
+        if k > 0:
+            piped.append(runner.collect().clone())
+    piped.append(runner.collect().clone())
+    assert len(piped) == len(sync) and all(torch.equal(a, b) for a, b in zip(piped, sync))
+    with pytest.raises(RuntimeError):
+        runner.collect()
+    runner.submit(host[0]); runner.submit(host[1])
+    with pytest.raises(RuntimeError):
+        runner.submit(host[2])
+    assert torch.equal(runner.collect(), sync[0]) and torch.equal(runner.collect(), sync[1])
     sampling = layers.CapturedGraphSage(model, table, 32, adjacency=csr, seed=5)
     o1 = sampling(batch.pin_memory()).clone()
     ids1 = [i.clone() for i in sampling.ids]
