@@ -12,11 +12,13 @@ through the aggregation hot path:
     hop-2 fused gather-mean  [25600 x 10 x 602]  } one launch (gnn_gather_reduce_multi_f32,
     hop-1 fused gather-mean  [ 1024 x 25 x 602]  } TMA ring)
     layer-2 mean             [ 1024 x 25 x 128]   (identity block over the hidden tensor)
-value    = sampled edges aggregated per second, kernels only, inputs resident in HBM.
-e2e      = the same metric through the public drop-in API (CapturedGraphSage over
-           GraphSage.forward_sampled): every step copies that step's sampled ids from pinned
+value    = sampled edges aggregated per second, kernels only, inputs resident in HBM; the L2 is
+           flushed between the timed iterations (flush outside the per-step event brackets);
+           `warm_l2` = the same steps back to back without the flush.
+e2e      = the same metric through the public drop-in API (CapturedGraphSage.submit/collect
+           over GraphSage.forward_sampled): every step copies that step's sampled ids from pinned
            host memory, runs the whole model forward (aggregation kernels + torch matmuls) and
-           reads the logits back to the host.
+           reads the logits back to the host; two minibatches in flight.
 roofline = the gather kernel (both hops): algorithmic bytes sum of n_src*fanout*(4+F*4)+n_src*F*4
            per launch over its CUDA-event duration, against the measured HBM peak.
 With N>1 every rank runs its own minibatches on its own replica of the table (SURVEY.md §8e:
