@@ -42,6 +42,7 @@ static std::map<std::string, int>& tune_map() {
       {"spmm.long_row", 2048},   // rows above this nnz go to the CTA-per-chunk path (planned call)
       {"spmm.chunk", 8192},      // edges per long-row chunk
       {"spmm.unroll", 0},        // 0 = heuristic
+      {"spmm.ctas3", 1},          // 1: multi-vector rows (CHUNKS 2..5) use the 3-CTAs/SM instantiation (0: 2 CTAs/SM)
       {"spmm.rows_per_team", 0},  // >0 overrides the caller's rows_per_team (tuning sweeps)
       {"spmm.team_edges", 512},   // host plan: edges one team should hold (graph.py rows_per_team)
       {"gat.stage_edges", 128},  // logits staged per warp pass

@@ -55,8 +55,13 @@ constexpr int kSpmmThreads = 256;
 // One-vector-per-lane variants are held to 64 registers (4 CTAs/SM): next to the 3 CTAs that a
 // concurrently running halo-push CTA leaves room for, this keeps the local-column pass of the
 // partitioned SpMM at full occupancy (at 80 registers it dropped from 3 to 2 CTAs per SM).
-template <typename T, int VEC, int GROUP, int CHUNKS, int U, bool EPI>
-__global__ void __launch_bounds__(kSpmmThreads, (CHUNKS == 1) ? 4 : 1) spmm_rbs_kernel(const SpmmArgs<T> a) {
+// MINB: CTAs per SM the register allocation is held to.  Multi-vector rows (CHUNKS 2..5) run the
+// instantiation held to 3 CTAs/SM (80 registers, a few spilled words): on the Reddit-shaped graph the
+// kernel is latency-bound and the third CTA is worth 4-11 % (F=602 fp32 34.1 -> 30.6 ms, bf16 23.6 ->
+// 21.7 ms; profiles/r01s2_kbench_spmm_reddit_ctas3_ab.jsonl).  "spmm.ctas3" = 0 selects the unconstrained
+// instantiation (100-140 registers, 2 CTAs/SM).
+template <typename T, int VEC, int GROUP, int CHUNKS, int U, bool EPI, int MINB = ((CHUNKS == 1) ? 4 : 1)>
+__global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_rbs_kernel(const SpmmArgs<T> a) {
   const int lane = threadIdx.x & 31;
   const int gl = threadIdx.x % GROUP;
   const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane - gl));
@@ -352,8 +357,14 @@ inline void spmm_rbs_launch(const SpmmArgs<T>& a, cudaStream_t st) {
   // token dynamic shared memory (<= 48 KB, unused by the kernel) keeps these CTAs off the SMs a
   // dedicated halo push has claimed (peer.cu); 0 outside the partitioned SpMM's local pass
   const size_t sm = (size_t)tuning("spmm.exclusion_smem_kb", 0) * 1024;
-  if (a.bias || a.relu) spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, true><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
-  else spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
+  if (a.bias || a.relu) {
+    spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, true><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
+  } else if (CHUNKS >= 2 && CHUNKS <= 5 && tuning("spmm.ctas3", 1)) {
+    spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false, (CHUNKS >= 2 && CHUNKS <= 5) ? 3 : 1>
+        <<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
+  } else {
+    spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
+  }
 }
 
 template <typename T, int VEC>

@@ -92,8 +92,9 @@ def bench_spmm(args, n, mean_deg, tag):
 
 
 def bench_gat(args):
-    for n, mean_deg, tag in ((2708, 4.9, "cora"), (3025, 730, "acm_dense"), (232_965, 100, "reddit_d100")):
-        if args.graph and tag != args.graph:
+    for n, mean_deg, tag in ((2708, 4.9, "cora"), (3025, 730, "acm_dense"), (232_965, 100, "reddit_d100"),
+                             (232_965, 492, "reddit_full")):
+        if (args.graph and tag != args.graph) or (tag == "reddit_full" and args.graph != tag):
             continue
         # skew=1: uniform targets, so in-degrees stay moderate like in the symmetric adjacencies
         # GAT/HAN are given (the transposed graph the backward walks has no 100k-edge rows)
