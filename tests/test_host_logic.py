@@ -33,6 +33,62 @@ def test_state_dict_matches_reference(fixture, prefix, build):
     assert ours == {k: tuple(v) for k, v in ref.items()}
 
 
+@pytest.mark.parametrize("tag,build", [
+    ("pt_t_sum", lambda f: layers.GraphEncoder(300, 32, 10, 3, 20, None)),
+    ("pt_i_sum", lambda f: layers.GraphEncoder(300, 32, 10, 3, 20, f)),
+    ("v1_t", lambda f: layers.GATNEModelV1(300, 32, 10, 3, 20, None)),
+    ("v1_i", lambda f: layers.GATNEModelV1(300, 32, 10, 3, 20, f)),
+])
+def test_gatne_state_dict_matches_reference(tag, build):
+    g = load_golden("gatne_small.npz")
+    ref = _golden_param_shapes(g, tag + ".")
+    ours = {k: tuple(v.shape) for k, v in build(torch.from_numpy(g["features"])).state_dict().items()}
+    assert ours == {k: tuple(v) for k, v in ref.items()}
+    full = layers.GATNEModel(300, 32, 10, 3, 20, None)  # GATNE_Pytorch/models/GATNE.py:117-128
+    assert set(full.state_dict()) == {"encoder." + k for k in _golden_param_shapes(g, "pt_t_sum.")} | {"decoder.weights"}
+
+
+@pytest.mark.parametrize("num_layers", [1, 2, 3, 4])
+def test_gcn_model_layout_matches_reference(num_layers):
+    """Module names, order and widths of GCN/GCN.py:5-19 for every depth (the fused-ReLU walk of our forward
+    relies on the Graph_conv_layer -> ReLU -> Dropout order)."""
+    m = layers.GCN_Model(30, 16, 7, num_layers, 0.5)
+    names = [n for n, _ in m.gcn_blocks.named_children()]
+    expect, widths = [], []
+    for i in range(num_layers):
+        if i == 0:
+            expect += ["gcn0", "relu0", "dropout0"]
+            widths.append((30, 16))
+        elif i == num_layers - 1:
+            expect += [f"gcn{i}"]
+            widths.append((16, 7))
+        else:
+            expect += [f"gcn{i}", f"relu{i}", f"dropout{i}"]
+            widths.append((16, 16))
+    assert names == expect
+    got = [(l.in_features, l.out_features) for l in m.gcn_blocks if l._get_name() == "Graph_conv_layer"]
+    assert got == widths
+    assert set(m.state_dict()) == {f"gcn_blocks.gcn{i}.{p}" for i in range(num_layers) for p in ("dense.weight", "bias")}
+    assert "bias" not in dict(layers.Graph_conv_layer(4, 2, is_bias=False).named_parameters())
+
+
+def test_runtime_and_new_entry_points_refuse_cpu():
+    from graphneuralnetwork_b200 import runtime
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.GnnError):
+            runtime.CapturedTrainStep(torch.nn.Linear(2, 2), lambda: torch.zeros(()))
+        with pytest.raises(_lib.GnnError):
+            runtime.CapturedForward(lambda: torch.zeros(()))
+    with pytest.raises(_lib.GnnError):
+        Fn.typed_gather_reduce(torch.zeros(4, 2, 3), torch.zeros(2, 2, 2, dtype=torch.int64))
+    with pytest.raises(ValueError, match="please choice else aggregator"):
+        Fn.typed_gather_reduce(torch.zeros(4, 2, 3), torch.zeros(2, 2, 2, dtype=torch.int64), "max")
+    with pytest.raises(_lib.GnnError):
+        Fn.sddmm(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64), torch.zeros(2, 4), torch.zeros(2, 4))
+    with pytest.raises(_lib.GnnError):
+        layers.SpecialSpmm()(torch.zeros(2, 3, dtype=torch.int64), torch.zeros(3), torch.Size([2, 2]), torch.zeros(2, 4))
+
+
 def test_class_names_and_signatures():
     assert layers.Graph_conv_layer(4, 2)._get_name() == "Graph_conv_layer"  # GCN/GCN.py:23 dispatches on this
     sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]
@@ -46,6 +102,14 @@ def test_class_names_and_signatures():
     assert list(inspect.signature(layers.GraphSAGE.forward).parameters)[1:5] == [
         "center_feats_data", "center_nodes_map", "center_neigh_feats_data", "center_neigh_nodes_map"]
     assert list(inspect.signature(layers.Aggregator).parameters) == ["neigh_feat", "agg_func"]
+    assert sig(layers.GraphEncoder) == ["num_nodes", "embedding_size", "embedding_u_size", "edge_type_count",
+                                        "attention_size", "features", "agg_func", "kwargs"]
+    assert sig(layers.GATNEModelV1) == ["num_nodes", "embedding_size", "embedding_u_size", "edge_type_count", "dim_a",
+                                        "features", "kwargs"]
+    assert list(inspect.signature(layers.GATNEModel.forward).parameters)[1:] == ["inputs", "node_types", "node_neigh",
+                                                                                "context_negative"]
+    assert list(inspect.signature(layers.SpecialSpmm.forward).parameters)[1:] == ["indices", "values", "shape", "b"]
+    assert list(inspect.signature(layers.SageLayer.__init__).parameters)[1:4] == ["input_size", "output_size", "gcn"]
 
 
 def test_cpu_tensors_are_refused_no_fallback(lib):
