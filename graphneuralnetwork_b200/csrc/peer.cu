@@ -65,25 +65,43 @@ __global__ void __launch_bounds__(THREADS) halo_push_kernel(const PushArgs a) {
     k_end = total;
   }
   const int64_t rot_rows = a.send_off[a.rot];
+  // position k of this warp's walk -> index into send_rows (SCHED 0 walks the segments rotated by rot)
+  auto slot_of = [&](int64_t k) -> int64_t {
+    if (SCHED == 1) return seg0 + k;
+    k += rot_rows;
+    return k >= total ? k - total : k;
+  };
+  // The sent-row ids of the NEXT iteration are loaded before the rows of this one are stored: without
+  // this prefetch every iteration was a chain of two dependent DRAM round trips (id, then row), which
+  // held a dedicated push SM to ~15 GB/s.
+  int32_t rid[UNROLL], rid_next[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const int64_t k = k_begin + u;
+    rid[u] = (k < k_end) ? __ldg(a.send_rows + slot_of(k)) : -1;
+  }
   for (int64_t k0 = k_begin; k0 < k_end; k0 += k_step) {
     const float* src[UNROLL];
     float* dst[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      int64_t k = k0 + u;
+      const int64_t kn = k0 + k_step + u;
+      rid_next[u] = (kn < k_end) ? __ldg(a.send_rows + slot_of(kn)) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t k = k0 + u;
       src[u] = nullptr;
       dst[u] = nullptr;
       if (k < k_end) {
+        src[u] = a.X + (int64_t)rid[u] * a.ldx;
         if (SCHED == 1) {
-          src[u] = a.X + (int64_t)__ldg(a.send_rows + seg0 + k) * a.ldx;
           dst[u] = halo_q + k * a.ld_halo;
         } else {
-          k += rot_rows;
-          k = k >= total ? k - total : k;
+          const int64_t ks = slot_of(k);
           int q = 0;
-          while (q + 1 < a.n_peers && k >= a.send_off[q + 1]) ++q;
-          src[u] = a.X + (int64_t)__ldg(a.send_rows + k) * a.ldx;
-          dst[u] = a.halo[q] + (a.dst_off[q] + (k - a.send_off[q])) * a.ld_halo;
+          while (q + 1 < a.n_peers && ks >= a.send_off[q + 1]) ++q;
+          dst[u] = a.halo[q] + (a.dst_off[q] + (ks - a.send_off[q])) * a.ld_halo;
         }
       }
     }
@@ -96,6 +114,8 @@ __global__ void __launch_bounds__(THREADS) halo_push_kernel(const PushArgs a) {
       for (int u = 0; u < UNROLL; ++u)
         if (dst[u]) VecIO<float, VEC>::store(dst[u] + c, v[u]);
     }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) rid[u] = rid_next[u];
   }
 }
 
@@ -183,11 +203,13 @@ int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* sen
     static size_t configured = 0;
     if (smem > configured) {
       GNN_CUDA(cudaFuncSetAttribute(halo_push_kernel<4, 4, 0, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      GNN_CUDA(cudaFuncSetAttribute(halo_push_kernel<4, 8, 0, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GNN_CUDA(cudaFuncSetAttribute(halo_push_kernel<4, 8, 0, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
     const unsigned gd = (unsigned)(dedicated < num_sms() ? dedicated : num_sms());
-    if (unroll >= 8) halo_push_kernel<4, 8, 0, 1024><<<gd, 1024, smem, st>>>(a);
+    // 64 KB of rows in flight per SM either way: 32 warps x 4 rows, or 16 warps x 8 rows (8 rows per
+    // warp need more than the 64 registers a 1024-thread CTA leaves each thread)
+    if (unroll >= 8) halo_push_kernel<4, 8, 0, 512><<<gd, 512, smem, st>>>(a);
     else halo_push_kernel<4, 4, 0, 1024><<<gd, 1024, smem, st>>>(a);
   } else if (vec4) {
     if (sched == 1 && unroll >= 8) halo_push_kernel<4, 8, 1, 256><<<g, 256, 0, st>>>(a);

@@ -50,8 +50,10 @@ def main():
     ap.add_argument("--scatter", action="store_true")
     ap.add_argument("--halo-ctas", type=int, default=1)
     ap.add_argument("--halo-sched", type=int, default=0)
-    ap.add_argument("--halo-unroll", type=int, default=8)
+    ap.add_argument("--halo-unroll", type=int, nargs="+", default=[8])
     ap.add_argument("--overlap-only", action="store_true")
+    ap.add_argument("--cross-check", action="store_true",
+                    help="compare the last p2p result with the NCCL transport's (any graph size)")
     ap.add_argument("--dedicated", type=int, nargs="+", default=[0], help="PartitionedSpmm.dedicated values to sweep")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -61,7 +63,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_tuning("halo.ctas_per_sm", a.halo_ctas)
     _lib.set_tuning("halo.schedule", a.halo_sched)
-    _lib.set_tuning("halo.unroll", a.halo_unroll)
+    _lib.set_tuning("halo.unroll", a.halo_unroll[0])
     csr, bounds, nnz_total = build_rank_block(a.n, a.deg, rank, world, dev, skew=a.skew, p_local=a.p_local, window=a.window,
                                                   scatter=a.scatter)
     plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world)
@@ -79,9 +81,13 @@ def main():
     for transport in (a.transports if world > 1 else ["none"]):
         op = PartitionedSpmm(plan, a.F, dev, transport=transport)
         Y = torch.empty(n_loc, a.F, device=dev)
-        for overlap, dedicated in [(o, d) for d in (a.dedicated if transport == "p2p" else [0])
-                                   for o in ([True] if (a.overlap_only or world == 1) else [True, False])]:
+        for overlap, dedicated, unroll in [(o, d, u) for u in (a.halo_unroll if transport == "p2p" else a.halo_unroll[:1])
+                                           for d in (a.dedicated if transport == "p2p" else [0])
+                                           for o in ([True] if (a.overlap_only or world == 1) else [True, False])]:
+            if unroll != a.halo_unroll[0] and dedicated == 0:
+                continue  # the shared-SM schedule is swept with the first unroll only
             op.dedicated = dedicated
+            _lib.set_tuning("halo.unroll", unroll)
             for _ in range(a.warmup):
                 op.forward(X, out=Y, overlap=overlap)
             torch.cuda.synchronize()
@@ -99,7 +105,7 @@ def main():
             if rank == 0:
                 hal = [int(s[0]) for s in allstats]
                 print(json.dumps({"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F,
-                                  "transport": transport, "overlap": overlap, "dedicated_sms": dedicated, "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": a.halo_unroll, "ms": ms.item(),
+                                  "transport": transport, "overlap": overlap, "dedicated_sms": dedicated, "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": unroll, "ms": ms.item(),
                                   "edges_per_s": nnz_total / ms.item() * 1e3, "p_local": a.p_local, "window": a.window, "scatter": a.scatter, "skew": a.skew,
                                   "halo_rows_max": max(hal), "halo_rows_mean": sum(hal) / world,
                                   "halo_gb_recv_max": max(hal) * a.F * 4 / 1e9,
@@ -130,6 +136,18 @@ def main():
             if rank == 0:
                 print(json.dumps({"phases": transport, "exchange_ms": t_x, "local_ms": t_l, "remote_ms": t_r,
                                   "exchange_gbs_recv": max(int(s[0]) for s in allstats) * a.F * 4 / t_x / 1e6}), flush=True)
+        if a.cross_check and world > 1 and transport == "p2p":
+            ref_op = PartitionedSpmm(plan, a.F, dev, transport="nccl")
+            Yr = ref_op.forward(X, overlap=False)
+            torch.cuda.synchronize()
+            err = (Y - Yr).abs().max().item() / max(Yr.abs().max().item(), 1e-30)
+            errs = torch.tensor([err], device=dev, dtype=torch.float64)
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(json.dumps({"cross_check": "p2p vs nccl transport", "max_rel_err": errs.item(),
+                                  "ok": errs.item() < 1e-6}), flush=True)
+            ref_op.close()
+            del ref_op, Yr
         if a.check:
             # every rank rebuilds the FULL graph (small n only) and checks its own rows
             full = S.powerlaw_csr(a.n, a.deg, seed=0, device=dev, skew=a.skew, p_local=a.p_local, window=a.window,
