@@ -137,13 +137,13 @@ class PartitionedSpmm:
     def __init__(self, plan: HaloPlan, F: int, device, group=None, transport: str = "p2p",
                  dedicated_sms: Optional[int] = None):
         """dedicated_sms: SMs the fused NVLink push gets to itself while the local-column pass runs on
-        the rest (peer.cu).  None = measured default: 48 at 8 GPUs, where the exchange is the critical
-        path (r01, papers100M-shaped: 34.9 ms shared SMs -> 33.5 / 32.8 ms with 32 / 48 dedicated; 16
-        SMs cannot feed NVLink: 53 ms); 0 (one small push CTA on every SM) below that."""
+        the rest (peer.cu).  None = measured default: 32 at 8 GPUs, where the exchange is the critical
+        path (r01, papers100M-shaped: 36.4 ms on shared SMs -> 35.7 / 30.5 / 31.7 ms with 24 / 32 / 48
+        dedicated; 16 SMs cannot feed NVLink: 47 ms); 0 (one small push CTA on every SM) below that."""
         from .graph import CSRGraph
         self.plan, self.F, self.dev, self.group = plan, int(F), torch.device(device), group
         self.transport = transport if plan.world > 1 else "none"
-        self.dedicated = (48 if plan.world >= 8 else 0) if dedicated_sms is None else int(dedicated_sms)
+        self.dedicated = (32 if plan.world >= 8 else 0) if dedicated_sms is None else int(dedicated_sms)
         n_loc, n_halo = plan.n_local, max(plan.n_halo, 1)
         self.A_loc = CSRGraph(plan.rowptr_loc, plan.col_loc, plan.val_loc, n_loc, n_loc)
         self.A_rem = CSRGraph(plan.rowptr_rem, plan.col_rem, plan.val_rem, n_loc, n_halo)
