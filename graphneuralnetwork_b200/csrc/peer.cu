@@ -119,6 +119,91 @@ __global__ void __launch_bounds__(THREADS) halo_push_kernel(const PushArgs a) {
   }
 }
 
+// ---- TMA variant of the push (experimental, "halo.tma" = 1; not the default) -------------------
+// The vector-store push sustains only ~16-20 GB/s of remote stores per SM (r01 8-GPU sweep), so NVLink
+// needs >= 32 SMs.  Here no feature row passes through registers or the load/store unit: every warp is
+// an independent mover with a ring of kTmaStages shared-memory stages of 32 rows.  32 lanes issue one
+// bulk gather (cp.async.bulk global -> shared) each; when the stage's mbarrier completes, ONE lane issues
+// ONE bulk store (cp.async.bulk shared -> peer global) for the whole stage: the rows a peer receives are
+// consecutive in its halo buffer, so a stage leaves as a single 16 KB NVLink write.  The host deals whole
+// stages ("chunks") that never straddle a peer segment, in the rotated order of SCHED 0.
+constexpr int kTmaStages = 3;
+constexpr int kTmaWarps = 4;
+
+struct PushTmaArgs {
+  const float* X;
+  int64_t ldx;
+  int32_t row_bytes;            // F * 4, multiple of 16, == ld_halo * 4 (received rows are contiguous)
+  const int32_t* send_rows;
+  int64_t seg_begin[kMaxPeers];   // rotated slot s: first entry of send_rows
+  int64_t seg_rows[kMaxPeers];    // rotated slot s: rows to send
+  int64_t chunk_off[kMaxPeers + 1];  // rotated slot s: first chunk id (32 rows per chunk)
+  float* dst[kMaxPeers];          // rotated slot s: peer halo base + dst_off rows
+  int32_t n_slots;
+};
+
+__global__ void __launch_bounds__(kTmaWarps * 32) halo_push_tma_kernel(const PushTmaArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = 32 * a.row_bytes;
+  unsigned char* ring = smem + (size_t)warp * kTmaStages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kTmaWarps * kTmaStages * stage_bytes) + warp * kTmaStages;
+  if (lane == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(full + s, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const int64_t n_chunks = a.chunk_off[a.n_slots];
+  const int64_t w = (int64_t)blockIdx.x * kTmaWarps + warp;
+  const int64_t nw = (int64_t)gridDim.x * kTmaWarps;
+  // chunk id -> (slot, first row of the chunk within the slot's segment)
+  auto locate = [&](int64_t c, int& slot, int64_t& row0) {
+    slot = 0;
+    while (slot + 1 < a.n_slots && c >= a.chunk_off[slot + 1]) ++slot;
+    row0 = (c - a.chunk_off[slot]) * 32;
+  };
+  auto load_id = [&](int64_t c) -> int32_t {
+    if (c >= n_chunks) return -1;
+    int slot;
+    int64_t row0;
+    locate(c, slot, row0);
+    const int64_t r = row0 + lane;
+    return r < a.seg_rows[slot] ? __ldg(a.send_rows + a.seg_begin[slot] + r) : -1;
+  };
+  int32_t rid = load_id(w);
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t c = w; c < n_chunks; c += nw) {
+    const int32_t rid_next = load_id(c + nw);  // ids of the next chunk while this one moves
+    int slot;
+    int64_t row0;
+    locate(c, slot, row0);
+    const int64_t left = a.seg_rows[slot] - row0;
+    const int rows = (int)(left < 32 ? left : 32);
+    // the stage is reused every kTmaStages chunks: its previous bulk store must have read it
+    if (lane == 0) bulk_wait_group_read<kTmaStages - 1>();
+    __syncwarp();
+    unsigned char* st = ring + (size_t)stage * stage_bytes;
+    if (lane == 0) mbar_arrive_expect_tx(full + stage, (uint32_t)rows * (uint32_t)a.row_bytes);
+    __syncwarp();
+    if (lane < rows)
+      bulk_g2s(st + (size_t)lane * a.row_bytes, a.X + (int64_t)rid * a.ldx, (uint32_t)a.row_bytes, full + stage);
+    mbar_wait(full + stage, parity);
+    if (lane == 0) {
+      fence_proxy_async_smem();
+      bulk_s2g(reinterpret_cast<unsigned char*>(a.dst[slot]) + row0 * a.row_bytes, st, (uint32_t)rows * (uint32_t)a.row_bytes);
+      bulk_commit_group();
+    }
+    rid = rid_next;
+    if (++stage == kTmaStages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane == 0) bulk_wait_group<0>();  // every store performed before the kernel (and the barrier after it) ends
+  __syncwarp();
+}
+
 }  // namespace
 
 extern "C" {
@@ -198,7 +283,37 @@ int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* sen
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = (unsigned)grid;
   const int dedicated = tuning("halo.dedicated_sms", 0);
-  if (dedicated > 0 && vec4) {
+  if (tuning("halo.tma", 0) && vec4 && ld_halo == F && ((int64_t)F * 4) % 16 == 0 && (int64_t)F * 4 * 32 * kTmaStages <= 56 * 1024) {
+    // experimental TMA mover (see halo_push_tma_kernel); needs contiguous received rows (ld_halo == F)
+    PushTmaArgs t{};
+    t.X = X;
+    t.ldx = ldx;
+    t.row_bytes = F * 4;
+    t.send_rows = send_rows;
+    int ns = 0;
+    t.chunk_off[0] = 0;
+    for (int s = 0; s < n_peers; ++s) {
+      const int q = (first_peer + s) % n_peers;
+      const int64_t rows = a.send_off[q + 1] - a.send_off[q];
+      if (rows == 0) continue;
+      t.seg_begin[ns] = a.send_off[q];
+      t.seg_rows[ns] = rows;
+      t.dst[ns] = a.halo[q] + a.dst_off[q] * ld_halo;
+      t.chunk_off[ns + 1] = t.chunk_off[ns] + (rows + 31) / 32;
+      ++ns;
+    }
+    t.n_slots = ns;
+    const size_t smem = (size_t)kTmaWarps * kTmaStages * 32 * t.row_bytes + (size_t)kTmaWarps * kTmaStages * 8;
+    static size_t configured = 0;
+    if (smem > configured) {
+      GNN_CUDA(cudaFuncSetAttribute(halo_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    int64_t gt = dedicated > 0 ? dedicated : num_sms();
+    const int64_t need = (t.chunk_off[ns] + kTmaWarps - 1) / kTmaWarps;
+    gt = gt > need ? need : gt;
+    halo_push_tma_kernel<<<(unsigned)(gt < 1 ? 1 : gt), kTmaWarps * 32, smem, st>>>(t);
+  } else if (dedicated > 0 && vec4) {
     const size_t smem = (size_t)tuning("halo.exclusion_smem_kb", 200) * 1024;
     static size_t configured = 0;
     if (smem > configured) {

@@ -144,6 +144,7 @@ class PartitionedSpmm:
         self.plan, self.F, self.dev, self.group = plan, int(F), torch.device(device), group
         self.transport = transport if plan.world > 1 else "none"
         self.dedicated = (32 if plan.world >= 8 else 0) if dedicated_sms is None else int(dedicated_sms)
+        self.tma = False  # experimental TMA mover of peer.cu ("halo.tma"); not validated on hardware yet
         n_loc, n_halo = plan.n_local, max(plan.n_halo, 1)
         self.A_loc = CSRGraph(plan.rowptr_loc, plan.col_loc, plan.val_loc, n_loc, n_loc)
         self.A_rem = CSRGraph(plan.rowptr_rem, plan.col_rem, plan.val_rem, n_loc, n_halo)
@@ -199,6 +200,7 @@ class PartitionedSpmm:
             b = self._step & 1
             ptrs = (C.c_void_p * plan.world)(*self._peer_ptrs[b])
             _lib.set_tuning("halo.dedicated_sms", self.dedicated)
+            _lib.set_tuning("halo.tma", 1 if self.tma else 0)
             _lib.check(lib.gnn_halo_push_f32(X.data_ptr(), X.stride(0), self.F, plan.send_rows.data_ptr(), self._send_off,
                                              ptrs, self._dst_off, self.ld, plan.world, (plan.rank + 1) % plan.world,
                                              torch.cuda.current_stream().cuda_stream), "gnn_halo_push_f32")
@@ -230,7 +232,8 @@ class PartitionedSpmm:
                 self._ev_halo.record(self.comm)
             # local columns while the halo is in flight; with a dedicated push (halo.dedicated_sms) this
             # pass asks for token shared memory so the scheduler keeps it off the push's SMs
-            excl = 28 if (self.transport == "p2p" and self.dedicated > 0) else 0
+            # (the TMA mover's ring leaves 35 KB of an SM's shared memory free: ask for 40 KB then)
+            excl = (40 if self.tma else 28) if (self.transport == "p2p" and self.dedicated > 0) else 0
             if excl:
                 _lib.set_tuning("spmm.exclusion_smem_kb", excl)
             try:

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--halo-sched", type=int, default=0)
     ap.add_argument("--halo-unroll", type=int, nargs="+", default=[8])
     ap.add_argument("--overlap-only", action="store_true")
+    ap.add_argument("--tma", action="store_true", help="experimental TMA mover for the p2p push (halo.tma)")
     ap.add_argument("--cross-check", action="store_true",
                     help="compare the last p2p result with the NCCL transport's (any graph size)")
     ap.add_argument("--dedicated", type=int, nargs="+", default=[0], help="PartitionedSpmm.dedicated values to sweep")
@@ -87,6 +88,7 @@ def main():
             if unroll != a.halo_unroll[0] and dedicated == 0:
                 continue  # the shared-SM schedule is swept with the first unroll only
             op.dedicated = dedicated
+            op.tma = bool(a.tma)
             _lib.set_tuning("halo.unroll", unroll)
             for _ in range(a.warmup):
                 op.forward(X, out=Y, overlap=overlap)
@@ -105,7 +107,7 @@ def main():
             if rank == 0:
                 hal = [int(s[0]) for s in allstats]
                 print(json.dumps({"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F,
-                                  "transport": transport, "overlap": overlap, "dedicated_sms": dedicated, "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": unroll, "ms": ms.item(),
+                                  "transport": transport, "overlap": overlap, "dedicated_sms": dedicated, "tma": bool(a.tma), "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": unroll, "ms": ms.item(),
                                   "edges_per_s": nnz_total / ms.item() * 1e3, "p_local": a.p_local, "window": a.window, "scatter": a.scatter, "skew": a.skew,
                                   "halo_rows_max": max(hal), "halo_rows_mean": sum(hal) / world,
                                   "halo_gb_recv_max": max(hal) * a.F * 4 / 1e9,
