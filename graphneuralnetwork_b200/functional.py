@@ -166,7 +166,7 @@ class _GcnAggregateFn(torch.autograd.Function):
             (Y,) = ctx.saved_tensors
             dZ = dY * (Y > 0).to(dY.dtype)
         dS = spmm_raw(ctx.g.transpose(), dZ.contiguous()) if ctx.needs_input_grad[0] else None
-        db = dZ.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        db = dZ.sum(dim=0, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[1]) else None  # bias is fp32
         return dS, db, None, None
 
 
