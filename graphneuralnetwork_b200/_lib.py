@@ -62,6 +62,7 @@ SIGNATURES = {
     "gnn_peer_open": (cint, [ptr, C.POINTER(ptr)]),
     "gnn_peer_close": (cint, [ptr]),
     "gnn_peer_free": (cint, [ptr]),
+    "gnn_peer_copy_async": (cint, [ptr, ptr, size_t, ptr]),
     "gnn_halo_push_f32": (cint, [ptr, i64, i32, ptr, ptr, ptr, ptr, i64, i32, i32, ptr]),
 }
 

@@ -244,6 +244,13 @@ int gnn_peer_free(void* dev_ptr) {
   return GNN_OK;
 }
 
+int gnn_peer_copy_async(void* dst, const void* src, size_t bytes, gnn_stream_t stream) {
+  if (bytes == 0) return GNN_OK;
+  GNN_REQUIRE(dst && src, GNN_ERR_BAD_ARG, "null pointer");
+  GNN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return GNN_OK;
+}
+
 int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F, const int32_t* send_rows, const int64_t* send_off_host,
                       float* const* peer_halo_host, const int64_t* dst_off_host, int64_t ld_halo, int32_t n_peers,
                       int32_t first_peer, gnn_stream_t stream) {

@@ -156,6 +156,13 @@ class PartitionedSpmm:
         self._step = 0
         self._peer_ptrs = None
         lib = _lib.load()
+        if self.transport == "ce":
+            # experimental (not validated on hardware yet): same IPC halo buffers as "p2p", but the rows are
+            # first packed into a local send buffer and then moved by the copy engines, one copy per peer
+            self._ce = True
+            self.transport = "p2p"
+        else:
+            self._ce = False
         if self.transport == "p2p":
             # two halo buffers (ping-pong), exported to every peer through CUDA IPC
             self._own, handles = [], []
@@ -186,6 +193,12 @@ class PartitionedSpmm:
                 off.append(off[-1] + c)
             self._send_off = (C.c_int64 * (plan.world + 1))(*off)
             self._dst_off = (C.c_int64 * plan.world)(*plan.dst_off)
+            if self._ce:
+                self._off = off
+                self._sendbuf = torch.empty((max(off[-1], 1), self.ld), dtype=torch.float32, device=self.dev)
+                self._copy_streams = [torch.cuda.Stream(device=self.dev, priority=-1) for _ in range(4)]
+                self._ev_packed = torch.cuda.Event()
+                self._ev_copied = [torch.cuda.Event() for _ in range(4)]
         elif self.transport == "nccl":
             self.halo = [torch.empty((n_halo, self.F), dtype=torch.float32, device=self.dev)]
             self._sendbuf = torch.empty((max(int(plan.send_rows.numel()), 1), self.F), dtype=torch.float32, device=self.dev)
@@ -196,6 +209,31 @@ class PartitionedSpmm:
     # -- halo exchange ---------------------------------------------------------------------
     def _exchange(self, X: torch.Tensor) -> torch.Tensor:
         plan, lib = self.plan, _lib.load()
+        if self.transport == "p2p" and self._ce:
+            # pack: the push kernel with this rank's own send buffer as every "peer" (rows land in send order)
+            b = self._step & 1
+            cur = torch.cuda.current_stream()
+            own = (C.c_void_p * plan.world)(*([self._sendbuf.data_ptr()] * plan.world))
+            _lib.set_tuning("halo.dedicated_sms", 0)
+            _lib.set_tuning("halo.tma", 0)
+            _lib.check(lib.gnn_halo_push_f32(X.data_ptr(), X.stride(0), self.F, plan.send_rows.data_ptr(), self._send_off,
+                                             own, (C.c_int64 * plan.world)(*self._off[:plan.world]), self.ld, plan.world,
+                                             0, cur.cuda_stream), "gnn_halo_push_f32(pack)")
+            self._ev_packed.record(cur)
+            row_bytes = self.ld * 4
+            for s_i in range(1, plan.world):  # rotated: rank r copies to r+1 first
+                q = (plan.rank + s_i) % plan.world
+                st = self._copy_streams[s_i % len(self._copy_streams)]
+                st.wait_event(self._ev_packed)
+                n_rows = self._off[q + 1] - self._off[q]
+                _lib.check(lib.gnn_peer_copy_async(self._peer_ptrs[b][q] + plan.dst_off[q] * row_bytes,
+                                                   self._sendbuf.data_ptr() + self._off[q] * row_bytes,
+                                                   n_rows * row_bytes, st.cuda_stream), "gnn_peer_copy_async")
+            for k, st in enumerate(self._copy_streams):
+                self._ev_copied[k].record(st)
+                cur.wait_event(self._ev_copied[k])
+            dist.all_reduce(self._flag, group=self.group)
+            return self.halo[b]
         if self.transport == "p2p":
             b = self._step & 1
             ptrs = (C.c_void_p * plan.world)(*self._peer_ptrs[b])

@@ -283,6 +283,11 @@ int gnn_synth_gcn_values(int64_t n_rows, int64_t row_offset, const int64_t* rowp
                          const int64_t* deg_all /*[n_cols] global degrees*/, float* val, gnn_stream_t stream);
 
 /* ---- multi-GPU halo exchange over NVLink peer memory ------------ */
+/* Copy-engine transfer between two device allocations of this process' address space (a peer's
+ * gnn_peer_open mapping included): cudaMemcpyAsync device-to-device on `stream`.  Used by the
+ * experimental transport="ce" of the partitioned SpMM (pack locally, then one copy per peer). */
+int gnn_peer_copy_async(void* dst, const void* src, size_t bytes, gnn_stream_t stream);
+
 /* Peer buffers are plain cudaMalloc allocations exported with CUDA IPC, one process per
  * GPU.  gnn_halo_push copies, for every peer q, the rows send_rows[send_off[q]..send_off[q+1])
  * of the local X straight into peer q's halo buffer at row dst_off[q] with 128-bit

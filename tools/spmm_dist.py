@@ -82,6 +82,7 @@ def main():
     for transport in (a.transports if world > 1 else ["none"]):
         op = PartitionedSpmm(plan, a.F, dev, transport=transport)
         Y = torch.empty(n_loc, a.F, device=dev)
+        # transports: p2p (fused NVLink push), nccl (library baseline), ce (experimental: local pack + copy engines)
         for overlap, dedicated, unroll in [(o, d, u) for u in (a.halo_unroll if transport == "p2p" else a.halo_unroll[:1])
                                            for d in (a.dedicated if transport == "p2p" else [0])
                                            for o in ([True] if (a.overlap_only or world == 1) else [True, False])]:
@@ -138,7 +139,7 @@ def main():
             if rank == 0:
                 print(json.dumps({"phases": transport, "exchange_ms": t_x, "local_ms": t_l, "remote_ms": t_r,
                                   "exchange_gbs_recv": max(int(s[0]) for s in allstats) * a.F * 4 / t_x / 1e6}), flush=True)
-        if a.cross_check and world > 1 and transport == "p2p":
+        if a.cross_check and world > 1 and transport in ("p2p", "ce"):
             ref_op = PartitionedSpmm(plan, a.F, dev, transport="nccl")
             Yr = ref_op.forward(X, overlap=False)
             torch.cuda.synchronize()
