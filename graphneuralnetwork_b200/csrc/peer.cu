@@ -170,31 +170,56 @@ __global__ void __launch_bounds__(kTmaWarps * 32) halo_push_tma_kernel(const Pus
     const int64_t r = row0 + lane;
     return r < a.seg_rows[slot] ? __ldg(a.send_rows + a.seg_begin[slot] + r) : -1;
   };
-  int32_t rid = load_id(w);
-  int stage = 0;
-  uint32_t parity = 0;
-  for (int64_t c = w; c < n_chunks; c += nw) {
-    const int32_t rid_next = load_id(c + nw);  // ids of the next chunk while this one moves
+  // gathers of chunk c into ring stage `stg` (ids already in `rid_c`)
+  auto issue = [&](int64_t c, int32_t rid_c, int stg) {
     int slot;
     int64_t row0;
     locate(c, slot, row0);
     const int64_t left = a.seg_rows[slot] - row0;
     const int rows = (int)(left < 32 ? left : 32);
-    // the stage is reused every kTmaStages chunks: its previous bulk store must have read it
-    if (lane == 0) bulk_wait_group_read<kTmaStages - 1>();
-    __syncwarp();
-    unsigned char* st = ring + (size_t)stage * stage_bytes;
-    if (lane == 0) mbar_arrive_expect_tx(full + stage, (uint32_t)rows * (uint32_t)a.row_bytes);
+    if (lane == 0) mbar_arrive_expect_tx(full + stg, (uint32_t)rows * (uint32_t)a.row_bytes);
     __syncwarp();
     if (lane < rows)
-      bulk_g2s(st + (size_t)lane * a.row_bytes, a.X + (int64_t)rid * a.ldx, (uint32_t)a.row_bytes, full + stage);
+      bulk_g2s(ring + (size_t)stg * stage_bytes + (size_t)lane * a.row_bytes, a.X + (int64_t)rid_c * a.ldx,
+               (uint32_t)a.row_bytes, full + stg);
+  };
+  // Software pipeline: the gathers of the next kTmaStages-1 chunks are in flight while chunk k is stored.
+  constexpr int P = kTmaStages - 1;
+  int32_t rid_ahead = load_id(w);
+  int fill_stage = 0;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int64_t c = w + (int64_t)k * nw;
+    if (c < n_chunks) issue(c, rid_ahead, fill_stage);
+    rid_ahead = load_id(c + nw);
+    fill_stage = (fill_stage + 1 == kTmaStages) ? 0 : fill_stage + 1;
+  }
+  // here: rid_ahead = ids of chunk w + P*nw, fill_stage = P % kTmaStages
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t c = w; c < n_chunks; c += nw) {
+    int slot;
+    int64_t row0;
+    locate(c, slot, row0);
+    const int64_t left = a.seg_rows[slot] - row0;
+    const int rows = (int)(left < 32 ? left : 32);
     mbar_wait(full + stage, parity);
     if (lane == 0) {
       fence_proxy_async_smem();
-      bulk_s2g(reinterpret_cast<unsigned char*>(a.dst[slot]) + row0 * a.row_bytes, st, (uint32_t)rows * (uint32_t)a.row_bytes);
+      bulk_s2g(reinterpret_cast<unsigned char*>(a.dst[slot]) + row0 * a.row_bytes, ring + (size_t)stage * stage_bytes,
+               (uint32_t)rows * (uint32_t)a.row_bytes);
       bulk_commit_group();
     }
-    rid = rid_next;
+    // refill the stage chunk c - nw was stored from: that store must have read it (at most the store just
+    // committed may still be reading)
+    const int64_t cf = c + (int64_t)P * nw;
+    if (cf < n_chunks) {
+      if (lane == 0) bulk_wait_group_read<1>();
+      __syncwarp();
+      issue(cf, rid_ahead, fill_stage);
+    }
+    rid_ahead = load_id(cf + nw);
+    fill_stage = (fill_stage + 1 == kTmaStages) ? 0 : fill_stage + 1;
     if (++stage == kTmaStages) {
       stage = 0;
       parity ^= 1u;
