@@ -149,6 +149,24 @@ SAGE_WORKLOAD = ("sage_reddit: GraphSAGE_Pytorch mean aggregator, fanout (25,10)
                  "232,965 x 602 fp32 (BASELINE.json configs[2])")
 
 
+def sage_config(world):
+    """`config` of the JSON line — identical in the b200 and the reference arm."""
+    return {"workload": SAGE_WORKLOAD, "edges_per_step": SAGE_EDGES,
+            "parallelism": f"replicas x{world} (independent minibatches per rank, no collective)",
+            "l2_policy": "L2 flushed between timed iterations; inputs larger than L2"}
+
+
+def measured_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed ncu
+    capture of THIS round's kernel (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the raw
+    ncu CSV beside it); None when no capture is committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel_key]
+        return float(t["dram_bytes"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 def sage_algorithmic_bytes(n_src, fanout, F, s=4):
     return n_src * fanout * (4 + F * s) + n_src * F * s  # SURVEY.md §8d
 
@@ -307,12 +325,11 @@ def run_sage_b200(args, rank, world, dev):
         "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": SAGE_WORKLOAD,
-                   "edges_per_step": SAGE_EDGES, "launches_per_step": 2, "minibatch_pool": pool,
+        "config": sage_config(world),
+        "timing": {"launches_per_step": 2, "minibatch_pool": pool,
                    "l2_policy": "L2 flushed between timed iterations (256 MB written before every step, outside "
                                 "the per-step CUDA-event brackets that ms_per_step sums); inputs are also larger "
-                                "than L2: 561 MB table, ~374 MB distinct rows per step, 8 distinct minibatches cycled",
-                   "parallelism": f"replicas x{world} (independent minibatches per rank, no collective)"},
+                                "than L2: 561 MB table, ~374 MB distinct rows per step, 8 distinct minibatches cycled"},
         "hbm_gbs_step": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
         "wall_ms_per_step_incl_flush": wall_ms_incl_flush / args.steps,
         "warm_l2": {"value": world * args.steps * SAGE_EDGES / (warm_ms_total * 1e-3), "unit": "edges/s",
@@ -326,9 +343,8 @@ def run_sage_b200(args, rank, world, dev):
                                  "note": "same launches back to back without the flush: ~1/5 of the table is still "
                                          "in L2 from the previous minibatch, so the no-reuse byte model overcounts "
                                          "DRAM traffic there and no HBM fraction is claimed for it"},
-                     # dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture (profiles/README.md):
-                     # hop-2 559.3 + 56.6 MB, hop-1 61.1 + 1.1 MB (captured as separate launches of this kernel)
-                     "traffic": 678.0e6},
+                     "traffic": measured_traffic("sage_multi")[0],
+                     "traffic_source": measured_traffic("sage_multi")[1]},
         "e2e": {"value": world * args.steps * SAGE_EDGES / (e2e_ms * 1e-3), "unit": "edges/s",
                 "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "graphneuralnetwork_b200.layers.CapturedGraphSage(GraphSage.forward_sampled).submit/collect: "
@@ -366,7 +382,7 @@ def sage_cpu_setup():
     return table, params
 
 
-def run_sage_cpu(steps):
+def run_sage_cpu(steps, warmup=1):
     """The reference's CPU arithmetic for one step (oracle port of GraphSAGE_Pytorch):
     feature gather (data_utils.py:64, vectorised) + GraphSage.forward (GraphSage.py:18-30)."""
     from oracle import sage as osage
@@ -379,10 +395,11 @@ def run_sage_cpu(steps):
         with torch.no_grad():
             return osage.graphsage_forward(feats, params, list(SAGE["fanout"]))
 
-    step(0)
+    for i in range(max(warmup, 1)):
+        step(i)
     t0 = time.perf_counter()
     for i in range(steps):
-        step(i)
+        step(warmup + i)
     dt = time.perf_counter() - t0
     return steps * SAGE_EDGES / dt, dt / steps * 1e3
 
@@ -574,6 +591,7 @@ def run_other_configs_cpu():
 # configs[4]: papers100M-shaped SpMM, 1-D row partition + NVLink halo exchange
 # ------------------------------------------------------------------------------------------
 PAPERS = dict(n=111_059_956, deg=13.55, F=128)
+PART_WAVES = 4  # row chunks / exchange waves of the partitioned SpMM (partition.py)
 GRAPHS = {
     "random": dict(p_local=0.0, window=0, scatter=True,
                    note="power-law, hub-skewed targets spread over the id range, NO locality: the worst case for "
@@ -584,7 +602,10 @@ GRAPHS = {
 }
 
 
-def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("locality", "random")):
+def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("random", "locality")):
+    """configs[4]: Y = A.X, papers100M-shaped, F=128 fp32; total work fixed (strong scaling).  X is a hash of the
+    GLOBAL row id, so every rank recomputes sampled rows of its Y block in float64 (no communication) and the
+    leg FAILS (ok: false, ms withheld from `strong_scaling`) above 1e-5 relative."""
     from graphneuralnetwork_b200 import _lib, synthetic as S
     from graphneuralnetwork_b200.graph import _p, _stream_ptr
     from graphneuralnetwork_b200.partition import PartitionedSpmm, balanced_bounds, build_halo_plan
@@ -593,6 +614,13 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("locality", "random"
     peak, _ = hbm_peak()
     n, deg, F = PAPERS["n"], PAPERS["deg"], PAPERS["F"]
     out = {}
+
+    def rmax(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
     for gname in graphs:
         gcfg = GRAPHS[gname]
         deg_all = torch.empty(n, dtype=torch.int64, device=dev)
@@ -606,12 +634,13 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("locality", "random"
         csr = S.powerlaw_csr(hi - lo, deg, n_cols=n, row_offset=lo, seed=0, device=dev, deg_all=deg_all,
                              p_local=gcfg["p_local"], window=gcfg["window"], scatter_hubs=gcfg["scatter"])
         del deg_all
-        plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world)
+        rows = S.spmm_check_rows(csr, 4096, 17 + rank)
+        ref_rows = S.spmm_sampled_reference(csr, rows, F)
+        plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world, waves=PART_WAVES, F=F)
         del csr
         torch.cuda.empty_cache()
         op = PartitionedSpmm(plan, F, dev, transport="p2p")
-        gen = torch.Generator(device=dev).manual_seed(1 + rank)
-        X = torch.randn(plan.n_local, F, device=dev, generator=gen)
+        X = S.hashed_feature_block(lo, hi, F, dev)
         Y = torch.empty(plan.n_local, F, device=dev)
         for _ in range(3):
             op.forward(X, out=Y)
@@ -624,16 +653,24 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("locality", "random"
             op.forward(X, out=Y)
         t1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([t0.elapsed_time(t1) / steps, float(plan.n_halo)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms, halo_max = ms.tolist()
+        op.check_status()
+        diff = (Y[rows].double() - ref_rows).abs()
+        err_max = float(diff.max().item()) / max(float(ref_rows.abs().max().item()), 1e-30)
+        # element-wise criterion beside the max-norm one: |a-b| <= atol + rtol*|b| with atol tied to the row scale
+        elem_bad = int((diff > 1e-6 * ref_rows.abs().amax(dim=1, keepdim=True) + 1e-5 * ref_rows.abs()).sum().item())
+        ms, halo_max, err, bad = rmax([t0.elapsed_time(t1) / steps, float(plan.n_halo), err_max, float(elem_bad)])
         B = nnz_total * 8 + nnz_total * F * 4 + n * F * 4 + (n + 1) * 8
+        ok = bool(err < 1e-5 and bad == 0)
         res = {"graph": gcfg["note"], "n": n, "nnz": nnz_total, "F": F, "world": world, "ms": ms,
-               "edges_per_s": nnz_total / ms * 1e3, "scaling": "strong",
+               "edges_per_s": nnz_total / ms * 1e3, "scaling": "strong", "ok": ok,
+               "check": {"what": "4096+8 sampled rows per rank of Y recomputed in float64 from the hashed X (global ids), "
+                                 "max over ranks", "max_rel_err": err, "elementwise_violations": int(bad), "tol": 1e-5},
                "halo_rows_max": int(halo_max), "halo_gb_received_max": halo_max * F * 4 / 1e9,
-               "transport": "fused NVLink P2P push (gnn_halo_push_f32) overlapped with local-column SpMM"
-               if world > 1 else "none (single GPU)"}
+               "schedule": {"waves": plan.waves, "two_pass_chunks": plan.two_pass_chunks,
+                            "model_ms": {k: round(v, 2) for k, v in plan.model.items()
+                                         if k.startswith("c0=") or k == "exchange_ms"}} if world > 1 else None,
+               "transport": "gnn_halo_push (TMA mover, one warp per SM) + per-wave arrival flags, overlapped with the "
+                            "local-column SpMM" if world > 1 else "none (single GPU)"}
         if world == 1:
             res["roofline"] = {"bound": "hbm", "achieved": B / ms / 1e6, "peak": peak, "unit": "GB/s",
                                "frac": B / ms / 1e6 / peak, "algorithmic_bytes": B,
@@ -642,8 +679,21 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("locality", "random"
             res["nvlink_floor_ms"] = halo_max * F * 4 / (NVLINK_GBS * 1e6)
         out[gname] = res
         op.close()
-        del op, X, Y, plan
+        del op, X, Y, plan, ref_rows
         torch.cuda.empty_cache()
+    return out
+
+
+def strong_scaling_summary(part):
+    """Compact top-level key: one short entry per graph (ms withheld when the correctness check failed)."""
+    if not isinstance(part, dict) or "error" in part:
+        return {"error": (part or {}).get("error", "not run")}
+    out = {"workload": "papers100M-shaped SpMM Y=A.X, 111,059,956 nodes, F=128 fp32, 1-D row partition (BASELINE configs[4])",
+           "headline_graph": "random (plain power-law, no locality: SURVEY 8d row 5)"}
+    for name, r in part.items():
+        out[name] = {"world": r["world"], "ms": r["ms"] if r["ok"] else None, "ok": r["ok"],
+                     "max_rel_err": r["check"]["max_rel_err"], "halo_gb": round(r["halo_gb_received_max"], 2),
+                     "nnz": r["nnz"]}
     return out
 
 
@@ -665,16 +715,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 20))  # bounded sample: whole minibatches, ~0.1-0.3 s each on the host
-        v, ms = run_sage_cpu(steps)
+        # every host thread the box has (torchrun exports OMP_NUM_THREADS=1 to its ranks: undo that here)
+        torch.set_num_threads(cores)
+        steps = args.steps  # a step is one whole minibatch (a bounded sample of the workload, ~60 ms on 16 threads)
+        v, ms = run_sage_cpu(steps, args.warmup)
         line = {"impl": "reference", "metric": "aggregated_edges_per_sec", "value": v, "unit": "edges/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": SAGE_WORKLOAD, "edges_per_step": SAGE_EDGES},
+                "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": sage_config(args.gpus),
                 "cpu_baseline": {"value": v, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": f"{steps} full minibatches: torch-CPU feature gather of the 3 id blocks + "
-                                           "GraphSage forward (oracle/sage.py restating GraphSAGE_Pytorch); the Python "
-                                           "reference itself cannot travel to the GPU box"},
+                                 "sample": f"{steps} full minibatches on rank 0's host cores (one replica, whatever N): "
+                                           "torch-CPU feature gather of the 3 id blocks + GraphSage forward "
+                                           "(oracle/sage.py restating GraphSAGE_Pytorch)"},
                 "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "host_cores": cores}
         if not args.skip_extra:
@@ -696,9 +748,14 @@ def main():
     res = run_sage_b200(args, rank, world, dev)
     if not args.skip_extra:
         try:
-            res["partitioned_spmm"] = run_partitioned_spmm(rank, world, dev)
+            part = run_partitioned_spmm(rank, world, dev)
         except Exception as e:
-            res["partitioned_spmm"] = {"error": repr(e), "trace": traceback.format_exc()[-600:]}
+            part = {"error": repr(e), "trace": traceback.format_exc()[-600:]}
+        # compact summary FIRST (right after the contract keys), details at the end of the line
+        head = {k: res.pop(k) for k in list(res) if k in ("metric", "value", "unit", "n_gpus", "steps", "warmup",
+                                                           "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                                                           "dtype", "data", "config")}
+        res = {**head, "strong_scaling": strong_scaling_summary(part), **res, "partitioned_spmm": part}
     if rank == 0:
         if world == 1 and not args.skip_extra:
             try:

@@ -63,8 +63,28 @@ SIGNATURES = {
     "gnn_peer_close": (cint, [ptr]),
     "gnn_peer_free": (cint, [ptr]),
     "gnn_peer_copy_async": (cint, [ptr, ptr, size_t, ptr]),
-    "gnn_halo_push_f32": (cint, [ptr, i64, i32, ptr, ptr, ptr, ptr, i64, i32, i32, ptr]),
+    "gnn_halo_push": (cint, [ptr, i64, i32, i32, ptr, ptr, ptr, ptr, ptr, i64, i32, ptr, ptr]),
+    "gnn_peer_signal": (cint, [ptr, i32, i32, i32, C.c_uint32, ptr]),
+    "gnn_peer_wait": (cint, [ptr, i32, i32, C.c_uint32, ptr, i64, ptr]),
+    "gnn_spmm_csr_ex_f32": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr, ptr]),
+    "gnn_spmm_csr_ex_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr, ptr]),
 }
+
+
+
+class SpmmOpts(C.Structure):
+    """gnn_spmm_opts of include/gnn_b200.h (field order and types must match)."""
+    _fields_ = [("struct_size", i32), ("accumulate", i32), ("accumulate_prefix", i64), ("rows_per_team", i32),
+                ("relu", i32), ("bias", ptr), ("row_map", ptr), ("X2", ptr), ("ldx2", i64), ("split", i64),
+                ("long_rows", ptr), ("n_long", i64), ("long_threshold", i64), ("chunk_off", ptr), ("n_chunks", i64),
+                ("chunk_edges", i32), ("exclusion_smem_bytes", i32), ("workspace", ptr), ("workspace_bytes", size_t)]
+
+
+class HaloOpts(C.Structure):
+    """gnn_halo_opts of include/gnn_b200.h."""
+    _fields_ = [("struct_size", i32), ("mover", i32), ("ctas", i32), ("warps_per_cta", i32),
+                ("claim_smem_bytes", i32), ("first_peer", i32)]
+
 
 GNN_OK = 0
 REDUCE = {"mean": 0, "sum": 1, "max": 2}

@@ -48,13 +48,6 @@ static std::map<std::string, int>& tune_map() {
       {"gat.stage_edges", 128},  // logits staged per warp pass
       {"gat.coop_min_avg_deg", 256},  // nnz/n at which every row gets a whole CTA
       {"gat.long_row", 1024},        // rows above this get a CTA in the otherwise warp-per-row schedule
-      {"halo.ctas_per_sm", 1},
-      {"halo.tma", 0},                 // 1: experimental TMA mover (bulk gather -> one bulk store per 32 rows)
-      {"halo.dedicated_sms", 0},       // >0: the push runs on this many SMs of its own (see peer.cu)
-      {"halo.exclusion_smem_kb", 200}, // shared memory a dedicated push CTA claims to keep the SpMM off its SM
-      {"spmm.exclusion_smem_kb", 0},   // dynamic shared memory per SpMM CTA while a dedicated push is in flight
-      {"halo.schedule", 0},      // 0 rotated segments, 1 warps interleaved over peers
-      {"halo.unroll", 4},        // rows in flight per warp of the push kernel   // footprint of the NVLink push kernel (the rest of the SM runs the SpMM)
   };
   return m;
 }

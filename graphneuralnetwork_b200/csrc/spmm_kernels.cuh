@@ -34,7 +34,21 @@ struct SpmmArgs {
   // fused epilogue of the GCN layer (GCN/GCN.py:44-45 `output + self.bias`, GCN.py:12 nn.ReLU):
   const float* bias;      // nullable, [F] fp32, added to every row
   int32_t relu;           // 1: max(., 0) after the bias
+  // ---- row-subset / two-table form (gnn_spmm_csr_ex_*; the partitioned SpMM's wave consumers) ----
+  const int32_t* row_map;  // nullable: the CSR is COMPACT (n_rows selected rows); row r writes Y row row_map[r]
+  int64_t acc_prefix;      // compact rows [0, acc_prefix) accumulate into Y even when accumulate == 0
+  const T* X2;             // SPLIT kernels: a column id c >= split reads row (c - split) of X2 (the halo buffer)
+  int64_t ldx2;
+  int32_t split;
+  int32_t excl_smem;       // host only: token dynamic shared memory per CTA (keeps CTAs off SMs a mover filled)
 };
+
+// source row of column id c (SPLIT: two tables, [0, split) -> X, [split, ...) -> X2)
+template <typename T, bool SPLIT>
+__device__ __forceinline__ const T* spmm_src_row(const SpmmArgs<T>& a, int32_t c) {
+  if (SPLIT) return (c < a.split) ? a.X + (int64_t)c * a.ldx : a.X2 + (int64_t)(c - a.split) * a.ldx2;
+  return a.X + (int64_t)c * a.ldx;
+}
 
 // y = relu?(acc + bias[col0..]) for the VEC columns starting at col0 (columns >= F are padding)
 template <int VEC>
@@ -60,7 +74,7 @@ constexpr int kSpmmThreads = 256;
 // kernel is latency-bound and the third CTA is worth 4-11 % (F=602 fp32 34.1 -> 30.6 ms, bf16 23.6 ->
 // 21.7 ms; profiles/r01s2_kbench_spmm_reddit_ctas3_ab.jsonl).  "spmm.ctas3" = 0 selects the unconstrained
 // instantiation (100-140 registers, 2 CTAs/SM).
-template <typename T, int VEC, int GROUP, int CHUNKS, int U, bool EPI, int MINB = ((CHUNKS == 1) ? 4 : 1)>
+template <typename T, int VEC, int GROUP, int CHUNKS, int U, bool EPI, int MINB = ((CHUNKS == 1) ? 4 : 1), bool SPLIT = false>
 __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_rbs_kernel(const SpmmArgs<T> a) {
   const int lane = threadIdx.x & 31;
   const int gl = threadIdx.x % GROUP;
@@ -87,12 +101,14 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_rbs_kernel(const Spmm
     for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
 
   auto flush = [&](int r) {
-    T* yr = a.Y + (r0 + r) * a.ldy;
+    const int64_t orow = a.row_map ? (int64_t)__ldg(a.row_map + r0 + r) : (r0 + r);
+    T* yr = a.Y + orow * a.ldy;
+    const bool accum = a.accumulate || (r0 + r) < a.acc_prefix;
 #pragma unroll
     for (int ch = 0; ch < CHUNKS; ++ch) {
       const int col0 = (gl + ch * GROUP) * VEC;
       if (col0 < a.F) {
-        if (a.accumulate) {
+        if (accum) {
           float prev[VEC];
           VecIO<T, VEC>::load(yr + col0, prev);
 #pragma unroll
@@ -136,7 +152,7 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_rbs_kernel(const Spmm
           const int32_t cj = __shfl_sync(gmask, c, jj, GROUP);
           vv[u] = __shfl_sync(gmask, v, jj, GROUP);
           const bool ok = jj < cnt;
-          const T* xr = a.X + (int64_t)(ok ? cj : 0) * a.ldx;
+          const T* xr = spmm_src_row<T, SPLIT>(a, ok ? cj : 0);
 #pragma unroll
           for (int ch = 0; ch < CHUNKS; ++ch) {
             const int col0 = (gl + ch * GROUP) * VEC;
@@ -192,7 +208,7 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_rbs_kernel(const Spmm
           const float vj = __shfl_sync(gmask, v, jj, GROUP);
           const bool ok = jj < cnt;
           vv[u] = ok ? vj : 0.f;
-          const T* xr = a.X + (int64_t)(ok ? cj : 0) * a.ldx;
+          const T* xr = spmm_src_row<T, SPLIT>(a, ok ? cj : 0);
 #pragma unroll
           for (int ch = 0; ch < CHUNKS; ++ch) {
             const int col0 = (gl + ch * GROUP) * VEC;
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_rbs_kernel(const Spmm
 // ---- long rows --------------------------------------------------------------------------
 constexpr int kLongChunkWarps = 8;
 
-template <typename T, int VEC, int GROUP, int CHUNKS>
+template <typename T, int VEC, int GROUP, int CHUNKS, bool SPLIT = false>
 __global__ void __launch_bounds__(kLongChunkWarps * 32)
     spmm_long_chunk_kernel(const SpmmArgs<T> a, const int64_t* __restrict__ long_rows,
                            const int64_t* __restrict__ chunk_off, int64_t n_long, int chunk_edges,
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(kLongChunkWarps * 32)
         const float vj = __shfl_sync(0xffffffffu, v, jj & 31);
         const bool ok = jj < cnt;
         vv[u] = ok ? vj : 0.f;
-        const T* xr = a.X + (int64_t)(ok ? cj : 0) * a.ldx;
+        const T* xr = spmm_src_row<T, SPLIT>(a, ok ? cj : 0);
 #pragma unroll
         for (int ch = 0; ch < CHUNKS; ++ch) {
           const int col0 = (gl + ch * GROUP) * VEC;
@@ -313,9 +329,12 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     spmm_long_finalize_kernel(const int64_t* __restrict__ long_rows, const int64_t* __restrict__ chunk_off,
                               const float* __restrict__ partial, int ldp, int col_base, int Ftile, T* __restrict__ Y,
-                              int64_t ldy, int accumulate, const float* __restrict__ bias, int relu) {
+                              int64_t ldy, int accumulate, const float* __restrict__ bias, int relu,
+                              const int32_t* __restrict__ row_map, int64_t acc_prefix) {
   const int64_t r = blockIdx.x;
-  const int64_t row = __ldg(long_rows + r);
+  const int64_t crow = __ldg(long_rows + r);  // (compact) CSR row
+  const int64_t row = row_map ? (int64_t)__ldg(row_map + crow) : crow;
+  accumulate = accumulate || crow < acc_prefix;
   const int64_t c0 = __ldg(chunk_off + r), c1 = __ldg(chunk_off + r + 1);
   for (int f = threadIdx.x; f < Ftile; f += blockDim.x) {
     float sum = 0.f;
@@ -334,11 +353,13 @@ __global__ void __launch_bounds__(256)
 
 // ---- host-side dispatch ------------------------------------------------------------------
 template <typename T>
-inline int spmm_pick_vec(const void* X, int64_t ldx, const void* Y, int64_t ldy, int F) {
+inline int spmm_pick_vec(const void* X, int64_t ldx, const void* Y, int64_t ldy, int F, const void* X2 = nullptr,
+                         int64_t ldx2 = 0) {
   for (int v = 16 / (int)sizeof(T); v > 1; v >>= 1) {
     const size_t bytes = (size_t)v * sizeof(T);
     const int64_t fpad = ((int64_t)F + v - 1) / v * v;
-    if (aligned_to(X, bytes) && aligned_to(Y, bytes) && ldx % v == 0 && ldy % v == 0 && fpad <= ldx && fpad <= ldy)
+    if (aligned_to(X, bytes) && aligned_to(Y, bytes) && ldx % v == 0 && ldy % v == 0 && fpad <= ldx && fpad <= ldy &&
+        (!X2 || (aligned_to(X2, bytes) && ldx2 % v == 0 && fpad <= ldx2)))
       return v;
   }
   return 1;
@@ -356,8 +377,12 @@ inline void spmm_rbs_launch(const SpmmArgs<T>& a, cudaStream_t st) {
   // the bias/ReLU epilogue is a separate instantiation: the plain one keeps its register budget
   // token dynamic shared memory (<= 48 KB, unused by the kernel) keeps these CTAs off the SMs a
   // dedicated halo push has claimed (peer.cu); 0 outside the partitioned SpMM's local pass
-  const size_t sm = (size_t)tuning("spmm.exclusion_smem_kb", 0) * 1024;
-  if (a.bias || a.relu) {
+  const size_t sm = (size_t)(a.excl_smem > 0 ? a.excl_smem : 0);
+  constexpr int MINB_DEF = (CHUNKS == 1) ? 4 : ((CHUNKS <= 5) ? 3 : 1);
+  if (a.X2) {
+    // two-table form (never combined with the bias/ReLU epilogue: spmm_impl rejects that)
+    spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false, MINB_DEF, true><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
+  } else if (a.bias || a.relu) {
     spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, true><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
   } else if (CHUNKS >= 2 && CHUNKS <= 5 && tuning("spmm.ctas3", 1)) {
     spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false, (CHUNKS >= 2 && CHUNKS <= 5) ? 3 : 1>
@@ -373,6 +398,7 @@ inline int spmm_main_vec(const SpmmArgs<T>& a0, cudaStream_t st) {
   for (int c0 = 0; c0 < a0.F; c0 += tile_cols) {
     SpmmArgs<T> a = a0;
     a.X = a0.X + c0;
+    a.X2 = a0.X2 ? a0.X2 + c0 : nullptr;
     a.Y = a0.Y + c0;
     a.bias = a0.bias ? a0.bias + c0 : nullptr;
     a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
@@ -395,7 +421,7 @@ inline int spmm_main_vec(const SpmmArgs<T>& a0, cudaStream_t st) {
 template <typename T>
 inline int spmm_main(const SpmmArgs<T>& a, cudaStream_t st) {
   GNN_REQUIRE(a.n_rows < (1LL << 33), GNN_ERR_UNSUPPORTED, "too many rows");  // grid <= n_rows / 8
-  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F);
+  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F, a.X2, a.ldx2);
   if (sizeof(T) == 2 && vec == 8) return spmm_main_vec<T, (sizeof(T) == 2 ? 8 : 4)>(a, st);
   if (vec >= 4) return spmm_main_vec<T, 4>(a, st);
   if (vec == 2) return spmm_main_vec<T, 2>(a, st);
@@ -410,12 +436,20 @@ inline int spmm_long_vec(const SpmmArgs<T>& a0, const int64_t* long_rows, int64_
   for (int c0 = 0; c0 < a0.F; c0 += tile_cols) {
     SpmmArgs<T> a = a0;
     a.X = a0.X + c0;
+    a.X2 = a0.X2 ? a0.X2 + c0 : nullptr;
     a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
     const int nvec = (a.F + VEC - 1) / VEC;
     const unsigned grid = (unsigned)n_chunks;
     const int thr = kLongChunkWarps * 32;
-#define GNN_LONG(G, C) \
-  spmm_long_chunk_kernel<T, VEC, G, C><<<grid, thr, 0, st>>>(a, long_rows, chunk_off, n_long, chunk_edges, partial, ldp)
+#define GNN_LONG(G, C)                                                                                               \
+  do {                                                                                                               \
+    if (a.X2)                                                                                                        \
+      spmm_long_chunk_kernel<T, VEC, G, C, true><<<grid, thr, 0, st>>>(a, long_rows, chunk_off, n_long, chunk_edges, \
+                                                                       partial, ldp);                                \
+    else                                                                                                             \
+      spmm_long_chunk_kernel<T, VEC, G, C><<<grid, thr, 0, st>>>(a, long_rows, chunk_off, n_long, chunk_edges,       \
+                                                                 partial, ldp);                                      \
+  } while (0)
     if (nvec <= 4) GNN_LONG(4, 1);
     else if (nvec <= 8) GNN_LONG(8, 1);
     else if (nvec <= 16) GNN_LONG(16, 1);
@@ -425,7 +459,8 @@ inline int spmm_long_vec(const SpmmArgs<T>& a0, const int64_t* long_rows, int64_
 #undef GNN_LONG
     GNN_LAUNCH_CHECK();
     spmm_long_finalize_kernel<T><<<(unsigned)n_long, 256, 0, st>>>(long_rows, chunk_off, partial, ldp, c0, a.F, a0.Y,
-                                                                   a0.ldy, a0.accumulate, a0.bias, a0.relu);
+                                                                   a0.ldy, a0.accumulate, a0.bias, a0.relu,
+                                                                   a0.row_map, a0.acc_prefix);
     GNN_LAUNCH_CHECK();
   }
   return GNN_OK;
@@ -434,7 +469,7 @@ inline int spmm_long_vec(const SpmmArgs<T>& a0, const int64_t* long_rows, int64_
 template <typename T>
 inline int spmm_long(const SpmmArgs<T>& a, const int64_t* long_rows, int64_t n_long, const int64_t* chunk_off,
                      int64_t n_chunks, int chunk_edges, float* partial, cudaStream_t st) {
-  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F);
+  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F, a.X2, a.ldx2);
   if (sizeof(T) == 2 && vec == 8)
     return spmm_long_vec<T, (sizeof(T) == 2 ? 8 : 4)>(a, long_rows, n_long, chunk_off, n_chunks, chunk_edges, partial, st);
   if (vec >= 4) return spmm_long_vec<T, 4>(a, long_rows, n_long, chunk_off, n_chunks, chunk_edges, partial, st);

@@ -76,6 +76,51 @@ def spmm_raw(g: CSRGraph, X: torch.Tensor, out: Optional[torch.Tensor] = None, p
     return out
 
 
+def spmm_ex(g: CSRGraph, X: torch.Tensor, out: torch.Tensor, row_map: Optional[torch.Tensor] = None,
+            accumulate: bool = False, accumulate_prefix: int = 0, X2: Optional[torch.Tensor] = None, split: int = 0,
+            exclusion_smem: int = 0) -> torch.Tensor:
+    """Row-subset / two-table SpMM (gnn_spmm_csr_ex_*, no autograd): `g` is a CSR that is COMPACT over the
+    selected rows; compact row r writes `out[row_map[r]]` (row_map None: out[r]); rows below
+    `accumulate_prefix` (or all, with accumulate) add into `out`; column ids >= `split` read row
+    (c - split) of X2.  The consumers of the partitioned SpMM's waves (partition.py)."""
+    import ctypes as C
+    _require_cuda(X, out, row_map, X2)
+    lib = _lib.load()
+    X = _rowmajor(X)
+    if X.dtype not in (torch.float32, torch.bfloat16) or out.dtype != X.dtype:
+        raise _lib.GnnError(f"spmm_ex: unsupported dtypes {X.dtype} / {out.dtype}")
+    F = X.shape[1]
+    n_src = X.shape[0] + (X2.shape[0] if X2 is not None else 0)
+    if X2 is None and X.shape[0] != g.n_cols:
+        raise _lib.GnnError(f"spmm_ex: X has {X.shape[0]} rows, adjacency has {g.n_cols} columns")
+    if X2 is not None and (X2.dtype != X.dtype or X2.shape[1] != F or split != X.shape[0] or n_src < g.n_cols):
+        raise _lib.GnnError("spmm_ex: X2 must match X in dtype and width, split must equal X.shape[0] and the "
+                            "two tables must cover the adjacency's columns")
+    if row_map is not None and (row_map.dtype != torch.int32 or row_map.numel() != g.n_rows):
+        raise _lib.GnnError("spmm_ex: row_map must be int32 with one entry per compact row")
+    if out.stride(1) != 1 or out.shape[1] != F:
+        raise _lib.GnnError("spmm_ex: `out` must be [*, F] with unit column stride")
+    plan = g.long_row_plan()
+    lr, thr, chunk_off, n_chunks, chunk, ws = plan if plan is not None else (None, 0, None, 0, 0, None)
+    o = _lib.SpmmOpts()
+    o.struct_size = C.sizeof(_lib.SpmmOpts)
+    o.accumulate = 1 if accumulate else 0
+    o.accumulate_prefix = int(accumulate_prefix)
+    o.rows_per_team = g.rows_per_team()
+    o.row_map = _p(row_map)
+    if X2 is not None:
+        X2 = _rowmajor(X2)
+        o.X2, o.ldx2, o.split = _p(X2), _ld(X2), int(split)
+    o.long_rows, o.n_long, o.long_threshold = _p(lr), 0 if lr is None else lr.numel(), thr
+    o.chunk_off, o.n_chunks, o.chunk_edges = _p(chunk_off), n_chunks, chunk
+    o.exclusion_smem_bytes = int(exclusion_smem)
+    o.workspace, o.workspace_bytes = _p(ws), 0 if ws is None else ws.numel()
+    fn = lib.gnn_spmm_csr_ex_f32 if X.dtype == torch.float32 else lib.gnn_spmm_csr_ex_bf16
+    _lib.check(fn(_p(g.rowptr), _p(g.col), _p(g.val), _p(X), _p(out), g.n_rows, max(g.n_cols, n_src), F, _ld(X),
+                  _ld(out), C.byref(o), _stream_ptr()), "gnn_spmm_csr_ex")
+    return out
+
+
 class _SpmmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, g: CSRGraph):
@@ -461,9 +506,9 @@ class _GatFn(torch.autograd.Function):
                                              lrt.numel(), thr, _stream_ptr()),
                    "gnn_gat_fused_bwd_f32")
         if g.has_empty_rows():
-            # rows without edges output the mean of all Wh rows (GAT/models/layers.py:28-30)
-            deg = g.rowptr[1:] - g.rowptr[:-1]
-            d_Wh += d_out[deg == 0].sum(dim=0, keepdim=True) / n
+            # rows without edges output the mean of all Wh rows (GAT/models/layers.py:28-30).  Sync-free
+            # (no boolean-mask indexing): this runs inside CapturedTrainStep's CUDA-graph capture
+            d_Wh += (d_out * g.empty_row_mask().unsqueeze(1)).sum(dim=0, keepdim=True) / n
         return d_Wh, d_s, d_t, None, None, None, None, None, None
 
 

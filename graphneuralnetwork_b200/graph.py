@@ -156,6 +156,12 @@ class CSRGraph:
             self._zero_rows = bool((deg == 0).any().item()) if self.n_rows > 0 else False
         return self._zero_rows
 
+    def empty_row_mask(self) -> torch.Tensor:
+        """fp32 [n_rows] indicator of rows without edges (cached with the pattern)."""
+        if getattr(self, "_empty_mask", None) is None:
+            self._empty_mask = ((self.rowptr[1:] - self.rowptr[:-1]) == 0).to(torch.float32)
+        return self._empty_mask
+
     # -- builders --------------------------------------------------------------------
     @staticmethod
     def from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int,

@@ -20,15 +20,26 @@ _pattern_cache = {}
 
 
 def _coo_pattern(indices, shape):
-    """CSR pattern + COO->CSR permutation of an `indices [2, nnz]` tensor, built once per tensor."""
+    """CSR pattern + COO->CSR permutation of an `indices [2, nnz]` tensor, built once per tensor.
+
+    The reference rebuilds `edge = adj.nonzero().t()` on every forward (GAT/models/layers.py:98) and the
+    caching allocator hands the same block back, so (data_ptr, _version, shape) alone would match a
+    DIFFERENT graph of equal nnz: a hit also requires that the cached entry's tensor object is still
+    alive and is this very tensor (weakref identity, as graph._AdjCache does)."""
+    import weakref
     key = (indices.data_ptr(), indices._version, tuple(indices.shape), tuple(shape))
     hit = _pattern_cache.get(key)
-    if hit is None:
-        if len(_pattern_cache) >= 16:
-            _pattern_cache.pop(next(iter(_pattern_cache)))
-        hit = CSRGraph.from_coo(indices[0], indices[1], None, int(shape[0]), int(shape[1]), return_perm=True)
-        _pattern_cache[key] = hit
-    return hit
+    if hit is not None:
+        ref, value = hit
+        if ref() is indices:
+            return value
+    for k in [k for k, (r, _) in _pattern_cache.items() if r() is None]:  # evict entries of dead tensors
+        _pattern_cache.pop(k)
+    if len(_pattern_cache) >= 16:
+        _pattern_cache.pop(next(iter(_pattern_cache)))
+    value = CSRGraph.from_coo(indices[0], indices[1], None, int(shape[0]), int(shape[1]), return_perm=True)
+    _pattern_cache[key] = (weakref.ref(indices), value)
+    return value
 
 
 class SpecialSpmmFunction:

@@ -130,3 +130,47 @@ def powerlaw_csr(n_rows: int, mean_degree: float, *, n_cols: int | None = None, 
                                             _stream_ptr()), "gnn_synth_gcn_values")
     del deg
     return CSRGraph(rowptr, col, val, n_rows, n_cols)
+
+
+def hashed_features(rows: torch.Tensor, F: int, dtype=torch.float32, salt: int = 0) -> torch.Tensor:
+    """Feature rows that are a pure function of the GLOBAL row id: x[i, f] = g(i * F + f) in (-1, 1), exact
+    integer arithmetic (two rounds of a Lehmer generator), so any rank — and a float64 checker — can
+    recompute any row of X without communication (bench.py's partitioned-SpMM correctness check)."""
+    M = 2147483647
+    z = (rows.to(torch.int64).view(-1, 1) * F + torch.arange(F, dtype=torch.int64, device=rows.device) + salt) % M
+    z = (z * 48271 + 11) % M
+    z = (z * 69621 + 7) % M
+    return (z.to(torch.float64) * (2.0 / M) - 1.0).to(dtype)
+
+
+def hashed_feature_block(lo: int, hi: int, F: int, device, dtype=torch.float32, salt: int = 0,
+                         rows_per_pass: int = 1 << 21, out: torch.Tensor | None = None) -> torch.Tensor:
+    """hashed_features for the contiguous global rows [lo, hi), generated in passes (bounded scratch)."""
+    X = out if out is not None else torch.empty((hi - lo, F), dtype=dtype, device=device)
+    for a in range(lo, hi, rows_per_pass):
+        b = min(a + rows_per_pass, hi)
+        X[a - lo:b - lo] = hashed_features(torch.arange(a, b, dtype=torch.int64, device=device), F, dtype, salt)
+    return X
+
+
+def spmm_check_rows(csr: CSRGraph, n_samples: int, seed: int) -> torch.Tensor:
+    """Row sample for the float64 spot check: uniform rows plus the longest ones (chunked path)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    rows = torch.randint(0, csr.n_rows, (n_samples,), generator=g).to(csr.rowptr.device)
+    deg = csr.rowptr[1:] - csr.rowptr[:-1]
+    hubs = torch.topk(deg, min(8, csr.n_rows)).indices
+    return torch.unique(torch.cat([rows, hubs]))
+
+
+def spmm_sampled_reference(csr: CSRGraph, rows: torch.Tensor, F: int, dtype=torch.float32, salt: int = 0) -> torch.Tensor:
+    """float64 rows `rows` of Â·X where X = hashed_features of the GLOBAL column ids held in `csr.col`
+    (recomputed here, no communication) — torch float64 arithmetic in plain CSR order."""
+    from .partition import select_rows
+    rp, cc, vv = select_rows(csr.rowptr, csr.col, csr.val, rows)
+    src = hashed_features(cc.to(torch.int64), F, dtype, salt).double()
+    if vv is not None:
+        src *= vv.double().unsqueeze(1)
+    owner = torch.repeat_interleave(torch.arange(rows.numel(), device=rows.device), rp[1:] - rp[:-1])
+    ref = torch.zeros((rows.numel(), F), dtype=torch.float64, device=rows.device)
+    ref.index_add_(0, owner, src)
+    return ref

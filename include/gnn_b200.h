@@ -152,6 +152,46 @@ int gnn_spmm_csr_planned_bf16(const int64_t* rowptr, const int32_t* col, const f
                               const float* bias /*nullable [F], fp32*/, int32_t relu,
                               void* workspace, size_t workspace_bytes, gnn_stream_t stream);
 
+/* Extended form of the planned SpMM for ROW SUBSETS and TWO SOURCE TABLES — the consumers of the
+ * wave-pipelined halo exchange of the partitioned SpMM (reference seam GCN/GCN.py:43).
+ * The CSR passed in is compact over the selected rows (rowptr has n_rows+1 entries):
+ *   row_map (nullable, int32 [n_rows], ascending): compact row r writes Y row row_map[r];
+ *   accumulate_prefix: compact rows [0, accumulate_prefix) add into Y (their local-column part was
+ *     written by an earlier pass), the others overwrite — one launch serves both kinds of row;
+ *   X2/ldx2/split: a column id c >= split reads row (c - split) of X2 (the halo buffer) instead of X,
+ *     so rows that need local AND remote columns finish in ONE pass with no read-modify-write of Y;
+ *   exclusion_smem_bytes: token dynamic shared memory per CTA (<= 48 KB), for callers that keep this
+ *     kernel off SMs a shared-memory-filling mover kernel has claimed.  0 = none.
+ * Every per-call choice is an argument: no process-global state is consulted.
+ * struct_size = sizeof(gnn_spmm_opts) (ABI versioning); zero-initialise the rest. */
+typedef struct gnn_spmm_opts {
+  int32_t struct_size;
+  int32_t accumulate;
+  int64_t accumulate_prefix;
+  int32_t rows_per_team;
+  int32_t relu;
+  const float* bias;
+  const int32_t* row_map;
+  const void* X2;
+  int64_t ldx2;
+  int64_t split;
+  const int64_t* long_rows;
+  int64_t n_long;
+  int64_t long_threshold;
+  const int64_t* chunk_off;
+  int64_t n_chunks;
+  int32_t chunk_edges;
+  int32_t exclusion_smem_bytes;
+  void* workspace;
+  size_t workspace_bytes;
+} gnn_spmm_opts;
+int gnn_spmm_csr_ex_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                        const float* X, float* Y, int64_t n_rows, int64_t n_cols, int32_t F,
+                        int64_t ldx, int64_t ldy, const gnn_spmm_opts* opts, gnn_stream_t stream);
+int gnn_spmm_csr_ex_bf16(const int64_t* rowptr, const int32_t* col, const float* val,
+                         const void* X, void* Y, int64_t n_rows, int64_t n_cols, int32_t F,
+                         int64_t ldx, int64_t ldy, const gnn_spmm_opts* opts, gnn_stream_t stream);
+
 /* Edge-gradient SDDMM: out[e] = <A[row[e], 0:F], B[col[e], 0:F]> for e in [0, nnz).
  * The gradient of Y = S·B with respect to the VALUES of S is dY_i · B_j on the pattern of S:
  * GAT/models/layers.py:55-61 (SpecialSpmmFunction.backward) forms the dense N x N product
@@ -284,24 +324,56 @@ int gnn_synth_gcn_values(int64_t n_rows, int64_t row_offset, const int64_t* rowp
 
 /* ---- multi-GPU halo exchange over NVLink peer memory ------------ */
 /* Copy-engine transfer between two device allocations of this process' address space (a peer's
- * gnn_peer_open mapping included): cudaMemcpyAsync device-to-device on `stream`.  Used by the
- * experimental transport="ce" of the partitioned SpMM (pack locally, then one copy per peer). */
+ * gnn_peer_open mapping included): cudaMemcpyAsync device-to-device on `stream` (zero SMs).  Used for
+ * the contiguous segments of the partitioned backward's reverse halo exchange and by transport="ce". */
 int gnn_peer_copy_async(void* dst, const void* src, size_t bytes, gnn_stream_t stream);
 
-/* Peer buffers are plain cudaMalloc allocations exported with CUDA IPC, one process per
- * GPU.  gnn_halo_push copies, for every peer q, the rows send_rows[send_off[q]..send_off[q+1])
- * of the local X straight into peer q's halo buffer at row dst_off[q] with 128-bit
- * stores over NVLink — pack and transfer in one kernel, no staging buffer. */
+/* Peer buffers are plain cudaMalloc allocations (zero-initialised) exported with CUDA IPC, one
+ * process per GPU: gnn_peer_alloc on the owner, gnn_peer_open of the 64-byte handle on every peer. */
 int gnn_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64B_host);
 int gnn_peer_open(const void* ipc_handle_64B_host, void** dev_ptr);
 int gnn_peer_close(void* dev_ptr);
 int gnn_peer_free(void* dev_ptr);
-int gnn_halo_push_f32(const float* X, int64_t ldx, int32_t F,
-                      const int32_t* send_rows, const int64_t* send_off_host /*[n_peers+1]*/,
-                      float* const* peer_halo_host /*[n_peers] device ptrs*/, const int64_t* dst_off_host /*[n_peers]*/,
-                      int64_t ld_halo, int32_t n_peers,
-                      int32_t first_peer /*segment pushed first; (rank+1)%n_peers staggers the all-to-all*/,
-                      gnn_stream_t stream);
+
+/* Fused pack + transfer of halo rows.  For every peer q the rows
+ *   send_rows[seg_begin[q] + k], k in [0, seg_rows[q])      (send_rows == NULL: local rows seg_begin[q] + k)
+ * of the local X [*, ldx] (elem_size 4 = fp32, 2 = bf16 wire for the bf16 variant) are written to row
+ * dst_row[q] + k of peer q's buffer peer_dst[q] [*, ld_dst] over NVLink, segments served in rotated
+ * order starting at opts->first_peer.  A call moves ONE WAVE: the caller passes the sub-range of each
+ * peer segment that belongs to the wave and signals the peers afterwards (gnn_peer_signal).
+ * Every scheduling choice is an explicit argument (no process-global knobs):
+ *   mover          0 auto | 1 vector loads/stores | 2 TMA bulk copies (rows must be 16-byte multiples
+ *                  <= 16 KB and ld_dst == F; GNN_ERR_UNSUPPORTED otherwise)
+ *   ctas           CTAs launched (0 = one per SM)
+ *   warps_per_cta  0 = default (TMA: 1 — a 48 KB ring next to the SpMM CTAs of every SM; vector: 8)
+ *   claim_smem_bytes  vector mover only: dynamic shared memory each CTA claims so that a kernel asking
+ *                  for gnn_spmm_opts.exclusion_smem_bytes cannot share its SM (SM partition)
+ * opts == NULL selects the defaults.  struct_size = sizeof(gnn_halo_opts). */
+typedef struct gnn_halo_opts {
+  int32_t struct_size;
+  int32_t mover;
+  int32_t ctas;
+  int32_t warps_per_cta;
+  int32_t claim_smem_bytes;
+  int32_t first_peer;
+} gnn_halo_opts;
+int gnn_halo_push(const void* X, int64_t ldx, int32_t F, int32_t elem_size,
+                  const int32_t* send_rows /*nullable*/,
+                  const int64_t* seg_begin_host /*[n_peers]*/, const int64_t* seg_rows_host /*[n_peers]*/,
+                  void* const* peer_dst_host /*[n_peers] device ptrs*/, const int64_t* dst_row_host /*[n_peers]*/,
+                  int64_t ld_dst, int32_t n_peers, const gnn_halo_opts* opts, gnn_stream_t stream);
+
+/* Per-peer arrival flags: monotonic uint32 counters living in peer memory (one array of n_peers slots
+ * per rank, slot p written by rank p).  gnn_peer_signal stores `value` into slot my_slot of every
+ * peer's array (release, system scope) — stream-ordered behind the pushes it announces.
+ * gnn_peer_wait makes `stream` wait (a one-warp kernel polling with acquire loads) until every slot
+ * except skip_slot has reached `value`; after timeout_ms it gives up and writes 1 + the late slot to
+ * *status (nullable) instead of hanging the GPU.  These replace a collective barrier: the consumer of
+ * wave w waits only for wave w's flags. */
+int gnn_peer_signal(uint32_t* const* peer_flags_host /*[n_peers] device ptrs*/, int32_t n_peers, int32_t my_slot,
+                    int32_t skip_peer, uint32_t value, gnn_stream_t stream);
+int gnn_peer_wait(const uint32_t* flags, int32_t n_slots, int32_t skip_slot, uint32_t value,
+                  uint32_t* status /*nullable device word*/, int64_t timeout_ms, gnn_stream_t stream);
 
 #ifdef __cplusplus
 }

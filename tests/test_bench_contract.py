@@ -27,6 +27,22 @@ def test_reference_arm_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "minibatch" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # same `config` object as the B200 arm prints (the driver compares them key by key)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.sage_config(1)
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its ranks; the CPU arm must still use every core, honour
+    --steps/--warmup and report them (the N>=2 reference lines ran single-threaded)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--warmup", "3", "--skip-extra"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["steps"] == 2 and d["warmup"] == 3 and d["n_gpus"] == 2
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from graphneuralnetwork_b200.partition import balanced_bounds, build_halo_plan, split_columns
+from graphneuralnetwork_b200.partition import (balanced_bounds, build_halo_plan, choose_two_pass_chunks,
+                                               reference_step_cpu, select_rows, split_columns)
 
 
 def _free_port():
@@ -35,7 +36,7 @@ def _global_graph(n, seed):
     return rowptr, col, val, X
 
 
-def _worker(rank, world, port, n, seed, out_q):
+def _worker(rank, world, port, n, seed, waves, c0, out_q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -46,57 +47,135 @@ def _worker(rank, world, port, n, seed, out_q):
         rp = torch.from_numpy(rowptr[lo:hi + 1] - rowptr[lo])
         c = torch.from_numpy(col[rowptr[lo]:rowptr[hi]])
         v = torch.from_numpy(val[rowptr[lo]:rowptr[hi]])
-        plan = build_halo_plan(rp, c, v, bounds, rank, world)
+        plan = build_halo_plan(rp, c, v, bounds, rank, world, waves=waves, two_pass_chunks=c0, F=X.shape[1])
+        K = plan.waves
         # invariants of the plan
-        assert plan.n_local == hi - lo
+        assert plan.n_local == hi - lo and K == waves
         h = plan.halo_ids.numpy()
-        assert np.all(np.diff(h) > 0)                       # sorted, de-duplicated
+        assert len(np.unique(h)) == len(h)                  # de-duplicated
         assert not np.any((h >= lo) & (h < hi))             # never asks for its own rows
         assert sum(plan.recv_counts) == len(h) and plan.recv_counts[rank] == 0
         assert plan.send_counts[rank] == 0 and int(plan.send_rows.numel()) == sum(plan.send_counts)
         assert plan.rowptr_loc[-1] + plan.rowptr_rem[-1] == rp[-1]
-        # replay the exchange
+        # slot order: by owner, then wave, then id; wave = first row chunk that needs the row
+        owner = np.searchsorted(np.asarray(bounds[1:-1]), h, side="right")
+        off = np.concatenate([[0], np.cumsum(plan.recv_counts)])
+        for q in range(world):
+            assert np.all(owner[off[q]:off[q + 1]] == q)
+            seg = h[off[q]:off[q + 1]]
+            wc = np.concatenate([[0], np.cumsum(plan.recv_wave_counts[q])])
+            for w in range(K):
+                assert np.all(np.diff(seg[wc[w]:wc[w + 1]]) > 0)
+        rem_rows = np.repeat(np.arange(hi - lo), np.diff(plan.rowptr_rem.numpy()))
+        chunk_of_row = np.searchsorted(np.asarray(plan.chunk_bounds[1:-1]), np.arange(hi - lo), side="right")
+        first = np.full(len(h), K)
+        np.minimum.at(first, plan.col_rem.numpy(), chunk_of_row[rem_rows])
+        wave_of_slot = np.concatenate([np.repeat(np.arange(K), plan.recv_wave_counts[q]) for q in range(world)]) \
+            if len(h) else np.zeros(0, int)
+        assert np.array_equal(first, wave_of_slot)
+        # replay the exchange wave by wave, as the movers do: segment sub-ranges into the peers' halos
         Xl = torch.from_numpy(X[lo:hi])
-        send = Xl[plan.send_rows.long()]
-        halo = torch.empty((len(h), X.shape[1]))
-        dist.all_to_all_single(halo, send, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts)
+        halo = torch.full((len(h), X.shape[1]), float("nan"))
+        send_off = plan.send_off()
+        for w in range(K):
+            send_parts, recv_sizes = [], []
+            for p in range(world):
+                b = send_off[p] + sum(plan.send_wave_counts[p][:w])
+                send_parts.append(Xl[plan.send_rows[b:b + plan.send_wave_counts[p][w]].long()])
+            send = torch.cat(send_parts, 0)
+            recv_sizes = [plan.recv_wave_counts[q][w] for q in range(world)]
+            recv = torch.empty((sum(recv_sizes), X.shape[1]))
+            dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes,
+                                   input_split_sizes=[plan.send_wave_counts[p][w] for p in range(world)])
+            pos = 0
+            for q in range(world):
+                d = off[q] + sum(plan.recv_wave_counts[q][:w])
+                halo[d:d + recv_sizes[q]] = recv[pos:pos + recv_sizes[q]]
+                pos += recv_sizes[q]
+            # after wave w every mixed row of chunk w has what it reads
+            cons = plan.p2[w]
+            if cons is not None:
+                cols = cons.col.long()
+                rem = cols if cons.mode == "remote" else cols[cols >= plan.n_local] - plan.n_local
+                assert not torch.isnan(halo[rem]).any()
         assert np.array_equal(halo.numpy(), X[h])           # every halo slot holds the right global row
         # dst_off: owner q's segment for requester p starts where p's halo lists q's rows
         offs = torch.tensor(plan.dst_off)
         gathered = [torch.empty_like(offs) for _ in range(world)]
         dist.all_gather(gathered, offs)
-        my_off = np.concatenate([[0], np.cumsum(plan.recv_counts)])
         for q in range(world):
-            assert int(gathered[q][rank]) == int(my_off[q])
-        # aggregate: local columns + remote columns == the global product's rows
+            assert int(gathered[q][rank]) == int(off[q])
+        # back_off (backward): where this rank's partial segment lands in owner q's send list
+        so = torch.tensor(send_off[:world])
+        gathered = [torch.empty_like(so) for _ in range(world)]
+        dist.all_gather(gathered, so)
+        for q in range(world):
+            assert plan.back_off[q] == int(gathered[q][rank])
+        # forward: the scheduled consumers (P1 + wave consumers) == the global product's rows
+        Y = reference_step_cpu(plan, Xl, halo).numpy()
+        A = sp.csr_matrix((val.astype(np.float64), col, rowptr), shape=(n, n))
+        ref = (A @ X.astype(np.float64))[lo:hi]
+        err = float(np.abs(Y - ref).max())
+        # consumers cover every row exactly once as a writer
+        written = np.zeros(hi - lo, int)
+        for cons in [plan.p1] + list(plan.p2):
+            if cons is not None and cons.mode != "remote":
+                written[(np.arange(hi - lo) if cons.row_map is None else cons.row_map.numpy())] += 1
+        assert np.all(written == 1)
+        # backward: dX = (A^T dY)[own rows] via remote partials + reverse exchange + ordered accumulation
+        dY = np.random.default_rng(seed + 1).standard_normal((n, X.shape[1]))
         A_loc = sp.csr_matrix((plan.val_loc.numpy().astype(np.float64), plan.col_loc.numpy(), plan.rowptr_loc.numpy()),
                               shape=(hi - lo, hi - lo))
         A_rem = sp.csr_matrix((plan.val_rem.numpy().astype(np.float64), plan.col_rem.numpy(), plan.rowptr_rem.numpy()),
                               shape=(hi - lo, max(len(h), 1)))
-        Y = A_loc @ X[lo:hi].astype(np.float64) + (A_rem @ halo.numpy().astype(np.float64) if len(h) else 0)
-        A = sp.csr_matrix((val.astype(np.float64), col, rowptr), shape=(n, n))
-        ref = (A @ X.astype(np.float64))[lo:hi]
-        err = float(np.abs(Y - ref).max())
-        out_q.put((rank, err, len(h), bounds))
+        partial = torch.from_numpy(np.ascontiguousarray((A_rem.T @ dY[lo:hi])[:len(h)]))
+        back = torch.empty((sum(plan.send_counts), X.shape[1]), dtype=torch.float64)
+        dist.all_to_all_single(back, partial, output_split_sizes=plan.send_counts, input_split_sizes=plan.recv_counts)
+        dX = A_loc.T @ dY[lo:hi]
+        np.add.at(dX, plan.send_rows.numpy(), back.numpy())
+        err_b = float(np.abs(dX - (A.T @ dY)[lo:hi]).max())
+        out_q.put((rank, max(err, err_b), len(h), bounds, plan.two_pass_chunks))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_halo_plan_reproduces_global_spmm(world):
+@pytest.mark.parametrize("world,waves,c0", [(2, 1, None), (2, 1, 0), (2, 3, None), (3, 1, 1), (3, 4, 2), (3, 3, 0)])
+def test_halo_plan_reproduces_global_spmm(world, waves, c0):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 400, 7, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 400, 7, waves, c0, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err, n_halo, bounds in results:
+    for rank, err, n_halo, bounds, chosen in results:
         assert err < 1e-9, (rank, err)
         assert n_halo > 0 and bounds[0] == 0 and bounds[-1] == 400
+        assert 0 <= chosen <= waves and (c0 is None or chosen == c0)
+
+
+def test_select_rows_compacts_csr():
+    rowptr = torch.tensor([0, 2, 2, 5, 6])
+    col = torch.tensor([1, 3, 0, 2, 4, 9])
+    val = torch.arange(6, dtype=torch.float32)
+    rp, c, v = select_rows(rowptr, col, val, torch.tensor([0, 2]))
+    assert rp.tolist() == [0, 2, 5] and c.tolist() == [1, 3, 0, 2, 4] and v.tolist() == [0., 1., 2., 3., 4.]
+    rp, c, v = select_rows(rowptr, col, None, torch.tensor([1, 3]))
+    assert rp.tolist() == [0, 0, 1] and c.tolist() == [9] and v is None
+
+
+def test_two_pass_model_prefers_single_pass_when_exchange_is_short():
+    # a short exchange (few halo bytes) next to a lot of local work: nothing to hide it under is needed,
+    # so the byte model keeps as little as possible two-pass; a long exchange flips it
+    K = 4
+    few, _ = choose_two_pass_chunks(K, 128, 4, 10_000_000, 1_000_000, [2_000_000] * K, [30_000_000] * K,
+                                    [5_000_000] * K, [1e8] * K)
+    many, _ = choose_two_pass_chunks(K, 128, 4, 1_000_000, 100_000, [2_000_000] * K, [30_000_000] * K,
+                                     [5_000_000] * K, [6e9] * K)
+    assert few < many and many == K
 
 
 def test_balanced_bounds_by_nnz():

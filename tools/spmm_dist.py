@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Partitioned SpMM driver (torchrun, one rank per GPU): papers100M-shaped power-law graph,
-1-D row partition balanced by nnz, halo exchange over NVLink.  JSON lines on rank 0.
-    torchrun --nproc-per-node N tools/spmm_dist.py [--n ...] [--deg ...] [--F 128] [--check]"""
+1-D row partition balanced by nnz, wave-pipelined halo exchange over NVLink.  JSON lines on rank 0.
+    torchrun --nproc-per-node N tools/spmm_dist.py [--nodes ...] [--F 128] --configs "K:c0:mover:ctas:warps[:dedicated]" ...
+Every configuration is checked against a float64 recomputation of sampled rows (X is a hash of the global
+row id, so any rank can recompute any row) and, with --backward, through the adjoint identity
+<dY, A·X> = <Aᵀ·dY, X> reduced over the ranks."""
 import argparse
 import json
 import os
@@ -13,7 +16,7 @@ import torch.distributed as dist  # noqa: E402
 
 from graphneuralnetwork_b200 import _lib, functional as Fn, synthetic as S  # noqa: E402
 from graphneuralnetwork_b200.graph import _p, _stream_ptr  # noqa: E402
-from graphneuralnetwork_b200.partition import PartitionedSpmm, balanced_bounds, build_halo_plan  # noqa: E402
+from graphneuralnetwork_b200.partition import PartitionedSpmm, balanced_bounds, build_halo_plan, select_rows  # noqa: E402
 
 
 def build_rank_block(n, deg, rank, world, dev, seed=0, exponent=2.5, skew=3.0, p_local=0.0, window=0,
@@ -39,137 +42,135 @@ def main():
     ap.add_argument("--nodes", dest="n", type=int, default=S.PAPERS100M["n"])
     ap.add_argument("--deg", type=float, default=13.55)
     ap.add_argument("--F", type=int, default=128)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--p-local", type=float, default=0.0)
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--skew", type=float, default=3.0)
-    ap.add_argument("--transports", nargs="+", default=["p2p", "nccl"])
-    ap.add_argument("--check", action="store_true")
-    ap.add_argument("--phases", action="store_true")
     ap.add_argument("--scatter", action="store_true")
-    ap.add_argument("--halo-ctas", type=int, default=1)
-    ap.add_argument("--halo-sched", type=int, default=0)
-    ap.add_argument("--halo-unroll", type=int, nargs="+", default=[8])
-    ap.add_argument("--overlap-only", action="store_true")
-    ap.add_argument("--tma", action="store_true", help="experimental TMA mover for the p2p push (halo.tma)")
-    ap.add_argument("--cross-check", action="store_true",
-                    help="compare the last p2p result with the NCCL transport's (any graph size)")
-    ap.add_argument("--dedicated", type=int, nargs="+", default=[0], help="PartitionedSpmm.dedicated values to sweep")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--transports", nargs="+", default=["p2p"])
+    ap.add_argument("--configs", nargs="+", default=["4:auto:tma:0:0"],
+                    help="waves:two_pass_chunks(auto|int):mover(tma|vector):ctas:warps[:dedicated_sms]")
+    ap.add_argument("--backward", action="store_true")
+    ap.add_argument("--phases", action="store_true")
+    ap.add_argument("--full-check", action="store_true", help="small graphs: compare every row with a 1-GPU SpMM")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    _lib.set_tuning("halo.ctas_per_sm", a.halo_ctas)
-    _lib.set_tuning("halo.schedule", a.halo_sched)
-    _lib.set_tuning("halo.unroll", a.halo_unroll[0])
-    csr, bounds, nnz_total = build_rank_block(a.n, a.deg, rank, world, dev, skew=a.skew, p_local=a.p_local, window=a.window,
-                                                  scatter=a.scatter)
-    plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world)
-    n_loc = plan.n_local
-    gen = torch.Generator(device=dev).manual_seed(1 + rank)
-    X = torch.randn(n_loc, a.F, device=dev, generator=gen)
-    stats = torch.tensor([plan.n_halo, csr.nnz, int(plan.rowptr_loc[-1].item()), int(plan.send_rows.numel())],
-                         dtype=torch.int64, device=dev)
-    allstats = [torch.empty_like(stats) for _ in range(world)]
-    if world > 1:
-        dist.all_gather(allstats, stats)
-    else:
-        allstats = [stats]
-    del csr
+    dtype = torch.float32 if a.dtype == "f32" else torch.bfloat16
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    csr, bounds, nnz_total = build_rank_block(a.n, a.deg, rank, world, dev, skew=a.skew, p_local=a.p_local,
+                                              window=a.window, scatter=a.scatter)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n_loc = hi - lo
+    X = S.hashed_feature_block(lo, hi, a.F, dev, dtype)
+    rows = S.spmm_check_rows(csr, 4096, 17 + rank)
+    ref_rows = S.spmm_sampled_reference(csr, rows, a.F, dtype)  # the checker sees the same (rounded) inputs
+    ref_scale = float(ref_rows.abs().max().item())
+
+    def reduce_max(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def reduce_sum(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t)
+        return t.item()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return reduce_max(t0.elapsed_time(t1) / steps)
+
+    Y = torch.empty(n_loc, a.F, device=dev, dtype=dtype)
+    configs = a.configs if world > 1 else ["1:auto:tma:0:0"]
+    plans, plan = {}, None
     for transport in (a.transports if world > 1 else ["none"]):
-        op = PartitionedSpmm(plan, a.F, dev, transport=transport)
-        Y = torch.empty(n_loc, a.F, device=dev)
-        # transports: p2p (fused NVLink push), nccl (library baseline), ce (experimental: local pack + copy engines)
-        for overlap, dedicated, unroll in [(o, d, u) for u in (a.halo_unroll if transport == "p2p" else a.halo_unroll[:1])
-                                           for d in (a.dedicated if transport == "p2p" else [0])
-                                           for o in ([True] if (a.overlap_only or world == 1) else [True, False])]:
-            if unroll != a.halo_unroll[0] and dedicated == 0:
-                continue  # the shared-SM schedule is swept with the first unroll only
-            op.dedicated = dedicated
-            op.tma = bool(a.tma)
-            _lib.set_tuning("halo.unroll", unroll)
-            for _ in range(a.warmup):
-                op.forward(X, out=Y, overlap=overlap)
-            torch.cuda.synchronize()
+        for cfg in configs:
+            parts = cfg.split(":")
+            K, c0 = int(parts[0]), (None if parts[1] == "auto" else int(parts[1]))
+            mover, ctas, warps = parts[2], int(parts[3]), int(parts[4])
+            dedicated = int(parts[5]) if len(parts) > 5 else 0
+            if transport == "nccl":
+                K, c0 = 1, (1 if c0 is None else min(c0, 1))
+            key = (K, c0)
+            if key not in plans:
+                plans.clear()
+                plan = None
+                torch.cuda.empty_cache()
+                plans[key] = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world, waves=K,
+                                             two_pass_chunks=c0, F=a.F, elem_size=X.element_size())
+            plan = plans[key]
+            op = PartitionedSpmm(plan, a.F, dev, transport=transport, dtype=dtype, mover=mover, mover_ctas=ctas,
+                                 mover_warps=warps, dedicated_sms=dedicated)
+            ms = timed(lambda: op.forward(X, out=Y), a.steps, a.warmup)
+            op.check_status()
+            err = reduce_max(float((Y[rows].double() - ref_rows).abs().max().item()) / max(ref_scale, 1e-30))
+            stats = torch.tensor([plan.n_halo, int(plan.send_rows.numel()), plan.model.get("rows_interior", 0),
+                                  plan.two_pass_chunks], dtype=torch.int64, device=dev)
+            allstats = [torch.empty_like(stats) for _ in range(world)]
             if world > 1:
-                dist.barrier()
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for _ in range(a.steps):
-                op.forward(X, out=Y, overlap=overlap)
-            t1.record()
-            torch.cuda.synchronize()
-            ms = torch.tensor([t0.elapsed_time(t1) / a.steps], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            if rank == 0:
-                hal = [int(s[0]) for s in allstats]
-                print(json.dumps({"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F,
-                                  "transport": transport, "overlap": overlap, "dedicated_sms": dedicated, "tma": bool(a.tma), "halo_ctas": a.halo_ctas, "sched": a.halo_sched, "unroll": unroll, "ms": ms.item(),
-                                  "edges_per_s": nnz_total / ms.item() * 1e3, "p_local": a.p_local, "window": a.window, "scatter": a.scatter, "skew": a.skew,
-                                  "halo_rows_max": max(hal), "halo_rows_mean": sum(hal) / world,
-                                  "halo_gb_recv_max": max(hal) * a.F * 4 / 1e9,
-                                  "send_rows_max": max(int(s[3]) for s in allstats),
-                                  "local_edge_frac": sum(int(s[2]) for s in allstats) / max(sum(int(s[1]) for s in allstats), 1),
-                                  "bounds": bounds if world <= 8 else None}), flush=True)
-        if world > 1 and a.phases:
-            from graphneuralnetwork_b200.functional import spmm_raw
-
-            def timed(fn, reps=5):
-                fn()
-                torch.cuda.synchronize()
-                dist.barrier()
-                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0.record()
-                for _ in range(reps):
-                    fn()
-                t1.record()
-                torch.cuda.synchronize()
-                m = torch.tensor([t0.elapsed_time(t1) / reps], device=dev, dtype=torch.float64)
-                dist.all_reduce(m, op=dist.ReduceOp.MAX)
-                return m.item()
-
-            t_x = timed(lambda: op._exchange(X))
-            t_l = timed(lambda: spmm_raw(op.A_loc, X, out=Y))
-            halo = op.halo[0]
-            t_r = timed(lambda: spmm_raw(op.A_rem, halo, out=Y, accumulate=True))
-            if rank == 0:
-                print(json.dumps({"phases": transport, "exchange_ms": t_x, "local_ms": t_l, "remote_ms": t_r,
-                                  "exchange_gbs_recv": max(int(s[0]) for s in allstats) * a.F * 4 / t_x / 1e6}), flush=True)
-        if a.cross_check and world > 1 and transport in ("p2p", "ce"):
-            ref_op = PartitionedSpmm(plan, a.F, dev, transport="nccl")
-            Yr = ref_op.forward(X, overlap=False)
-            torch.cuda.synchronize()
-            err = (Y - Yr).abs().max().item() / max(Yr.abs().max().item(), 1e-30)
-            errs = torch.tensor([err], device=dev, dtype=torch.float64)
-            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
-            if rank == 0:
-                print(json.dumps({"cross_check": "p2p vs nccl transport", "max_rel_err": errs.item(),
-                                  "ok": errs.item() < 1e-6}), flush=True)
-            ref_op.close()
-            del ref_op, Yr
-        if a.check:
-            # every rank rebuilds the FULL graph (small n only) and checks its own rows
-            full = S.powerlaw_csr(a.n, a.deg, seed=0, device=dev, skew=a.skew, p_local=a.p_local, window=a.window,
-                                  scatter_hubs=a.scatter)
-            Xs = [torch.empty(bounds[q + 1] - bounds[q], a.F, device=dev) for q in range(world)]
-            if world > 1:
-                dist.all_gather(Xs, X)
+                dist.all_gather(allstats, stats)
             else:
-                Xs = [X]
-            ref = Fn.spmm_raw(full, torch.cat(Xs, 0))[bounds[rank]:bounds[rank + 1]]
-            err = (Y - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
-            errs = torch.tensor([err], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+                allstats = [stats]
+            line = {"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F, "dtype": a.dtype,
+                    "transport": transport, "waves": K, "two_pass_chunks": [int(s[3]) for s in allstats],
+                    "mover": mover, "mover_ctas": ctas, "mover_warps": warps, "dedicated_sms": dedicated,
+                    "ms": ms, "edges_per_s": nnz_total / ms * 1e3, "max_rel_err_sampled_rows": err, "ok": err < tol,
+                    "p_local": a.p_local, "window": a.window,
+                    "halo_gb_recv_max": max(int(s[0]) for s in allstats) * a.F * X.element_size() / 1e9,
+                    "send_gb_max": max(int(s[1]) for s in allstats) * a.F * X.element_size() / 1e9,
+                    "interior_row_frac": sum(int(s[2]) for s in allstats) / a.n,
+                    "model_ms": {k: round(v, 2) for k, v in plan.model.items() if k.startswith("c0=") or k == "exchange_ms"}}
+            if a.backward:
+                dY = S.hashed_feature_block(lo, hi, a.F, dev, dtype, salt=977)
+                dX = torch.empty_like(Y)
+                line["backward_ms"] = timed(lambda: op.backward(dY, out=dX), max(a.steps // 2, 2), 1)
+                op.check_status()
+                lhs = reduce_sum(float((dY.double() * Y.double()).sum().item()))
+                rhs = reduce_sum(float((dX.double() * X.double()).sum().item()))
+                norm = reduce_sum(float((dY.double().abs() * Y.double().abs()).sum().item()))
+                line["adjoint_rel_err"] = abs(lhs - rhs) / max(norm, 1e-30)
+                line["backward_ok"] = line["adjoint_rel_err"] < (1e-6 if dtype == torch.float32 else 1e-2)
+                del dY, dX
+            if a.phases and world > 1:
+                t_x = timed(lambda: op.exchange_only(X), 4, 1)
+                line["exchange_alone_ms"] = t_x
+                line["exchange_alone_gbs"] = line["halo_gb_recv_max"] / t_x * 1e3
+            if a.full_check:
+                full = S.powerlaw_csr(a.n, a.deg, seed=0, device=dev, skew=a.skew, p_local=a.p_local, window=a.window,
+                                      scatter_hubs=a.scatter)
+                Xf = S.hashed_feature_block(0, a.n, a.F, dev, dtype)
+                ref = Fn.spmm_raw(full, Xf)[lo:hi]
+                line["full_check_max_rel_err"] = reduce_max(float((Y.float() - ref.float()).abs().max().item()) /
+                                                            max(float(ref.float().abs().max().item()), 1e-30))
+                if a.backward:
+                    dYf = S.hashed_feature_block(0, a.n, a.F, dev, dtype, salt=977)
+                    refb = Fn.spmm_raw(full.transpose(), dYf)[lo:hi]
+                    dX = op.backward(dYf[lo:hi].contiguous())
+                    line["full_check_backward_max_rel_err"] = reduce_max(
+                        float((dX.float() - refb.float()).abs().max().item()) / max(float(refb.float().abs().max().item()), 1e-30))
+                del full, Xf
             if rank == 0:
-                print(json.dumps({"check": transport, "max_rel_err": errs.item(), "ok": errs.item() < 1e-5}), flush=True)
-            del full
-        op.close()
-        del op
+                print(json.dumps(line), flush=True)
+            op.close()
+            del op
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
