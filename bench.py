@@ -533,7 +533,38 @@ def run_other_configs_b200(dev, reps=20):
     out["spmm_reddit_f602"] = {"config": "GCN aggregation Y=A.X on the Reddit-shaped power-law graph (232,965 nodes, "
                                          "nnz %d), F=602 fp32, X 561 MB >> L2" % csr.nnz,
                                "ms": ms, "edges_per_s": csr.nnz / ms * 1e3, "roofline": roof}
-    del csr, Xr, Y
+    del Xr, Y
+    torch.cuda.empty_cache()
+    # GAT aggregation (8 heads x 8) on the same Reddit-shaped graph: forward and backward of the fused
+    # attention kernels.  The Wh table is 60 MB (L2-resident): per SURVEY 8d's validity rule no HBM fraction
+    # is claimed; the bound that applies is L2 gather bandwidth, reported as gather-model GB/s.
+    try:
+        gcsr = S.powerlaw_csr(S.REDDIT["n"], 492.0, seed=0, device=dev, with_values=False,
+                              max_degree=20000, skew=1.0)
+        n, H, Fp = S.REDDIT["n"], 8, 8
+        gat_res = {"config": "fused GAT aggregation, 8 heads x 8, Reddit-shaped graph (232,965 nodes, nnz %d)" % gcsr.nnz,
+                   "roofline": "n/a as an HBM fraction: the 60 MB Wh table is L2-resident (validity rule); "
+                               "gather_model_gbs is the L2-side gather rate"}
+        for dt, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+            Wh = torch.randn(n, H * Fp, device=dev).to(dt).requires_grad_(True)
+            s_ = torch.randn(n, H, device=dev, requires_grad=True)
+            t_ = torch.randn(n, H, device=dev, requires_grad=True)
+            ms_f = cuda_time(lambda: Fn.gat_fwd_raw(gcsr, Wh.detach(), s_.detach(), t_.detach(), H, Fp, 0.2, elu=1), 5,
+                             flush_dev=dev)
+            o = Fn.gat_aggregate(gcsr, Wh, s_, t_, H, Fp, 0.2)
+            gy = torch.randn_like(o)
+            ms_b = cuda_time(lambda: torch.autograd.grad(o, (Wh, s_, t_), gy, retain_graph=True), 5, flush_dev=dev)
+            es = Wh.element_size()
+            Bg = gcsr.nnz * (4 + H * Fp * es + H * 4) + n * (H * 4 + H * Fp * es) + (n + 1) * 8
+            gat_res[tag] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_edges_per_s": gcsr.nnz / ms_f * 1e3,
+                            "bwd_edges_per_s": gcsr.nnz / ms_b * 1e3, "fwd_gather_model_gbs": Bg / ms_f / 1e6,
+                            "bwd_over_fwd": ms_b / ms_f}
+            del Wh, s_, t_, o, gy
+        out["gat_reddit"] = gat_res
+        del gcsr
+    except Exception as e:  # pragma: no cover
+        out["gat_reddit"] = {"error": repr(e)[:300]}
+    del csr
     torch.cuda.empty_cache()
     return out
 
@@ -635,7 +666,7 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("random", "locality"
                              p_local=gcfg["p_local"], window=gcfg["window"], scatter_hubs=gcfg["scatter"])
         del deg_all
         rows = S.spmm_check_rows(csr, 4096, 17 + rank)
-        ref_rows = S.spmm_sampled_reference(csr, rows, F)
+        ref_rows, ref_mag = S.spmm_sampled_reference(csr, rows, F, with_abs=True)
         plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world, waves=PART_WAVES, F=F)
         del csr
         torch.cuda.empty_cache()
@@ -656,8 +687,9 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("random", "locality"
         op.check_status()
         diff = (Y[rows].double() - ref_rows).abs()
         err_max = float(diff.max().item()) / max(float(ref_rows.abs().max().item()), 1e-30)
-        # element-wise criterion beside the max-norm one: |a-b| <= atol + rtol*|b| with atol tied to the row scale
-        elem_bad = int((diff > 1e-6 * ref_rows.abs().amax(dim=1, keepdim=True) + 1e-5 * ref_rows.abs()).sum().item())
+        # element-wise criterion beside the max-norm one: |a-b| <= 1e-5*|b| + 1e-6*sum_j|a_ij x_jf| (the second
+        # term is the scale an fp32 sum's rounding is relative to: hub rows add 10^5 signed terms)
+        elem_bad = int((diff > 1e-5 * ref_rows.abs() + 1e-6 * ref_mag).sum().item())
         ms, halo_max, err, bad = rmax([t0.elapsed_time(t1) / steps, float(plan.n_halo), err_max, float(elem_bad)])
         B = nnz_total * 8 + nnz_total * F * 4 + n * F * 4 + (n + 1) * 8
         ok = bool(err < 1e-5 and bad == 0)
@@ -679,7 +711,7 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("random", "locality"
             res["nvlink_floor_ms"] = halo_max * F * 4 / (NVLINK_GBS * 1e6)
         out[gname] = res
         op.close()
-        del op, X, Y, plan, ref_rows
+        del op, X, Y, plan, ref_rows, ref_mag
         torch.cuda.empty_cache()
     return out
 

@@ -52,9 +52,14 @@ SIGNATURES = {
     "gnn_gat_scores_f32": (cint, [ptr, i64, ptr, ptr, i64, i32, i32, ptr, ptr, ptr]),
     "gnn_gat_fused_fwd_f32": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr, ptr,
                                      i64, ptr, ptr, ptr, i64, i64, ptr]),
-    "gnn_gat_fused_bwd_f32": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
+    "gnn_gat_fused_bwd_f32": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
                                      i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64,
                                      ptr]),
+    "gnn_gat_fused_fwd_bf16": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr, ptr,
+                                      i64, ptr, ptr, ptr, i64, i64, ptr]),
+    "gnn_gat_fused_bwd_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
+                                      i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64,
+                                      ptr]),
     "gnn_synth_powerlaw_degrees": (cint, [i64, i64, f64, f64, i64, u64, ptr, ptr]),
     "gnn_synth_powerlaw_fill": (cint, [i64, i64, i64, ptr, f64, f64, i64, u64, ptr, ptr]),
     "gnn_synth_gcn_values": (cint, [i64, i64, ptr, ptr, ptr, ptr, ptr]),
@@ -64,6 +69,8 @@ SIGNATURES = {
     "gnn_peer_free": (cint, [ptr]),
     "gnn_peer_copy_async": (cint, [ptr, ptr, size_t, ptr]),
     "gnn_halo_push": (cint, [ptr, i64, i32, i32, ptr, ptr, ptr, ptr, ptr, i64, i32, ptr, ptr]),
+    "gnn_halo_rows_per_stage": (cint, [i32]),
+    "gnn_halo_push_waves": (cint, [ptr, i64, i32, i32, ptr, ptr, i32, i32, i64, ptr, ptr, i32, i32, C.c_uint32, ptr, ptr]),
     "gnn_peer_signal": (cint, [ptr, i32, i32, i32, C.c_uint32, ptr]),
     "gnn_peer_wait": (cint, [ptr, i32, i32, C.c_uint32, ptr, i64, ptr]),
     "gnn_spmm_csr_ex_f32": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr, ptr]),

@@ -28,8 +28,9 @@ constexpr int kGatWarps = 4;
 struct GatArgs {
   const int64_t* rowptr;
   const int32_t* col;
-  const int64_t* perm;  // backward B: transposed slot -> forward edge slot
-  const float* Wh;
+  const int64_t* perm;   // backward B: transposed slot -> forward edge slot (nullptr: the stash is in transposed order)
+  const int64_t* tslot;  // backward A: forward edge slot -> transposed slot (nullptr: stash in forward order)
+  const void* Wh;        // T [n, ldw]: fp32 or bf16 (softmax and accumulation are fp32 either way)
   int64_t ldw;
   const float* s;
   const float* t;
@@ -40,18 +41,17 @@ struct GatArgs {
   int elu;
   const float* col_mean;
   const float* keep;
-  float* out;
+  void* out;             // T [n, ldo]
   int64_t ldo;
   float* row_max;
   float* row_sum;
   int SE;
   // backward
-  const float* out_pre;
-  const float* d_out;
+  const void* out_pre;   // T
+  const void* d_out;     // T
   const float* rowdot;
-  float* edge_w;
-  float* edge_dz;
-  float* d_Wh;
+  float* edge_st;        // [nnz][2][H] fp32: per edge (keep*alpha, dz), in transposed slot order when tslot != nullptr
+  void* d_Wh;            // T
   int64_t ld_dwh;
   float* d_s;
   float* d_t;
@@ -63,6 +63,17 @@ struct GatArgs {
 
 __device__ __forceinline__ bool aligned_to_dev(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+template <typename T>
+__device__ __forceinline__ float ldv(const T* p);
+template <>
+__device__ __forceinline__ float ldv<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ldv<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float(((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+__device__ __forceinline__ void stv(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stv(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 __device__ __forceinline__ float act_elu(float x, int elu) {
   if (elu >= 1) x = elu1(x);
   if (elu >= 2) x = elu1(x);
@@ -71,6 +82,10 @@ __device__ __forceinline__ float act_elu(float x, int elu) {
 
 // floats of shared memory per warp for the staged chunk
 __host__ __device__ inline int gat_warp_floats(int SE, int H, int HF) { return SE * H + SE + 160 + HF; }
+// backward A additionally stages the int64 transposed slot of every edge of the chunk (first, 8-byte aligned)
+__host__ __device__ inline int gat_warp_floats_bwd(int SE, int H, int HF) {
+  return 2 * SE + SE * H + SE + 160 + ((HF + 1) & ~1);
+}
 
 // W  = warps that share one row: 1 -> one warp per row (4 rows per CTA); 4 / 16 -> one CTA of W
 //      warps per row, the warps take alternate SE-edge chunks and merge (max, sum, acc) in warp order.
@@ -83,7 +98,7 @@ struct GatBlock {
   static constexpr int kWarps = (W == 1) ? kGatWarps : W;
 };
 
-template <int CPL, int W, int HT>
+template <typename T, int CPL, int W, int HT>
 __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const GatArgs a) {
   constexpr int BW = GatBlock<W>::kWarps;
   extern __shared__ float sm[];
@@ -117,7 +132,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
   const int64_t e0 = __ldg(a.rowptr + i), e1 = __ldg(a.rowptr + i + 1);
   const int64_t d = e1 - e0;
   if (W == 1 && a.skip_deg_gt > 0 && d > a.skip_deg_gt) return;  // a long row: the CTA-per-row launch owns it
-  float* orow = a.out + i * a.ldo;
+  T* orow = reinterpret_cast<T*>(a.out) + i * a.ldo;
   if (d == 0) {
     // GAT/models/layers.py:28-30: an all -9e15 row soft-maxes to the uniform 1/N over ALL nodes
     if (wsub == 0) {
@@ -125,7 +140,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
       for (int c = 0; c < CPL; ++c)
         if (cv[c]) {
           const int ci = lane + 32 * c;
-          orow[ci] = act_elu(a.col_mean ? a.col_mean[ci] : 0.f, a.elu);
+          stv(orow + ci, act_elu(a.col_mean ? a.col_mean[ci] : 0.f, a.elu));
           if (ci % a.Fp == 0) {
             if (a.row_max) a.row_max[i * H + hc[c]] = 0.f;
             if (a.row_sum) a.row_sum[i * H + hc[c]] = 0.f;
@@ -231,9 +246,9 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const bool ok = k0 + u < ne;
-        const float* wr = a.Wh + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
+        const T* wr = reinterpret_cast<const T*>(a.Wh) + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? __ldg(wr + lane + 32 * c) : 0.f;
+        for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? ldv<T>(wr + lane + 32 * c) : 0.f;
       }
       const float* pk = logit + k0 * H;
 #pragma unroll
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
     for (int c = 0; c < CPL; ++c)
       if (cv[c]) {
         const int ci = lane + 32 * c;
-        orow[ci] = act_elu(acc[c] / l[c], a.elu);
+        stv(orow + ci, act_elu(acc[c] / l[c], a.elu));
         if (ci % a.Fp == 0) {
           if (a.row_max) a.row_max[i * H + hc[c]] = mh[hc[c]];
           if (a.row_sum) a.row_sum[i * H + hc[c]] = l[c];
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
           L = fmaf(larr[(w * CPL + c) * 32 + lane], f, L);
           A = fmaf(aarr[(w * CPL + c) * 32 + lane], f, A);
         }
-        orow[ci] = act_elu(A / L, a.elu);
+        stv(orow + ci, act_elu(A / L, a.elu));
         if (ci % a.Fp == 0) {
           if (a.row_max) a.row_max[i * H + hc[c]] = M;
           if (a.row_sum) a.row_sum[i * H + hc[c]] = L;
@@ -321,24 +336,25 @@ __global__ void __launch_bounds__(256) gat_scores_kernel(const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) gat_rowdot_kernel(const float* __restrict__ d_out,
-                                                         const float* __restrict__ out_pre, int64_t ldo, int64_t n,
+template <typename T>
+__global__ void __launch_bounds__(256) gat_rowdot_kernel(const T* __restrict__ d_out,
+                                                         const T* __restrict__ out_pre, int64_t ldo, int64_t n,
                                                          int H, int Fp, float* __restrict__ rowdot) {
   const int64_t total = n * H;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(p % H);
     const int64_t i = p / H;
-    const float* a = d_out + i * ldo + h * Fp;
-    const float* b = out_pre + i * ldo + h * Fp;
+    const T* a = d_out + i * ldo + h * Fp;
+    const T* b = out_pre + i * ldo + h * Fp;
     float acc = 0.f;
-    for (int f = 0; f < Fp; ++f) acc = fmaf(__ldg(a + f), __ldg(b + f), acc);
+    for (int f = 0; f < Fp; ++f) acc = fmaf(ldv<T>(a + f), ldv<T>(b + f), acc);
     rowdot[p] = acc;
   }
 }
 
 // Phase 1 of backward A for one staged chunk: dots dOut_i . Wh_j per head.  FPT = head width
 // (power of two <= 32: aligned lane groups, segmented xor-shuffle) or 0 (single head: full warp).
-template <int CPL, int FPT>
+template <typename T, int CPL, int FPT>
 __device__ __forceinline__ void bwd_head_dots(const GatArgs& a, const int* cols, int ne, const float (&dcol)[CPL],
                                               const bool (&cv)[CPL], const bool (&lead)[CPL], const int (&hc)[CPL],
                                               float* dot_s, int H, int lane) {
@@ -347,9 +363,9 @@ __device__ __forceinline__ void bwd_head_dots(const GatArgs& a, const int* cols,
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const bool ok = k0 + u < ne;
-      const float* wr = a.Wh + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
+      const T* wr = reinterpret_cast<const T*>(a.Wh) + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? __ldg(wr + lane + 32 * c) : 0.f;
+      for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? ldv<T>(wr + lane + 32 * c) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -379,7 +395,7 @@ __device__ __forceinline__ void bwd_head_dots(const GatArgs& a, const int* cols,
 // and d_s[i,h] = sum_j dz.  SEG == true: Fp is a power of two <= 32 (the head groups of the
 // lane->column map are aligned lane groups, reduced by segmented shuffle) or H == 1 (full-warp
 // reduce).  SEG == false: generic lane-per-edge dot (any H, Fp).
-template <int CPL, int W, bool SEG, int HT>
+template <typename T, int CPL, int W, bool SEG, int HT>
 __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(const GatArgs a) {
   constexpr int BW = GatBlock<W>::kWarps;
   extern __shared__ float sm[];
@@ -390,8 +406,9 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(
   if (W == 1 && i >= a.n) return;
   if (W == 1 && a.skip_deg_gt > 0 && __ldg(a.rowptr + i + 1) - __ldg(a.rowptr + i) > a.skip_deg_gt) return;
   const int H = HT ? HT : a.H, Hp = HT ? HT : a.Hp, SE = a.SE, HF = a.HF, Fp = a.Fp;
-  const int PW = gat_warp_floats(SE, H, HF);
-  float* dot_s = sm + (size_t)warp * PW;       // [SE*H]: head dots, then dz in place
+  const int PW = gat_warp_floats_bwd(SE, H, HF);
+  int64_t* tsl = reinterpret_cast<int64_t*>(sm + (size_t)warp * PW);  // [SE]: stash slot of every staged edge
+  float* dot_s = sm + (size_t)warp * PW + 2 * SE;                     // [SE*H]: head dots, then dz in place
   int* cols = reinterpret_cast<int*>(dot_s + SE * H);
   float* cst = reinterpret_cast<float*>(cols + SE);  // [4][32]: s_i, m_i, 1/l_i, D_i
   float* dout_s = cst + 128;                    // [HF] (generic path)
@@ -406,7 +423,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(
     cv[c] = ci < HF;
     hc[c] = cv[c] ? ci / Fp : 0;
     lead[c] = cv[c] && (ci % Fp) == 0;
-    dcol[c] = cv[c] ? __ldg(a.d_out + i * a.ldo + ci) : 0.f;
+    dcol[c] = cv[c] ? ldv<T>(reinterpret_cast<const T*>(a.d_out) + i * a.ldo + ci) : 0.f;
     if (!SEG && cv[c]) dout_s[ci] = dcol[c];
   }
   if (lane < H) {
@@ -422,29 +439,33 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(
   const int ngrp = 32 / Hp;
   const int hsub = lane % Hp, g = lane / Hp;
   float dsum = 0.f;
+  (void)e1;
   for (int64_t c0 = (int64_t)wsub * SE; c0 < d; c0 += (int64_t)W * SE) {
     const int ne = (int)((d - c0) < SE ? (d - c0) : SE);
-    for (int k = lane; k < ne; k += 32) cols[k] = __ldg(a.col + e0 + c0 + k);
+    for (int k = lane; k < ne; k += 32) {
+      cols[k] = __ldg(a.col + e0 + c0 + k);
+      tsl[k] = a.tslot ? __ldg(a.tslot + e0 + c0 + k) : (e0 + c0 + k);
+    }
     __syncwarp();
     // phase 1: per-head dots dOut_i . Wh_j
     if (SEG) {
       // the head-group reduction is unrolled for the common widths; `lead` marks the lane that
       // owns a head's first column (no run-time modulo or loop in the per-edge path)
       switch (H == 1 ? 0 : Fp) {
-        case 0: bwd_head_dots<CPL, 0>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 1: bwd_head_dots<CPL, 1>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 2: bwd_head_dots<CPL, 2>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 4: bwd_head_dots<CPL, 4>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 8: bwd_head_dots<CPL, 8>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 16: bwd_head_dots<CPL, 16>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        default: bwd_head_dots<CPL, 32>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 0: bwd_head_dots<T, CPL, 0>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 1: bwd_head_dots<T, CPL, 1>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 2: bwd_head_dots<T, CPL, 2>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 4: bwd_head_dots<T, CPL, 4>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 8: bwd_head_dots<T, CPL, 8>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        case 16: bwd_head_dots<T, CPL, 16>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
+        default: bwd_head_dots<T, CPL, 32>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
       }
     } else {
       for (int k = lane; k < ne; k += 32) {
-        const float* wr = a.Wh + (int64_t)cols[k] * a.ldw;
+        const T* wr = reinterpret_cast<const T*>(a.Wh) + (int64_t)cols[k] * a.ldw;
         for (int h = 0; h < H; ++h) {
           float dot = 0.f;
-          for (int f = 0; f < Fp; ++f) dot = fmaf(dout_s[h * Fp + f], __ldg(wr + h * Fp + f), dot);
+          for (int f = 0; f < Fp; ++f) dot = fmaf(dout_s[h * Fp + f], ldv<T>(wr + h * Fp + f), dot);
           dot_s[k * H + h] = dot;
         }
       }
@@ -464,8 +485,11 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(
       const float al = __expf(ee - cst[32 + h]) * cst[64 + h];
       const float kp = a.keep ? __ldg(a.keep + e * H + h) : 1.f;
       const float dz = al * (kp * dot_s[idx] - cst[96 + h]) * slope;
-      a.edge_w[e * H + h] = kp * al;
-      a.edge_dz[e * H + h] = dz;
+      // the stash is written in the order kernel B walks it (scattered 32-byte stores here, no stall;
+      // sequential reads there instead of a random 32-byte read per edge through the permutation)
+      float* stp = a.edge_st + tsl[k] * (2 * H);
+      stp[h] = kp * al;
+      stp[H + h] = dz;
       dot_s[idx] = dz;
     }
     __syncwarp();
@@ -488,7 +512,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(
 }
 
 // Backward B: transposed CSR rows (source node j), sources of the forward edges ascending.
-template <int CPL, int W>
+template <typename T, int CPL, int W>
 __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_cols_kernel(const GatArgs a) {
   constexpr int BW = GatBlock<W>::kWarps;
   __shared__ float accarr[(W > 1) ? BW * CPL * 32 : 1];
@@ -520,12 +544,12 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_cols_kernel(
     int64_t pl = 0;
     if (lane < ne) {
       il = __ldg(a.col + c0 + lane);
-      pl = __ldg(a.perm + c0 + lane);
+      pl = a.perm ? __ldg(a.perm + c0 + lane) : (c0 + lane);
     }
     for (int k0 = 0; k0 < ne; k0 += ngrp) {
       const int kk = k0 + g;
       const int64_t p = __shfl_sync(0xffffffffu, pl, kk & 31);
-      if (kk < ne && hsub < H) dtsum += __ldg(a.edge_dz + p * H + hsub);
+      if (kk < ne && hsub < H) dtsum += __ldg(a.edge_st + p * (2 * H) + H + hsub);
     }
     for (int k0 = 0; k0 < ne; k0 += 8) {
       float w[8][CPL], x[8][CPL];
@@ -534,12 +558,12 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_cols_kernel(
         const int i = __shfl_sync(0xffffffffu, il, (k0 + u) & 31);
         const int64_t p = __shfl_sync(0xffffffffu, pl, (k0 + u) & 31);
         const bool ok = k0 + u < ne;
-        const float* dr = a.d_out + (int64_t)i * a.ldo;
+        const T* dr = reinterpret_cast<const T*>(a.d_out) + (int64_t)i * a.ldo;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
           const bool on = ok && cv[c];
-          w[u][c] = on ? __ldg(a.edge_w + p * H + hc[c]) : 0.f;
-          x[u][c] = on ? __ldg(dr + lane + 32 * c) : 0.f;
+          w[u][c] = on ? __ldg(a.edge_st + p * (2 * H) + hc[c]) : 0.f;
+          x[u][c] = on ? ldv<T>(dr + lane + 32 * c) : 0.f;
         }
       }
 #pragma unroll
@@ -552,7 +576,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_cols_kernel(
   if (W == 1) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c)
-      if (cv[c]) a.d_Wh[j * a.ld_dwh + lane + 32 * c] = acc[c];
+      if (cv[c]) stv(reinterpret_cast<T*>(a.d_Wh) + j * a.ld_dwh + lane + 32 * c, acc[c]);
     if (lane < H) a.d_t[j * H + lane] = dtsum;
     return;
   }
@@ -566,7 +590,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_cols_kernel(
       if (cv[c]) {
         float tot = 0.f;
         for (int w = 0; w < BW; ++w) tot += accarr[(w * CPL + c) * 32 + lane];
-        a.d_Wh[j * a.ld_dwh + lane + 32 * c] = tot;
+        stv(reinterpret_cast<T*>(a.d_Wh) + j * a.ld_dwh + lane + 32 * c, tot);
       }
     if (lane < H) {
       float tot = 0.f;
@@ -604,26 +628,23 @@ bool cooperative(int64_t n, int64_t nnz) {
 }
 
 template <int W>
-size_t gat_smem_bytes(int SE, int H, int HF, int cpl) {
+size_t gat_smem_bytes(int SE, int H, int HF, int cpl, bool bwd = false) {
   constexpr int BW = GatBlock<W>::kWarps;
-  size_t f = (size_t)BW * gat_warp_floats(SE, H, HF);
+  size_t f = (size_t)BW * (bwd ? gat_warp_floats_bwd(SE, H, HF) : gat_warp_floats(SE, H, HF));
   if (W > 1) f += (size_t)BW * 32 + 2 * (size_t)BW * cpl * 32;
   return f * sizeof(float);
 }
 
 // forward launch: picks the compile-time head count when there is one
-template <int CPL, int W>
+template <typename T, int CPL, int W>
 int gat_fwd_launch(const GatArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
   constexpr int thr = GatBlock<W>::kWarps * 32;
-#define GNN_GAT_FWD(HT)                                                                                       \
-  do {                                                                                                        \
-    static size_t configured = 0;                                                                             \
-    if (smem > 48 * 1024 && smem > configured) {                                                              \
-      GNN_CUDA(cudaFuncSetAttribute(gat_fwd_kernel<CPL, W, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    (int)smem));                                                              \
-      configured = smem;                                                                                      \
-    }                                                                                                         \
-    gat_fwd_kernel<CPL, W, HT><<<grid, thr, smem, st>>>(a);                                                   \
+#define GNN_GAT_FWD(HT)                                                                                         \
+  do {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                       \
+      GNN_CUDA(cudaFuncSetAttribute(gat_fwd_kernel<T, CPL, W, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                \
+    gat_fwd_kernel<T, CPL, W, HT><<<grid, thr, smem, st>>>(a);                                                  \
   } while (0)
   if (a.H == 8) GNN_GAT_FWD(8);
   else if (a.H == 1) GNN_GAT_FWD(1);
@@ -633,50 +654,23 @@ int gat_fwd_launch(const GatArgs& a, unsigned grid, size_t smem, cudaStream_t st
   return GNN_OK;
 }
 
-template <int W>
+template <typename T, int W>
 int gat_fwd_dispatch(const GatArgs& a, int cpl, unsigned grid, cudaStream_t st) {
   const int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
   const size_t smem = gat_smem_bytes<W>(a.SE, a.H, a.HF, cplr);
   switch (cplr) {
-    case 1: return gat_fwd_launch<1, W>(a, grid, smem, st);
-    case 2: return gat_fwd_launch<2, W>(a, grid, smem, st);
-    case 4: return gat_fwd_launch<4, W>(a, grid, smem, st);
-    default: return gat_fwd_launch<8, W>(a, grid, smem, st);
+    case 1: return gat_fwd_launch<T, 1, W>(a, grid, smem, st);
+    case 2: return gat_fwd_launch<T, 2, W>(a, grid, smem, st);
+    case 4: return gat_fwd_launch<T, 4, W>(a, grid, smem, st);
+    default: return gat_fwd_launch<T, 8, W>(a, grid, smem, st);
   }
 }
 
-#define GNN_GAT_CPL_DISPATCH(KERNEL, ...)               \
-  do {                                                  \
-    if (cpl <= 1) KERNEL<1, __VA_ARGS__;                \
-    else if (cpl <= 2) KERNEL<2, __VA_ARGS__;           \
-    else if (cpl <= 4) KERNEL<4, __VA_ARGS__;           \
-    else KERNEL<8, __VA_ARGS__;                         \
-  } while (0)
-
-}  // namespace
-
-extern "C" {
-
-int gnn_gat_scores_f32(const float* Wh, int64_t ldw, const float* a_src, const float* a_dst, int64_t n, int32_t H,
-                       int32_t Fp, float* s, float* t, gnn_stream_t stream) {
-  int rc = check_common(n, H, Fp);
-  if (rc != GNN_OK) return rc;
-  if (n == 0) return GNN_OK;
-  GNN_REQUIRE(Wh && a_src && a_dst && s && t, GNN_ERR_BAD_ARG, "null pointer");
-  GNN_REQUIRE(ldw >= (int64_t)H * Fp, GNN_ERR_BAD_ARG, "ldw smaller than H*Fp");
-  int64_t grid = (n * H + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 16;
-  grid = grid > cap ? cap : grid;
-  gat_scores_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(Wh, ldw, a_src, a_dst, n, H, Fp, s, t);
-  GNN_LAUNCH_CHECK();
-  return GNN_OK;
-}
-
-int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw, const float* s,
-                          const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode,
-                          int apply_elu, const float* col_mean, const float* edge_keep, float* out, int64_t ldo,
-                          float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
-                          int64_t long_threshold, gnn_stream_t stream) {
+template <typename T>
+int gat_fwd_impl(const int64_t* rowptr, const int32_t* col, const T* Wh, int64_t ldw, const float* s, const float* t,
+                 int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode, int apply_elu,
+                 const float* col_mean, const float* edge_keep, T* out, int64_t ldo, float* row_max, float* row_sum,
+                 const int64_t* long_rows, int64_t n_long, int64_t long_threshold, cudaStream_t st) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
@@ -707,40 +701,82 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
   a.row_max = row_max;
   a.row_sum = row_sum;
   a.SE = stage_edges(H);
-  cudaStream_t st = (cudaStream_t)stream;
   const int cpl = (HF + 31) / 32;
   GNN_REQUIRE(n_long == 0 || (long_rows && long_threshold > 0), GNN_ERR_BAD_ARG, "inconsistent long-row list");
-  if (cooperative(n, nnz)) return gat_fwd_dispatch<kGatWarps>(a, cpl, (unsigned)n, st);
+  if (cooperative(n, nnz)) return gat_fwd_dispatch<T, kGatWarps>(a, cpl, (unsigned)n, st);
   if (n_long > 0) {  // hub rows: one 16-warp CTA each, launched first so the short rows fill in behind
     a.row_list = long_rows;
-    rc = gat_fwd_dispatch<16>(a, cpl, (unsigned)n_long, st);
+    rc = gat_fwd_dispatch<T, 16>(a, cpl, (unsigned)n_long, st);
     if (rc != GNN_OK) return rc;
     a.row_list = nullptr;
     a.skip_deg_gt = long_threshold;
   }
-  return gat_fwd_dispatch<1>(a, cpl, (unsigned)((n + kGatWarps - 1) / kGatWarps), st);
+  return gat_fwd_dispatch<T, 1>(a, cpl, (unsigned)((n + kGatWarps - 1) / kGatWarps), st);
 }
 
-int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
-                          const int64_t* perm_t, const float* Wh, int64_t ldw, const float* s, const float* t,
-                          const float* row_max, const float* row_sum, const float* out_pre, const float* d_out,
-                          int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
-                          const float* edge_keep, float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
-                          float* d_rowdot, float* edge_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
-                          const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
-                          gnn_stream_t stream) {
+// rows kernel launch for one (CPL, W): picks SEG / HT
+template <typename T, int CPLV, int WV>
+int gat_bwd_rows_launch(const GatArgs& a, bool seg, unsigned grid, cudaStream_t st) {
+  const size_t smem = gat_smem_bytes<WV>(a.SE, a.H, a.HF, CPLV, true);
+  constexpr int thrv = GatBlock<WV>::kWarps * 32;
+#define GNN_ROWS(SEGV, HTV)                                                                                 \
+  do {                                                                                                      \
+    if (smem > 48 * 1024)                                                                                   \
+      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<T, CPLV, WV, SEGV, HTV>,                            \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    gat_bwd_rows_kernel<T, CPLV, WV, SEGV, HTV><<<grid, thrv, smem, st>>>(a);                               \
+  } while (0)
+  if (!seg) GNN_ROWS(false, 0);
+  else if (a.H == 8) GNN_ROWS(true, 8);
+  else if (a.H == 1) GNN_ROWS(true, 1);
+  else GNN_ROWS(true, 0);
+#undef GNN_ROWS
+  GNN_LAUNCH_CHECK();
+  return GNN_OK;
+}
+
+template <typename T, int WV>
+int gat_bwd_rows_dispatch(const GatArgs& a, int cplr, bool seg, unsigned grid, cudaStream_t st) {
+  switch (cplr) {
+    case 1: return gat_bwd_rows_launch<T, 1, WV>(a, seg, grid, st);
+    case 2: return gat_bwd_rows_launch<T, 2, WV>(a, seg, grid, st);
+    case 4: return gat_bwd_rows_launch<T, 4, WV>(a, seg, grid, st);
+    default: return gat_bwd_rows_launch<T, 8, WV>(a, seg, grid, st);
+  }
+}
+
+template <typename T, int WV>
+int gat_bwd_cols_dispatch(const GatArgs& a, int cplr, unsigned grid, cudaStream_t st) {
+  constexpr int thrv = GatBlock<WV>::kWarps * 32;
+  switch (cplr) {
+    case 1: gat_bwd_cols_kernel<T, 1, WV><<<grid, thrv, 0, st>>>(a); break;
+    case 2: gat_bwd_cols_kernel<T, 2, WV><<<grid, thrv, 0, st>>>(a); break;
+    case 4: gat_bwd_cols_kernel<T, 4, WV><<<grid, thrv, 0, st>>>(a); break;
+    default: gat_bwd_cols_kernel<T, 8, WV><<<grid, thrv, 0, st>>>(a); break;
+  }
+  GNN_LAUNCH_CHECK();
+  return GNN_OK;
+}
+
+template <typename T>
+int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
+                 const int64_t* perm_t, const int64_t* edge_to_tslot, const T* Wh, int64_t ldw, const float* s,
+                 const float* t, const float* row_max, const float* row_sum, const T* out_pre, const T* d_out,
+                 int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode, const float* edge_keep, T* d_Wh,
+                 int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot, float* edge_scratch, int64_t nnz,
+                 const int64_t* long_rows, int64_t n_long, const int64_t* long_rows_t, int64_t n_long_t,
+                 int64_t long_threshold, cudaStream_t st) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
   GNN_REQUIRE(rowptr && rowptr_t && Wh && s && t && row_max && row_sum && out_pre && d_out && d_Wh && d_s && d_t &&
                   d_rowdot,
               GNN_ERR_BAD_ARG, "null pointer");
-  GNN_REQUIRE(nnz >= 0 && (nnz == 0 || (col && col_t && perm_t && edge_scratch)), GNN_ERR_BAD_ARG,
-              "null edge pointer (col/col_t/perm_t/edge_scratch)");
+  GNN_REQUIRE(nnz >= 0 && (nnz == 0 || (col && col_t && (perm_t || edge_to_tslot) && edge_scratch)), GNN_ERR_BAD_ARG,
+              "null edge pointer (col/col_t/perm_t|edge_to_tslot/edge_scratch)");
   GNN_REQUIRE(mode == GNN_GAT_SOFTMAX || mode == GNN_GAT_EXPNEG, GNN_ERR_BAD_ARG, "unknown mode %d", mode);
   const int HF = H * Fp;
   GNN_REQUIRE(ldw >= HF && ldo >= HF && ld_dwh >= HF, GNN_ERR_BAD_ARG, "leading dimension smaller than H*Fp");
-  cudaStream_t st = (cudaStream_t)stream;
   GatArgs a{};
   a.Wh = Wh;
   a.ldw = ldw;
@@ -765,13 +801,13 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64
   a.ld_dwh = ld_dwh;
   a.d_s = d_s;
   a.d_t = d_t;
-  a.edge_w = edge_scratch;
-  a.edge_dz = edge_scratch + nnz * H;
+  a.edge_st = edge_scratch;
+  a.tslot = edge_to_tslot;
   {
     int64_t grid = (n * H + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 16;
     grid = grid > cap ? cap : grid;
-    gat_rowdot_kernel<<<(unsigned)grid, 256, 0, st>>>(d_out, out_pre, ldo, n, H, Fp, d_rowdot);
+    gat_rowdot_kernel<T><<<(unsigned)grid, 256, 0, st>>>(d_out, out_pre, ldo, n, H, Fp, d_rowdot);
     GNN_LAUNCH_CHECK();
   }
   const int cpl = (HF + 31) / 32;
@@ -782,96 +818,105 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64
   GNN_REQUIRE((n_long == 0 || long_rows) && (n_long_t == 0 || long_rows_t) &&
                   ((n_long == 0 && n_long_t == 0) || long_threshold > 0),
               GNN_ERR_BAD_ARG, "inconsistent long-row lists");
-  // rows kernel: (CPL, W, SEG, HT) ; cols kernel: (CPL, W).  W: 1 warp per row, 4 = every row a CTA
-  // (dense graphs), 16 = the listed hub rows.
-  auto launch_rows = [&](int W, unsigned grid) -> int {
-#define GNN_ROWS(CPLV, WV)                                                                               \
-  do {                                                                                                   \
-    const size_t smem = gat_smem_bytes<WV>(a.SE, H, HF, CPLV);                                           \
-    constexpr int thrv = GatBlock<WV>::kWarps * 32;                                                      \
-    if (smem > 48 * 1024) {                                                                              \
-      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, true, 8>,                              \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, true, 1>,                              \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, true, 0>,                              \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<CPLV, WV, false, 0>,                             \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-    }                                                                                                    \
-    if (!seg) gat_bwd_rows_kernel<CPLV, WV, false, 0><<<grid, thrv, smem, st>>>(a);                      \
-    else if (H == 8) gat_bwd_rows_kernel<CPLV, WV, true, 8><<<grid, thrv, smem, st>>>(a);                \
-    else if (H == 1) gat_bwd_rows_kernel<CPLV, WV, true, 1><<<grid, thrv, smem, st>>>(a);                \
-    else gat_bwd_rows_kernel<CPLV, WV, true, 0><<<grid, thrv, smem, st>>>(a);                            \
-  } while (0)
-#define GNN_ROWS_W(CPLV)                          \
-  do {                                            \
-    if (W == 1) GNN_ROWS(CPLV, 1);                \
-    else if (W == 4) GNN_ROWS(CPLV, 4);           \
-    else GNN_ROWS(CPLV, 16);                      \
-  } while (0)
-    if (cplr == 1) GNN_ROWS_W(1);
-    else if (cplr == 2) GNN_ROWS_W(2);
-    else if (cplr == 4) GNN_ROWS_W(4);
-    else GNN_ROWS_W(8);
-#undef GNN_ROWS_W
-#undef GNN_ROWS
-    GNN_LAUNCH_CHECK();
-    return GNN_OK;
-  };
-  auto launch_cols = [&](int W, unsigned grid) -> int {
-#define GNN_COLS(CPLV)                                                                                  \
-  do {                                                                                                  \
-    if (W == 1) gat_bwd_cols_kernel<CPLV, 1><<<grid, GatBlock<1>::kWarps * 32, 0, st>>>(a);             \
-    else if (W == 4) gat_bwd_cols_kernel<CPLV, 4><<<grid, GatBlock<4>::kWarps * 32, 0, st>>>(a);        \
-    else gat_bwd_cols_kernel<CPLV, 16><<<grid, GatBlock<16>::kWarps * 32, 0, st>>>(a);                  \
-  } while (0)
-    if (cplr == 1) GNN_COLS(1);
-    else if (cplr == 2) GNN_COLS(2);
-    else if (cplr == 4) GNN_COLS(4);
-    else GNN_COLS(8);
-#undef GNN_COLS
-    GNN_LAUNCH_CHECK();
-    return GNN_OK;
-  };
-  // kernel A over the forward CSR
+  // kernel A over the forward CSR.  W: 1 warp per row, 4 = every row a CTA (dense graphs), 16 = the listed hub rows
   a.rowptr = rowptr;
   a.col = col;
   if (coop) {
-    rc = launch_rows(4, (unsigned)n);
+    rc = gat_bwd_rows_dispatch<T, 4>(a, cplr, seg, (unsigned)n, st);
     if (rc != GNN_OK) return rc;
   } else {
     if (n_long > 0) {
       a.row_list = long_rows;
-      rc = launch_rows(16, (unsigned)n_long);
+      rc = gat_bwd_rows_dispatch<T, 16>(a, cplr, seg, (unsigned)n_long, st);
       if (rc != GNN_OK) return rc;
       a.row_list = nullptr;
       a.skip_deg_gt = long_threshold;
     }
-    rc = launch_rows(1, grid1);
+    rc = gat_bwd_rows_dispatch<T, 1>(a, cplr, seg, grid1, st);
     if (rc != GNN_OK) return rc;
   }
-  // kernel B over the transposed CSR
+  // kernel B over the transposed CSR (the stash is in its own slot order when edge_to_tslot was given)
   a.rowptr = rowptr_t;
   a.col = col_t;
-  a.perm = perm_t;
+  a.perm = edge_to_tslot ? nullptr : perm_t;
   a.row_list = nullptr;
   a.skip_deg_gt = 0;
-  if (coop) {
-    rc = launch_cols(4, (unsigned)n);
+  if (coop) return gat_bwd_cols_dispatch<T, 4>(a, cplr, (unsigned)n, st);
+  if (n_long_t > 0) {
+    a.row_list = long_rows_t;
+    rc = gat_bwd_cols_dispatch<T, 16>(a, cplr, (unsigned)n_long_t, st);
     if (rc != GNN_OK) return rc;
-  } else {
-    if (n_long_t > 0) {
-      a.row_list = long_rows_t;
-      rc = launch_cols(16, (unsigned)n_long_t);
-      if (rc != GNN_OK) return rc;
-      a.row_list = nullptr;
-      a.skip_deg_gt = long_threshold;
-    }
-    rc = launch_cols(1, grid1);
-    if (rc != GNN_OK) return rc;
+    a.row_list = nullptr;
+    a.skip_deg_gt = long_threshold;
   }
+  return gat_bwd_cols_dispatch<T, 1>(a, cplr, grid1, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gnn_gat_scores_f32(const float* Wh, int64_t ldw, const float* a_src, const float* a_dst, int64_t n, int32_t H,
+                       int32_t Fp, float* s, float* t, gnn_stream_t stream) {
+  int rc = check_common(n, H, Fp);
+  if (rc != GNN_OK) return rc;
+  if (n == 0) return GNN_OK;
+  GNN_REQUIRE(Wh && a_src && a_dst && s && t, GNN_ERR_BAD_ARG, "null pointer");
+  GNN_REQUIRE(ldw >= (int64_t)H * Fp, GNN_ERR_BAD_ARG, "ldw smaller than H*Fp");
+  int64_t grid = (n * H + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  grid = grid > cap ? cap : grid;
+  gat_scores_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(Wh, ldw, a_src, a_dst, n, H, Fp, s, t);
+  GNN_LAUNCH_CHECK();
   return GNN_OK;
+}
+
+int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw, const float* s,
+                          const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode,
+                          int apply_elu, const float* col_mean, const float* edge_keep, float* out, int64_t ldo,
+                          float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
+                          int64_t long_threshold, gnn_stream_t stream) {
+  return gat_fwd_impl<float>(rowptr, col, Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode, apply_elu, col_mean, edge_keep, out,
+                             ldo, row_max, row_sum, long_rows, n_long, long_threshold, (cudaStream_t)stream);
+}
+
+int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw, const float* s,
+                           const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode,
+                           int apply_elu, const float* col_mean, const float* edge_keep, void* out, int64_t ldo,
+                           float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
+                           int64_t long_threshold, gnn_stream_t stream) {
+  return gat_fwd_impl<__nv_bfloat16>(rowptr, col, (const __nv_bfloat16*)Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode,
+                                     apply_elu, col_mean, edge_keep, (__nv_bfloat16*)out, ldo, row_max, row_sum,
+                                     long_rows, n_long, long_threshold, (cudaStream_t)stream);
+}
+
+int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
+                          const int64_t* perm_t, const int64_t* edge_to_tslot, const float* Wh, int64_t ldw,
+                          const float* s, const float* t, const float* row_max, const float* row_sum,
+                          const float* out_pre, const float* d_out, int64_t ldo, int64_t n, int32_t H, int32_t Fp,
+                          float alpha, int mode, const float* edge_keep, float* d_Wh, int64_t ld_dwh, float* d_s,
+                          float* d_t, float* d_rowdot, float* edge_scratch, int64_t nnz, const int64_t* long_rows,
+                          int64_t n_long, const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
+                          gnn_stream_t stream) {
+  return gat_bwd_impl<float>(rowptr, col, rowptr_t, col_t, perm_t, edge_to_tslot, Wh, ldw, s, t, row_max, row_sum,
+                             out_pre, d_out, ldo, n, H, Fp, alpha, mode, edge_keep, d_Wh, ld_dwh, d_s, d_t, d_rowdot,
+                             edge_scratch, nnz, long_rows, n_long, long_rows_t, n_long_t, long_threshold,
+                             (cudaStream_t)stream);
+}
+
+int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
+                           const int64_t* perm_t, const int64_t* edge_to_tslot, const void* Wh, int64_t ldw,
+                           const float* s, const float* t, const float* row_max, const float* row_sum,
+                           const void* out_pre, const void* d_out, int64_t ldo, int64_t n, int32_t H, int32_t Fp,
+                           float alpha, int mode, const float* edge_keep, void* d_Wh, int64_t ld_dwh, float* d_s,
+                           float* d_t, float* d_rowdot, float* edge_scratch, int64_t nnz, const int64_t* long_rows,
+                           int64_t n_long, const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
+                           gnn_stream_t stream) {
+  return gat_bwd_impl<__nv_bfloat16>(rowptr, col, rowptr_t, col_t, perm_t, edge_to_tslot, (const __nv_bfloat16*)Wh, ldw,
+                                     s, t, row_max, row_sum, (const __nv_bfloat16*)out_pre, (const __nv_bfloat16*)d_out,
+                                     ldo, n, H, Fp, alpha, mode, edge_keep, (__nv_bfloat16*)d_Wh, ld_dwh, d_s, d_t,
+                                     d_rowdot, edge_scratch, nnz, long_rows, n_long, long_rows_t, n_long_t,
+                                     long_threshold, (cudaStream_t)stream);
 }
 
 }  // extern "C"

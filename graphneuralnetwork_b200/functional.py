@@ -448,27 +448,61 @@ def gat_scores_raw(Wh: torch.Tensor, a_src: torch.Tensor, a_dst: torch.Tensor, H
     return s, t
 
 
+def _gat_groups(H: int, Fp: int):
+    """Column groups one kernel call can take (H_g*Fp_g <= 256, H_g <= 32): whole heads when a head fits,
+    else column tiles of ONE head.  Yields (h0, h1, f0, f1): heads [h0,h1), columns [f0,f1) of each."""
+    if Fp <= 256:
+        per = max(1, min(32, 256 // Fp))
+        for h0 in range(0, H, per):
+            yield h0, min(H, h0 + per), 0, Fp
+    else:
+        for h in range(H):
+            for f0 in range(0, Fp, 256):
+                yield h, h + 1, f0, min(Fp, f0 + 256)
+
+
 def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=0, keep=None, save_stats=False,
                 out=None):
+    """Forward of the fused attention aggregation (no autograd).  Wh fp32 or bf16 ([n, H*Fp]); s, t fp32 [n,H];
+    `out` has Wh's dtype.  Layers wider than one call's 256 columns (e.g. 8 heads x 64) are run as head groups /
+    column tiles of a head; the softmax statistics are per head, so a tiled head recomputes them per tile."""
     _require_cuda(Wh, s, t, keep)
     lib = _lib.load()
     Wh = _rowmajor(Wh)
-    s = s.contiguous()
-    t = t.contiguous()
+    if Wh.dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.GnnError(f"gat: unsupported dtype {Wh.dtype} (fp32 and bf16 only)")
+    s = s.float().contiguous()
+    t = t.float().contiguous()
     n = g.n_rows
     if Wh.shape != (n, H * Fp) or g.n_cols != n:
         raise _lib.GnnError(f"gat: Wh {tuple(Wh.shape)} does not match graph n={n}, H*Fp={H * Fp}")
     if out is None:
-        out = torch.empty((n, H * Fp), dtype=torch.float32, device=Wh.device)
-    elif out.shape != (n, H * Fp) or out.dtype != torch.float32 or out.stride(1) != 1 or not out.is_cuda:
-        raise _lib.GnnError("gat: `out` must be a CUDA fp32 [n, H*Fp] view with unit column stride")
+        out = torch.empty((n, H * Fp), dtype=Wh.dtype, device=Wh.device)
+    elif out.shape != (n, H * Fp) or out.dtype != Wh.dtype or out.stride(1) != 1 or not out.is_cuda:
+        raise _lib.GnnError("gat: `out` must be a CUDA [n, H*Fp] view of Wh's dtype with unit column stride")
     row_max = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     row_sum = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
-    col_mean = Wh.mean(dim=0).contiguous() if g.has_empty_rows() else None
+    col_mean = Wh.float().mean(dim=0).contiguous() if g.has_empty_rows() else None
     lr, thr = g.gat_long_rows()
-    _lib.check(lib.gnn_gat_fused_fwd_f32(_p(g.rowptr), _p(g.col), _p(Wh), _ld(Wh), _p(s), _p(t), n, g.nnz, H, Fp,
-                                         float(alpha), mode, elu, _p(col_mean), _p(keep), _p(out), _ld(out), _p(row_max),
-                                         _p(row_sum), _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd_f32")
+    fn = lib.gnn_gat_fused_fwd_f32 if Wh.dtype == torch.float32 else lib.gnn_gat_fused_fwd_bf16
+    groups = list(_gat_groups(H, Fp))
+    for h0, h1, f0, f1 in groups:
+        whole = len(groups) == 1
+        Hg, Fg = h1 - h0, f1 - f0
+        c0 = h0 * Fp + f0
+        sg = s if whole else s[:, h0:h1].contiguous()
+        tg = t if whole else t[:, h0:h1].contiguous()
+        kg = keep if (whole or keep is None) else keep[:, h0:h1].contiguous()
+        cm = col_mean if (whole or col_mean is None) else col_mean[c0:c0 + Hg * Fg].contiguous()
+        rm = row_max if (whole or row_max is None) else torch.empty((n, Hg), dtype=torch.float32, device=Wh.device)
+        rs = row_sum if (whole or row_sum is None) else torch.empty((n, Hg), dtype=torch.float32, device=Wh.device)
+        esz = Wh.element_size()
+        _lib.check(fn(_p(g.rowptr), _p(g.col), Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), n, g.nnz, Hg, Fg,
+                      float(alpha), mode, elu, _p(cm), _p(kg), out.data_ptr() + c0 * esz, _ld(out), _p(rm), _p(rs),
+                      _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd")
+        if not whole and save_stats:
+            row_max[:, h0:h1] = rm
+            row_sum[:, h0:h1] = rs
     return out, row_max, row_sum
 
 
@@ -478,7 +512,8 @@ class _GatFn(torch.autograd.Function):
         Wh = _rowmajor(Wh)
         out, row_max, row_sum = gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=0, keep=keep, save_stats=True)
         ctx.g, ctx.cfg = g, (H, Fp, float(alpha), mode)
-        ctx.save_for_backward(Wh, s.contiguous(), t.contiguous(), row_max, row_sum, out,
+        ctx.st_dtypes = (s.dtype, t.dtype)
+        ctx.save_for_backward(Wh, s.float().contiguous(), t.float().contiguous(), row_max, row_sum, out,
                               keep if keep is not None else torch.empty(0))
         return out
 
@@ -490,26 +525,50 @@ class _GatFn(torch.autograd.Function):
         lib = _lib.load()
         keep = keep if keep.numel() > 0 else None
         n = g.n_rows
-        d_out = d_out.contiguous()
+        d_out = d_out.to(Wh.dtype)
+        if d_out.stride(1) != 1 or d_out.stride(0) != out.stride(0):
+            d_out = d_out.contiguous()  # out is contiguous [n, H*Fp]: one leading dimension for both
         gt = g.transpose()
         dev = Wh.device
-        d_Wh = torch.empty((n, H * Fp), dtype=torch.float32, device=dev)
+        d_Wh = torch.empty((n, H * Fp), dtype=Wh.dtype, device=dev)
         d_s = torch.empty((n, H), dtype=torch.float32, device=dev)
         d_t = torch.empty((n, H), dtype=torch.float32, device=dev)
-        rowdot = torch.empty((n, H), dtype=torch.float32, device=dev)
-        scratch = torch.empty((2, max(g.nnz, 1), H), dtype=torch.float32, device=dev)
         (lr, thr), (lrt, _) = g.gat_long_rows(), gt.gat_long_rows()
-        _lib.check(lib.gnn_gat_fused_bwd_f32(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t), _p(Wh),
-                                             _ld(Wh), _p(s), _p(t), _p(row_max), _p(row_sum), _p(out), _p(d_out),
-                                             _ld(out), n, H, Fp, alpha, mode, _p(keep), _p(d_Wh), _ld(d_Wh), _p(d_s),
-                                             _p(d_t), _p(rowdot), _p(scratch), g.nnz, _p(lr), lr.numel(), _p(lrt),
-                                             lrt.numel(), thr, _stream_ptr()),
-                   "gnn_gat_fused_bwd_f32")
+        fn = lib.gnn_gat_fused_bwd_f32 if Wh.dtype == torch.float32 else lib.gnn_gat_fused_bwd_bf16
+        groups = list(_gat_groups(H, Fp))
+        esz = Wh.element_size()
+        tslot = g.perm_t_inv
+        for gi, (h0, h1, f0, f1) in enumerate(groups):
+            whole = len(groups) == 1
+            Hg, Fg = h1 - h0, f1 - f0
+            c0 = h0 * Fp + f0
+            sg = s if whole else s[:, h0:h1].contiguous()
+            tg = t if whole else t[:, h0:h1].contiguous()
+            kg = keep if (whole or keep is None) else keep[:, h0:h1].contiguous()
+            rm = row_max if whole else row_max[:, h0:h1].contiguous()
+            rs = row_sum if whole else row_sum[:, h0:h1].contiguous()
+            ds = d_s if whole else torch.empty((n, Hg), dtype=torch.float32, device=dev)
+            dt = d_t if whole else torch.empty((n, Hg), dtype=torch.float32, device=dev)
+            rowdot = torch.empty((n, Hg), dtype=torch.float32, device=dev)
+            scratch = torch.empty((max(g.nnz, 1), 2, Hg), dtype=torch.float32, device=dev)
+            _lib.check(fn(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t), _p(tslot),
+                          Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), _p(rm), _p(rs), out.data_ptr() + c0 * esz,
+                          d_out.data_ptr() + c0 * esz, _ld(out), n, Hg, Fg, alpha, mode, _p(kg),
+                          d_Wh.data_ptr() + c0 * esz, _ld(d_Wh), _p(ds), _p(dt), _p(rowdot), _p(scratch), g.nnz, _p(lr),
+                          lr.numel(), _p(lrt), lrt.numel(), thr, _stream_ptr()), "gnn_gat_fused_bwd")
+            if not whole:
+                # dz is linear in (head dot, row dot): the tiles of one head add up (first tile assigns)
+                if f0 == 0:
+                    d_s[:, h0:h1] = ds
+                    d_t[:, h0:h1] = dt
+                else:
+                    d_s[:, h0:h1] += ds
+                    d_t[:, h0:h1] += dt
         if g.has_empty_rows():
             # rows without edges output the mean of all Wh rows (GAT/models/layers.py:28-30).  Sync-free
             # (no boolean-mask indexing): this runs inside CapturedTrainStep's CUDA-graph capture
-            d_Wh += (d_out * g.empty_row_mask().unsqueeze(1)).sum(dim=0, keepdim=True) / n
-        return d_Wh, d_s, d_t, None, None, None, None, None, None
+            d_Wh += ((d_out.float() * g.empty_row_mask().unsqueeze(1)).sum(dim=0, keepdim=True) / n).to(d_Wh.dtype)
+        return d_Wh, d_s.to(ctx.st_dtypes[0]), d_t.to(ctx.st_dtypes[1]), None, None, None, None, None, None
 
 
 def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tensor, H: int, Fp: int, alpha: float,
@@ -519,7 +578,8 @@ def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tenso
 
     With gradients enabled the kernel returns the pre-activation aggregate and the ELU(s)
     are applied by torch (elementwise, outside the hot path) so autograd can differentiate
-    them; without gradients the ELU is fused into the kernel's epilogue."""
+    them; without gradients the ELU is fused into the kernel's epilogue.
+    Wh may be fp32 or bf16 (the bf16-feature variant: bf16 rows, fp32 scores / softmax / accumulation)."""
     need_grad = torch.is_grad_enabled() and (Wh.requires_grad or s.requires_grad or t.requires_grad)
     if not need_grad:
         # `out` (optional): a strided [n, H*Fp] view the kernel writes in place, e.g. one metapath's

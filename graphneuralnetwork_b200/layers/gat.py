@@ -70,8 +70,9 @@ def _fused_heads(x, adj, Ws, a_srcs, a_dsts, alpha, mode, elu, dropout, training
     Wh3 = Wh.view(-1, H, Fp)
     a_src = a_srcs[0].view(1, Fp) if H == 1 else torch.stack(list(a_srcs), dim=0)
     a_dst = a_dsts[0].view(1, Fp) if H == 1 else torch.stack(list(a_dsts), dim=0)
-    s = (Wh3 * a_src.unsqueeze(0)).sum(-1)  # [N,H] = Wh_i·a[:F']
-    t = (Wh3 * a_dst.unsqueeze(0)).sum(-1)  # [N,H] = Wh_j·a[F':]
+    # scores are fp32 even for bf16 features (the softmax statistics live in fp32)
+    s = (Wh3.float() * a_src.float().unsqueeze(0)).sum(-1)  # [N,H] = Wh_i·a[:F']
+    t = (Wh3.float() * a_dst.float().unsqueeze(0)).sum(-1)  # [N,H] = Wh_j·a[F':]
     keep = None
     if training and dropout > 0.0:
         keep = attention_keep_mask(g, H, dropout)  # post-softmax dropout, layers.py:31

@@ -143,6 +143,10 @@ class GraphSage(nn.Module):
         assert len(node_id_blocks) == L + 1
         fused = (not (torch.is_grad_enabled() and table.requires_grad)) and L <= 4 \
             and layer0.aggr_neighbor_method in ("mean", "sum", "max")
+        no_grad = not (torch.is_grad_enabled() and (table.requires_grad or layer0.weight.requires_grad))
+        if fused and no_grad and 2 * L <= 4 and layer0.aggr_hidden_method == "sum" and not layer0.aggregator.use_bias \
+                and table.dtype == torch.float32:
+            return self._upper_layers(self._layer0_one_launch_one_gemm(table, node_id_blocks))
         if fused:
             # every hop of layer 0 aggregates from the same table: ONE launch for all of them
             pooled = gather_reduce_multi_raw(table, [(node_id_blocks[hop + 1], node_id_blocks[hop].numel(), fan[hop])
@@ -151,6 +155,47 @@ class GraphSage(nn.Module):
             pooled = [SampledBlock(table, node_id_blocks[hop + 1], fan[hop]) for hop in range(L)]
         hidden = [layer0(table.index_select(0, node_id_blocks[hop].to(torch.int64)), pooled[hop]) for hop in range(L)]
         return self._upper_layers(hidden)
+
+    def _layer0_one_launch_one_gemm(self, table, node_id_blocks):
+        """Inference form of layer 0 for all hops at once (SageGCN.py:23-27 on every hop of GraphSage.py:24-27):
+        ONE gather launch writes, for every source of every hop, its own feature row (a fanout-1 block — the
+        reference's `src_node_features` gather, data_utils.py:64) and the reduce of its sampled neighbours side
+        by side into one `[Σ n_hop, 2·ld]` operand, and ONE `[self ‖ pooled]·[W_self ; W_agg]` product (K = 2·F)
+        replaces the two products + add per hop.  Same arithmetic, one accumulation order change: the two
+        K-sums are one K-sum (fp32 re-association only)."""
+        L, fan, layer0 = self.num_layers, self.num_neighbors_list, self.gcn[0]
+        F_in, H = layer0.input_dim, layer0.hidden_dim
+        ld = (F_in + 3) // 4 * 4
+        n_hop = [node_id_blocks[hop].numel() for hop in range(L)]
+        total = sum(n_hop)
+        key = (total, table.device)
+        buf = getattr(self, "_l0_buf", None)
+        if buf is None or buf[0] != key:
+            # pad columns stay zero for the lifetime of the buffer: the gather writes F_in columns per row only
+            Z = torch.zeros((total, 2 * ld), dtype=torch.float32, device=table.device)
+            Wc = torch.zeros((2 * ld, H), dtype=torch.float32, device=table.device)
+            self._l0_buf = buf = (key, Z, Wc)
+        _, Z, Wc = buf
+        Wc[:F_in].copy_(layer0.weight)
+        Wc[ld:ld + F_in].copy_(layer0.aggregator.weight)
+        blocks, outs, row = [], [], 0
+        for hop in range(L):
+            n = n_hop[hop]
+            blocks += [(node_id_blocks[hop + 1], n, fan[hop]), (node_id_blocks[hop], n, 1)]
+            outs += [Z[row:row + n, ld:ld + F_in], Z[row:row + n, :F_in]]
+            row += n
+        # longest block first: the short ones ride in its shadow
+        order = sorted(range(len(blocks)), key=lambda i: -blocks[i][1] * blocks[i][2])
+        gather_reduce_multi_raw(table, [blocks[i] for i in order], layer0.aggr_neighbor_method,
+                                outs=[outs[i] for i in order])
+        hidden = torch.mm(Z, Wc)
+        if layer0.activation:
+            hidden = layer0.activation(hidden)
+        out, row = [], 0
+        for n in n_hop:
+            out.append(hidden[row:row + n])
+            row += n
+        return out
 
     def extra_repr(self):
         return 'in_features={}, num_neighbors_list={}'.format(self.input_dim, self.num_neighbors_list)

@@ -419,11 +419,14 @@ class PartitionedSpmm:
       dedicated_sms  > 0: vector mover on that many SMs of its own (each CTA claims 200 KB of shared memory
                      and the concurrent P1 asks for 28 KB so that the block scheduler keeps them apart)
       timeout_ms     bound of every flag wait (a lost peer must not hang the GPU)
+      fused_signal   p2p + TMA mover: all waves of a step in ONE launch, the arrival flags raised from inside
+                     the kernel by the last warp that finishes a wave (gnn_halo_push_waves); False = one
+                     mover launch + one signal launch per wave
     """
 
     def __init__(self, plan: HaloPlan, F: int, device, group=None, transport: str = "p2p",
                  dtype: torch.dtype = torch.float32, mover: str = "auto", mover_ctas: int = 0, mover_warps: int = 0,
-                 dedicated_sms: int = 0, timeout_ms: int = 20000):
+                 dedicated_sms: int = 0, timeout_ms: int = 20000, fused_signal: bool = True):
         from .graph import CSRGraph
         if dtype not in _TORCH_TYPESTR:
             raise _lib.GnnError(f"PartitionedSpmm: unsupported dtype {dtype}")
@@ -441,6 +444,7 @@ class PartitionedSpmm:
         self.ld = self.F if self.F % per16 == 0 else (self.F + per16 - 1) // per16 * per16
         self.A_loc = CSRGraph(plan.rowptr_loc, plan.col_loc, plan.val_loc, n_loc, n_loc)
         self._cons = {}
+        self._wave_table = None
         self._t_loc = self._t_rem = self._R = None
         self._fstep = self._bstep = 0
         self._bufs: List[_PeerBuffer] = []
@@ -458,6 +462,11 @@ class PartitionedSpmm:
             self._flags = _PeerBuffer(4 * 32 * 4, plan.rank, plan.world, group)  # arrive/consumed x fwd/bwd
             self._bufs += [self._halo_buf, self._flags]
             self.halo = self._view(self._halo_buf.own, n_halo, self.ld)[:, :self.F]
+            self._wave_table = None
+            R = _lib.load().gnn_halo_rows_per_stage(self.F * self.elem)
+            if (self.transport == "p2p" and fused_signal and self.mover != 1 and self.dedicated == 0 and R > 0
+                    and self.ld == self.F):
+                self._wave_table = self._build_wave_table(R)
             if self.transport == "ce":
                 self._sendbuf = torch.empty((max(self._send_off[-1], 1), self.ld), dtype=dtype, device=self.dev)
                 self._copy_streams = [torch.cuda.Stream(device=self.dev, priority=-1) for _ in range(4)]
@@ -467,6 +476,24 @@ class PartitionedSpmm:
             self.halo = torch.empty((n_halo, self.F), dtype=dtype, device=self.dev)
             self._sendbuf = torch.empty((max(int(plan.send_rows.numel()), 1), self.F), dtype=dtype, device=self.dev)
         self.halo_bytes_received = plan.n_halo * self.F * self.elem
+
+    def _build_wave_table(self, R: int):
+        """Device segment table of gnn_halo_push_waves: segments sorted by wave, peers in rotated order."""
+        plan, W = self.plan, self.plan.world
+        row_bytes = self.ld * self.elem
+        rows, chunk = [], 0
+        for w in range(plan.waves):
+            for s_i in range(1, W):
+                q = (plan.rank + s_i) % W
+                n = plan.send_wave_counts[q][w]
+                if n == 0:
+                    continue
+                b = self._wave_cum_send[q][w]
+                rows.append([self._send_off[q] + b, n, self._halo_buf.ptrs[q] + (plan.dst_off[q] + b) * row_bytes, chunk, w])
+                chunk += (n + R - 1) // R
+        table = torch.tensor(rows if rows else [[0, 0, 0, 0, 0]], dtype=torch.int64, device=self.dev)
+        done = torch.zeros(max(plan.waves, 1), dtype=torch.int32, device=self.dev)
+        return table, len(rows), chunk, done
 
     # -- helpers ---------------------------------------------------------------------------
     def _view(self, ptr: int, rows: int, ld: int) -> torch.Tensor:
@@ -567,6 +594,16 @@ class PartitionedSpmm:
             W = plan.world
             self._push(X, [self._sendbuf.data_ptr()] * W, self._send_off[:W], plan.send_counts, self._send_off[:W],
                        self.ld, plan.send_rows, stream, force_vector_shared=True)
+        if self._wave_table is not None:
+            table, n_segs, n_chunks, done = self._wave_table
+            o = _lib.HaloOpts()
+            o.struct_size = C.sizeof(_lib.HaloOpts)
+            o.ctas, o.warps_per_cta = self.mover_ctas, self.mover_warps
+            _lib.check(_lib.load().gnn_halo_push_waves(
+                X.data_ptr(), X.stride(0), self.F, self.elem, plan.send_rows.data_ptr(), table.data_ptr(), n_segs, K,
+                n_chunks, done.data_ptr(), self._flag_ptrs(0), plan.world, plan.rank, (s * K) & 0xFFFFFFFF, C.byref(o),
+                stream.cuda_stream), "gnn_halo_push_waves")
+            return
         for w in range(K):
             self._exchange_wave(X, w, stream)
             self._signal(0, s * K + w + 1, stream)

@@ -162,7 +162,8 @@ def spmm_check_rows(csr: CSRGraph, n_samples: int, seed: int) -> torch.Tensor:
     return torch.unique(torch.cat([rows, hubs]))
 
 
-def spmm_sampled_reference(csr: CSRGraph, rows: torch.Tensor, F: int, dtype=torch.float32, salt: int = 0) -> torch.Tensor:
+def spmm_sampled_reference(csr: CSRGraph, rows: torch.Tensor, F: int, dtype=torch.float32, salt: int = 0,
+                           with_abs: bool = False):
     """float64 rows `rows` of Â·X where X = hashed_features of the GLOBAL column ids held in `csr.col`
     (recomputed here, no communication) — torch float64 arithmetic in plain CSR order."""
     from .partition import select_rows
@@ -173,4 +174,9 @@ def spmm_sampled_reference(csr: CSRGraph, rows: torch.Tensor, F: int, dtype=torc
     owner = torch.repeat_interleave(torch.arange(rows.numel(), device=rows.device), rp[1:] - rp[:-1])
     ref = torch.zeros((rows.numel(), F), dtype=torch.float64, device=rows.device)
     ref.index_add_(0, owner, src)
+    if with_abs:
+        # Σ_j |a_ij x_jf|: the scale an fp32 sum's rounding error is relative to (a hub row adds 10^5 terms)
+        mag = torch.zeros_like(ref)
+        mag.index_add_(0, owner, src.abs())
+        return ref, mag
     return ref

@@ -294,19 +294,47 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
  *   d_Wh [n,H*Fp] and d_t [n,H] (row-parallel over the transposed CSR: rowptr_t/col_t,
  *   with perm_t mapping transposed slots to the forward edge slots of edge_scratch).
  * Both passes are ordered reductions — the edge-gradient SDDMM (layers.py:59-61) and the
- * transpose SpMM (layers.py:63) without the dense N×N intermediate and without atomics. */
+ * transpose SpMM (layers.py:63) without the dense N×N intermediate and without atomics.
+ * edge_to_tslot (the inverse of perm_t: forward edge slot -> transposed slot; CSRGraph.perm_t_inv):
+ * when given, the first pass writes its per-edge stash (attention weight, dz) straight into the
+ * order the second pass walks, which then streams it instead of chasing perm_t with one random
+ * 32-byte read per edge (r01: 26.5 ms backward vs 7.6 ms forward on the full Reddit shape). */
 int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
                           const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t,
+                          const int64_t* edge_to_tslot /*nullable [nnz]: inverse of perm_t*/,
                           const float* Wh, int64_t ldw, const float* s, const float* t,
                           const float* row_max, const float* row_sum,
                           const float* out_pre, const float* d_out, int64_t ldo,
                           int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
                           const float* edge_keep,
                           float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot /*[n,H] scratch*/,
-                          float* edge_scratch /*[2,nnz,H]: per-edge attention weight and dz*/, int64_t nnz,
+                          float* edge_scratch /*[nnz,2,H]: per-edge attention weight and dz*/, int64_t nnz,
                           const int64_t* long_rows, int64_t n_long /*forward CSR*/,
                           const int64_t* long_rows_t, int64_t n_long_t /*transposed CSR*/, int64_t long_threshold,
                           gnn_stream_t stream);
+/* bf16-feature variants (north_star: "bf16-feature variants within 1e-2"): Wh, out, out_pre, d_out and
+ * d_Wh are bf16; the scores s/t, the softmax statistics, the per-edge stash and every accumulation
+ * stay fp32.  Same reference call site (GAT/models/layers.py:22-37). */
+int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw,
+                           const float* s, const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp,
+                           float alpha, int mode, int apply_elu, const float* col_mean,
+                           const float* edge_keep, void* out, int64_t ldo,
+                           float* row_max, float* row_sum,
+                           const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
+                           gnn_stream_t stream);
+int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col,
+                           const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t,
+                           const int64_t* edge_to_tslot,
+                           const void* Wh, int64_t ldw, const float* s, const float* t,
+                           const float* row_max, const float* row_sum,
+                           const void* out_pre, const void* d_out, int64_t ldo,
+                           int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
+                           const float* edge_keep,
+                           void* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot,
+                           float* edge_scratch, int64_t nnz,
+                           const int64_t* long_rows, int64_t n_long,
+                           const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
+                           gnn_stream_t stream);
 
 /* ---- synthetic graphs for the benchmark shapes ---------------- */
 /* Power-law CSR generated on the device, row by row, from a counter-based hash of
@@ -362,6 +390,20 @@ int gnn_halo_push(const void* X, int64_t ldx, int32_t F, int32_t elem_size,
                   const int64_t* seg_begin_host /*[n_peers]*/, const int64_t* seg_rows_host /*[n_peers]*/,
                   void* const* peer_dst_host /*[n_peers] device ptrs*/, const int64_t* dst_row_host /*[n_peers]*/,
                   int64_t ld_dst, int32_t n_peers, const gnn_halo_opts* opts, gnn_stream_t stream);
+
+/* All waves of a step in ONE launch of the TMA mover, the arrival flags raised from inside the kernel:
+ * seg_table_dev is a device int64 [n_segs][5] table (first send_rows entry | rows | destination ADDRESS
+ * of the segment's first row (contiguous rows of F*elem_size bytes) | first chunk id | wave), sorted by
+ * wave; a chunk is gnn_halo_rows_per_stage(F*elem_size) rows and never straddles a segment; n_chunks is
+ * the total.  When the last warp of the grid has finished wave w (own bulk stores performed, fenced) it
+ * stores flag_base + w + 1 into slot my_slot of every peer's flag array (gnn_peer_wait on the other side).
+ * wave_done_dev: n_waves device counters (scratch, reset by the call).  opts: ctas / warps_per_cta. */
+int gnn_halo_rows_per_stage(int32_t row_bytes);
+int gnn_halo_push_waves(const void* X, int64_t ldx, int32_t F, int32_t elem_size, const int32_t* send_rows /*nullable*/,
+                        const int64_t* seg_table_dev, int32_t n_segs, int32_t n_waves, int64_t n_chunks,
+                        uint32_t* wave_done_dev, uint32_t* const* peer_flags_host /*[n_peers] device ptrs*/,
+                        int32_t n_peers, int32_t my_slot, uint32_t flag_base, const gnn_halo_opts* opts,
+                        gnn_stream_t stream);
 
 /* Per-peer arrival flags: monotonic uint32 counters living in peer memory (one array of n_peers slots
  * per rank, slot p written by rank p).  gnn_peer_signal stores `value` into slot my_slot of every

@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference modules from /root/reference (build container only).
+"""Import the UNMODIFIED reference modules: from /root/reference in the build container, from the
+verbatim snapshot in the git-ignored oracle/_ref/ (tools/make_ref_snapshot.py) on the GPU box.
 
-Used by tests/test_oracle_vs_reference.py and tests/golden/make_golden.py to pin the
-oracle restatement; never at GPU-test, smoke or bench time (the GPU box has no
-/root/reference).  The reference folders reuse top-level module names (`models`,
+Used by tests/test_oracle_vs_reference_live.py and tests/golden/make_golden.py to pin the oracle
+restatement, by tests/test_reference_substitution_gpu.py (the reference's own models / loops with the
+drop-in layers substituted) and by bench.py's `--impl reference` arm.  Test / baseline infrastructure:
+the product package never imports it.  The reference folders reuse top-level module names (`models`,
 `data_utils`, `utils`, ...) so each folder is imported in isolation (SURVEY.md §8c shims).
 """
 import contextlib
@@ -12,7 +14,18 @@ import os
 import sys
 import warnings
 
-REF_ROOT = os.environ.get("GNN_REFERENCE_ROOT", "/root/reference")
+_SNAPSHOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the verbatim snapshot tools/make_ref_snapshot.py
+    left in the git-ignored oracle/_ref/ (it travels with the gpurun snapshot like the built .so)."""
+    if os.path.isdir("/root/reference/GCN"):
+        return "/root/reference"
+    return _SNAPSHOT
+
+
+REF_ROOT = os.environ.get("GNN_REFERENCE_ROOT") or _default_root()
 _SHARED_NAMES = ("models", "data_utils", "sample_utils", "graph_utils", "utils", "train_utils", "train_eval",
                  "GCN", "GraphSAGE")
 
@@ -104,3 +117,16 @@ def han():
 def gatne():
     """(GATNE_Pytorch/models/GATNE.py, GATNE/models/GATNE.py) — both files import torch only."""
     return load_file("GATNE_Pytorch/models/GATNE.py", "ref_gatne_pytorch"), load_file("GATNE/models/GATNE.py", "ref_gatne_v1")
+
+
+def gcn_train_eval():
+    """GCN/train_eval.py (the reference training loop: Adam, cross-entropy, one full-graph step per epoch)."""
+    with folder("GCN"):
+        return load_file("GCN/train_eval.py", "ref_gcn_train_eval")
+
+
+def sage_data_utils():
+    """GraphSAGE_Pytorch/data_utils.py (collate_fn: the sampler + the python-list feature gather)."""
+    with folder("GraphSAGE_Pytorch"):
+        importlib.import_module("sample_utils")
+        return load_file("GraphSAGE_Pytorch/data_utils.py", "ref_sage_data_utils")

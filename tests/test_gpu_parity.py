@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import assert_close_elementwise, load_golden, rel_err
 from graphneuralnetwork_b200 import _lib, functional as Fn, layers, synthetic as S
 from graphneuralnetwork_b200.graph import CSRGraph, index_block_transpose
 from oracle import gat as ogat
@@ -136,6 +136,7 @@ def test_spmm_f32_shapes(lib, F):
     Y = Fn.spmm_raw(csr, cuda(X))
     ref = ogcn.spmm_f64(rowptr, col, val, X)
     assert rel_err(Y.cpu().numpy(), ref) < TOL32
+    assert_close_elementwise(Y.cpu().numpy(), ref)  # every element, not only the max norm
     # unplanned path (one warp walks the long row) gives the same result
     Y2 = Fn.spmm_raw(csr, cuda(X), planned=False)
     assert rel_err(Y2.cpu().numpy(), ref) < TOL32
@@ -296,6 +297,7 @@ def test_gather_reduce_f32(lib, F, fanout, idx_dtype, reduce):
     padded = Fn.pad_table(cuda(table))  # 16-byte aligned rows -> TMA bulk-copy path when F*4 >= 256
     out = Fn.gather_reduce_raw(padded, cuda(idx).to(idx_dtype), n_src, fanout, reduce)
     assert rel_err(out.cpu().numpy(), ref) < TOL32
+    assert_close_elementwise(out.cpu().numpy(), ref)
     raw = Fn.gather_reduce_raw(cuda(table), cuda(idx).to(idx_dtype), n_src, fanout, reduce)  # unpadded -> vector loads
     assert rel_err(raw.cpu().numpy(), ref) < TOL32
 
@@ -522,6 +524,34 @@ def test_captured_graphsage_runner(lib):
     assert not torch.equal(ids1[2], sampling.ids[2])  # a fresh draw on every replay
 
 
+def test_forward_sampled_one_launch_one_gemm_matches_reference_call_surface(lib):
+    """Inference fast path (self rows as fanout-1 blocks of the same gather launch, one [self ‖ pooled] GEMM)
+    == the reference call surface on the pre-gathered tensors (GraphSage.py:18-30), within 1e-5; the pad
+    columns of the fused operand stay zero (they meet zero weight rows in the product)."""
+    g = torch.Generator().manual_seed(3)
+    n, F_in, B, fan = 5000, 602, 64, [7, 4]
+    table = Fn.pad_table(torch.randn(n, F_in, generator=g).to(DEV))
+    torch.manual_seed(1)
+    model = layers.GraphSage(F_in, [128, 41], fan).to(DEV).eval()
+    blocks = [torch.randint(0, n, (s,), generator=g, dtype=torch.int32).to(DEV) for s in (B, B * 7, B * 28)]
+    before = lib.gnn_launch_count()
+    with torch.no_grad():
+        fast = model.forward_sampled(table, blocks)
+        launches = lib.gnn_launch_count() - before
+        ref = model([table[b.long()].contiguous() for b in blocks])
+    assert launches == 2  # layer-0 gather (4 blocks) + the layer-1 mean
+    assert rel_err(fast.cpu().numpy(), ref.cpu().numpy()) < TOL32
+    assert torch.allclose(fast, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
+    _, Z, Wc = model._l0_buf
+    assert float(Z[:, 602:604].abs().max()) == 0.0 and float(Z[:, 1206:].abs().max()) == 0.0
+    assert torch.equal(Z[:B, :602], table[blocks[0].long()])  # fanout-1 block = the rows themselves, bit for bit
+    # training still takes the autograd path and agrees
+    model.train()
+    out = model.forward_sampled(table, blocks)
+    out.sum().backward()
+    assert rel_err(out.detach().cpu().numpy(), ref.cpu().numpy()) < TOL32 and model.gcn[0].weight.grad is not None
+
+
 def test_sampler_is_uniform(lib):
     """Marginal frequencies over many independent sources of the same node: both branches."""
     deg = 50
@@ -626,11 +656,120 @@ def test_gat_fused_shapes_vs_f64(lib, H, Fp, deg):
         ref = ogat.edge_attention_f64(rowptr, col, Wh, s, t, 0.2, mode=mode).reshape(n, H * Fp)
         out = Fn.gat_fwd_raw(csr, cuda(Wh).view(n, -1), cuda(s), cuda(t), H, Fp, 0.2, mode=mode)[0]
         assert rel_err(out.cpu().numpy(), ref) < TOL32
+        assert_close_elementwise(out.cpu().numpy(), ref)
     a_src = rng.standard_normal((H, Fp)).astype(np.float32)
     a_dst = rng.standard_normal((H, Fp)).astype(np.float32)
     s2, t2 = Fn.gat_scores_raw(cuda(Wh).view(n, -1), cuda(a_src), cuda(a_dst), H, Fp)
     assert rel_err(s2.cpu().numpy(), np.einsum("nhf,hf->nh", Wh.astype(np.float64), a_src)) < TOL32
     assert rel_err(t2.cpu().numpy(), np.einsum("nhf,hf->nh", Wh.astype(np.float64), a_dst)) < TOL32
+
+
+def _gat_autograd_f64(rowptr, col, Wh, s, t, alpha, mode, G):
+    """float64 torch autograd of the edge attention on CPU: returns out and the gradients of sum(out*G)."""
+    n, H, Fp = Wh.shape
+    Wh_t = torch.tensor(Wh, dtype=torch.float64, requires_grad=True)
+    s_t = torch.tensor(s, dtype=torch.float64, requires_grad=True)
+    t_t = torch.tensor(t, dtype=torch.float64, requires_grad=True)
+    rows = torch.repeat_interleave(torch.arange(n), torch.from_numpy(np.diff(rowptr)))
+    cols = torch.from_numpy(col.astype(np.int64))
+    z = s_t[rows] + t_t[cols]
+    e = torch.nn.functional.leaky_relu(z, alpha)
+    if mode == 1:
+        w = torch.exp(-e)
+    else:
+        m = torch.full((n, H), -float("inf"), dtype=torch.float64).scatter_reduce(0, rows[:, None].expand(-1, H), e.detach(),
+                                                                                  "amax", include_self=True)
+        w = torch.exp(e - m[rows])
+    den = torch.zeros((n, H), dtype=torch.float64).index_add(0, rows, w)
+    att = w / den[rows]
+    out = torch.zeros((n, H, Fp), dtype=torch.float64).index_add(0, rows, att[:, :, None] * Wh_t[cols])
+    empty = torch.from_numpy(np.diff(rowptr) == 0)
+    # a row without edges is the uniform mean over ALL nodes (GAT/models/layers.py:28-30)
+    out = torch.where(empty[:, None, None], Wh_t.mean(dim=0, keepdim=True).expand(n, H, Fp), out)
+    (out * torch.from_numpy(G).double().view(n, H, Fp)).sum().backward()
+    return out.detach().numpy().reshape(n, H * Fp), Wh_t.grad.numpy().reshape(n, H * Fp), s_t.grad.numpy(), t_t.grad.numpy()
+
+
+@pytest.mark.parametrize("H,Fp,deg,dtype", [(8, 64, 12, torch.float32), (1, 300, 20, torch.float32), (2, 520, 9, torch.float32),
+                                            (40, 8, 15, torch.float32), (8, 8, 40, torch.bfloat16),
+                                            (1, 7, 30, torch.bfloat16), (8, 64, 10, torch.bfloat16)])
+def test_gat_wide_layers_and_bf16_forward_backward_vs_f64(lib, H, Fp, deg, dtype):
+    """Layers wider than one call's 256 columns (8 heads x 64 = 512; one head of 300 / 520 columns; 40 heads)
+    run as head groups / column tiles, and the bf16-feature variant (bf16 Wh / out / gradients, fp32 scores,
+    softmax and accumulation): forward and all three gradients against float64 autograd on the same
+    (rounded) inputs — 1e-5 for fp32, 1e-2 for bf16 (north_star)."""
+    n = 500
+    rowptr, col, _ = random_csr(n, n, deg, seed=H * 1000 + Fp, empty_every=n + 1)
+    rng = np.random.default_rng(H + Fp)
+    Wh = rng.standard_normal((n, H, Fp)).astype(np.float32)
+    G = rng.standard_normal((n, H * Fp)).astype(np.float32)
+    if dtype == torch.bfloat16:
+        Wh = torch.from_numpy(Wh).bfloat16().float().numpy()
+        G = torch.from_numpy(G).bfloat16().float().numpy()
+    s = rng.standard_normal((n, H)).astype(np.float32)
+    t = rng.standard_normal((n, H)).astype(np.float32)
+    csr = CSRGraph(cuda(rowptr), cuda(col), None, n, n)
+    tol = TOL32 if dtype == torch.float32 else TOLBF
+    for mode in (0, 1):
+        ref, dWh, ds, dt = _gat_autograd_f64(rowptr, col, Wh, s, t, 0.2, mode, G)
+        Wh_d = cuda(Wh).view(n, -1).to(dtype).requires_grad_(True)
+        s_d, t_d = cuda(s).requires_grad_(True), cuda(t).requires_grad_(True)
+        out = Fn.gat_aggregate(csr, Wh_d, s_d, t_d, H, Fp, 0.2, mode=mode)
+        assert out.dtype == dtype
+        assert rel_err(out.detach().float().cpu().numpy(), ref) < tol
+        out.backward(cuda(G).to(dtype))
+        assert Wh_d.grad.dtype == dtype
+        assert rel_err(Wh_d.grad.float().cpu().numpy(), dWh) < tol
+        assert rel_err(s_d.grad.cpu().numpy(), ds) < (2e-5 if dtype == torch.float32 else tol)
+        assert rel_err(t_d.grad.cpu().numpy(), dt) < (2e-5 if dtype == torch.float32 else tol)
+        with torch.no_grad():  # inference path with the fused ELU epilogue
+            o2 = Fn.gat_aggregate(csr, Wh_d.detach(), s_d.detach(), t_d.detach(), H, Fp, 0.2, mode=mode, elu=1)
+        want = np.where(ref > 0, ref, np.expm1(ref))
+        assert rel_err(o2.float().cpu().numpy(), want) < tol
+
+
+def test_gat_layer_8_heads_by_64_hidden(lib):
+    """8 heads x 64 hidden = 512 columns used to raise 'split the heads' in the drop-in GAT."""
+    n, nfeat = 200, 40
+    rng = np.random.default_rng(9)
+    adj = (rng.random((n, n)) < 0.05).astype(np.float32)
+    adj[np.arange(n), np.arange(n)] = 1
+    X = rng.standard_normal((n, nfeat)).astype(np.float32)
+    torch.manual_seed(4)
+    model = layers.GAT(nfeat, 64, 300, 0.0, 0.2, 8)  # out_att: one head of 300 classes (> 256 columns)
+    cpu_params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = ogat.gat_model(torch.from_numpy(X), cpu_params, torch.from_numpy(adj), 0.2, 8)
+    ref.sum().backward()
+    model = model.to(DEV).train()
+    out = model(cuda(X), cuda(adj))
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL32
+    out.sum().backward()
+    for name, p in model.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), cpu_params[name].grad.numpy()) < 2e-5, name
+
+
+def test_coo_pattern_cache_identity_guard(lib):
+    """the COO pattern cache must not serve a stale CSR when a NEW indices tensor of equal
+    shape lands on the same allocator block (the reference rebuilds `adj.nonzero().t()` every forward)."""
+    from graphneuralnetwork_b200.layers import gat as gat_layers
+    n = 64
+    b = torch.randn(n, 8, device=DEV)
+
+    def product(seed):
+        g = torch.Generator().manual_seed(seed)
+        idx = torch.randint(0, n, (2, 500), generator=g).to(DEV)
+        vals = torch.randn(500, generator=g).to(DEV)
+        ptr = idx.data_ptr()
+        out = gat_layers.SpecialSpmmFunction.apply(idx, vals, torch.Size([n, n]), b)
+        ref = torch.sparse_coo_tensor(idx, vals, (n, n)).to_dense() @ b
+        return out, ref, ptr
+
+    ptrs = set()
+    for seed in range(6):  # each iteration frees its indices; the caching allocator hands the block back
+        out, ref, ptr = product(seed)
+        ptrs.add(ptr)
+        assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4), seed
+    assert len(ptrs) < 6  # the address WAS reused at least once: the guard, not luck, kept the results right
 
 
 @pytest.mark.parametrize("nhid,density", [(8, 0.6), (5, 0.6), (8, 0.02), (5, 0.02), (16, 0.5)])

@@ -101,18 +101,20 @@ def bench_gat(args):
         csr = S.powerlaw_csr(n, mean_deg, seed=0, device=DEV, with_values=False, max_degree=min(n - 1, 20000),
                              skew=1.0)
         H, Fp = 8, 8
-        Wh = torch.randn(n, H * Fp, device=DEV, requires_grad=True)
+        fdt = torch.bfloat16 if args.bf16 else torch.float32
+        Wh = torch.randn(n, H * Fp, device=DEV).to(fdt).requires_grad_(True)
         s = torch.randn(n, H, device=DEV, requires_grad=True)
         t = torch.randn(n, H, device=DEV, requires_grad=True)
         med, best = timeit(lambda: Fn.gat_fwd_raw(csr, Wh.detach(), s.detach(), t.detach(), H, Fp, 0.2, elu=1), reps=args.reps)
-        B = csr.nnz * (4 + H * Fp * 4 + H * 4) + n * (H * 4 + H * Fp * 4) + (n + 1) * 8
-        emit(bench="gat_fwd", graph=tag, n=n, nnz=csr.nnz, ms=med, ms_best=best, gather_gbs=B / med / 1e6,
+        es = Wh.element_size()
+        B = csr.nnz * (4 + H * Fp * es + H * 4) + n * (H * 4 + H * Fp * es) + (n + 1) * 8
+        emit(bench="gat_fwd", graph=tag, dtype=str(fdt), n=n, nnz=csr.nnz, ms=med, ms_best=best, gather_gbs=B / med / 1e6,
              edges_per_s=csr.nnz / med * 1e3)
         csr.transpose()
         out = Fn.gat_aggregate(csr, Wh, s, t, H, Fp, 0.2)
         g = torch.randn_like(out)
         med, best = timeit(lambda: torch.autograd.grad(out, (Wh, s, t), g, retain_graph=True), reps=args.reps)
-        emit(bench="gat_bwd", graph=tag, n=n, nnz=csr.nnz, ms=med, ms_best=best, edges_per_s=csr.nnz / med * 1e3)
+        emit(bench="gat_bwd", graph=tag, dtype=str(fdt), n=n, nnz=csr.nnz, ms=med, ms_best=best, edges_per_s=csr.nnz / med * 1e3)
 
 
 if __name__ == "__main__":

@@ -51,7 +51,8 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--transports", nargs="+", default=["p2p"])
     ap.add_argument("--configs", nargs="+", default=["4:auto:tma:0:0"],
-                    help="waves:two_pass_chunks(auto|int):mover(tma|vector):ctas:warps[:dedicated_sms]")
+                    help="waves:two_pass_chunks(auto|int):mover(tma|vector):ctas:warps[:dedicated_sms[:sep]] (sep = one mover "
+                         "launch per wave instead of the single-launch wave mover)")
     ap.add_argument("--backward", action="store_true")
     ap.add_argument("--phases", action="store_true")
     ap.add_argument("--full-check", action="store_true", help="small graphs: compare every row with a 1-GPU SpMM")
@@ -107,6 +108,7 @@ def main():
             K, c0 = int(parts[0]), (None if parts[1] == "auto" else int(parts[1]))
             mover, ctas, warps = parts[2], int(parts[3]), int(parts[4])
             dedicated = int(parts[5]) if len(parts) > 5 else 0
+            fused = (parts[6] != "sep") if len(parts) > 6 else True
             if transport == "nccl":
                 K, c0 = 1, (1 if c0 is None else min(c0, 1))
             key = (K, c0)
@@ -118,7 +120,7 @@ def main():
                                              two_pass_chunks=c0, F=a.F, elem_size=X.element_size())
             plan = plans[key]
             op = PartitionedSpmm(plan, a.F, dev, transport=transport, dtype=dtype, mover=mover, mover_ctas=ctas,
-                                 mover_warps=warps, dedicated_sms=dedicated)
+                                 mover_warps=warps, dedicated_sms=dedicated, fused_signal=fused)
             ms = timed(lambda: op.forward(X, out=Y), a.steps, a.warmup)
             op.check_status()
             err = reduce_max(float((Y[rows].double() - ref_rows).abs().max().item()) / max(ref_scale, 1e-30))
@@ -131,7 +133,7 @@ def main():
                 allstats = [stats]
             line = {"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F, "dtype": a.dtype,
                     "transport": transport, "waves": K, "two_pass_chunks": [int(s[3]) for s in allstats],
-                    "mover": mover, "mover_ctas": ctas, "mover_warps": warps, "dedicated_sms": dedicated,
+                    "mover": mover, "fused_signal": bool(op._wave_table is not None) if world > 1 else None, "mover_ctas": ctas, "mover_warps": warps, "dedicated_sms": dedicated,
                     "ms": ms, "edges_per_s": nnz_total / ms * 1e3, "max_rel_err_sampled_rows": err, "ok": err < tol,
                     "p_local": a.p_local, "window": a.window,
                     "halo_gb_recv_max": max(int(s[0]) for s in allstats) * a.F * X.element_size() / 1e9,
