@@ -46,6 +46,7 @@ static std::map<std::string, int>& tune_map() {
       {"spmm.rows_per_team", 0},  // >0 overrides the caller's rows_per_team (tuning sweeps)
       {"spmm.team_edges", 512},   // host plan: edges one team should hold (graph.py rows_per_team)
       {"gat.stage_edges", 128},  // logits staged per warp pass
+      {"gat.bwd_stage_edges", 64},  // edges staged per warp pass of the backward kernels
       {"gat.coop_min_avg_deg", 256},  // nnz/n at which every row gets a whole CTA
       {"gat.long_row", 1024},        // rows above this get a CTA in the otherwise warp-per-row schedule
   };

@@ -14,9 +14,9 @@
 // Scheduling: W = 1 -> one warp per row (low-degree graphs: Cora); W = 4 -> one CTA per row,
 // the warps take alternate 128-edge chunks and their (max, sum, acc) partials are merged in
 // warp order (dense metapath / Reddit-like graphs).  Both are deterministic.
-// Backward: kernel A (CSR rows) computes the edge gradient dz (SDDMM dOut_i·Wh_j reduced per
-// head by segmented warp shuffle), stashes attention weight and dz per edge and reduces d_s;
-// kernel B (transposed CSR rows) reduces d_Wh and d_t in source order.  Ordered sums only.
+// Backward: two passes of the forward kernel's shape (see gat_bwd2_kernel): over the CSR rows for d_s, over the
+// transposed CSR rows for d_Wh and d_t.  The edge gradient is never materialised per edge: it factorises into
+// weighted row sums (FMA per column) plus a per-head correction.  Ordered sums only, no atomics, no edge stash.
 #include "common.cuh"
 
 using namespace gnn;
@@ -28,8 +28,7 @@ constexpr int kGatWarps = 4;
 struct GatArgs {
   const int64_t* rowptr;
   const int32_t* col;
-  const int64_t* perm;   // backward B: transposed slot -> forward edge slot (nullptr: the stash is in transposed order)
-  const int64_t* tslot;  // backward A: forward edge slot -> transposed slot (nullptr: stash in forward order)
+  const int64_t* perm;   // backward pass 2: transposed slot -> forward edge slot (dropout factors only)
   const void* Wh;        // T [n, ldw]: fp32 or bf16 (softmax and accumulation are fp32 either way)
   int64_t ldw;
   const float* s;
@@ -46,11 +45,11 @@ struct GatArgs {
   float* row_max;
   float* row_sum;
   int SE;
+  int packed;  // bf16 rows 4-byte aligned with even head width: lanes own column pairs (PK = 2)
   // backward
   const void* out_pre;   // T
   const void* d_out;     // T
-  const float* rowdot;
-  float* edge_st;        // [nnz][2][H] fp32: per edge (keep*alpha, dz), in transposed slot order when tslot != nullptr
+  float* rowstat;        // [n][4][H] fp32: s, row max, 1/row sum, D = <d_out_i, out_pre_i> per head (backward)
   void* d_Wh;            // T
   int64_t ld_dwh;
   float* d_s;
@@ -71,6 +70,53 @@ template <>
 __device__ __forceinline__ float ldv<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __uint_as_float(((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
 }
+// raw (unconverted) staging of gathered values: the loads of a batch are all issued before the first
+// conversion (with ldv<bf16> in the gather loop every shift waited on its own 2-byte load: ncu r02, 43 % of the
+// bf16 forward's stall samples sat on those shifts)
+template <typename T>
+struct RawOf { using type = float; };
+// (a bf16 value is staged zero-extended in a full 32-bit register: staged as 16-bit halves, ptxas gave several
+// in-flight loads the same register and the batch serialised load -> shift -> load)
+template <>
+struct RawOf<__nv_bfloat16> { using type = uint32_t; };
+__device__ __forceinline__ float ld_raw(const float* p) { return __ldg(p); }
+// The staged word is the aligned 32-bit word that CONTAINS the element (rows are 4-byte aligned: checked on the
+// host); the element's half is selected at use.  16-bit loads (LDG.U16) made ptxas funnel a whole batch of
+// in-flight loads through one destination register.
+__device__ __forceinline__ uint32_t ld_raw(const __nv_bfloat16* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3));
+  return (a & 2) ? (w & 0xffff0000u) : (w << 16);
+}
+__device__ __forceinline__ float raw_to_f(float v) { return v; }
+__device__ __forceinline__ float raw_to_f(uint32_t v) { return __uint_as_float(v); }
+
+// Column owned by (lane, c).  PK = 1: lane + 32c (one element per load).  PK = 2 (bf16 rows that are 4-byte
+// aligned): the pair (2q, 2q+1) of one 32-bit word, q = lane + 32*(c/2) — one 32-bit load per lane serves two
+// columns, the load pattern of the fp32 kernel at half the bytes.
+template <int PK>
+__device__ __forceinline__ int col_of(int lane, int c) {
+  return PK == 1 ? lane + 32 * c : (lane + 32 * (c >> 1)) * 2 + (c & 1);
+}
+// one staged load: PK = 1 -> the element (see ld_raw), PK = 2 -> the raw 32-bit word holding the pair
+template <typename T, int PK>
+__device__ __forceinline__ typename RawOf<T>::type ld_stage(const T* row, int lane, int q) {
+  if constexpr (PK == 1) {
+    return ld_raw(row + lane + 32 * q);
+  } else {
+    return __ldg(reinterpret_cast<const uint32_t*>(row) + lane + 32 * q);
+  }
+}
+// element c of the lane from the staged loads (x[c / PK])
+template <typename T, int PK>
+__device__ __forceinline__ float stage_elem(typename RawOf<T>::type v, int c) {
+  if constexpr (PK == 1) {
+    return raw_to_f(v);
+  } else {
+    return __uint_as_float((c & 1) ? (v & 0xffff0000u) : (v << 16));
+  }
+}
+
 __device__ __forceinline__ void stv(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stv(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
@@ -82,11 +128,6 @@ __device__ __forceinline__ float act_elu(float x, int elu) {
 
 // floats of shared memory per warp for the staged chunk
 __host__ __device__ inline int gat_warp_floats(int SE, int H, int HF) { return SE * H + SE + 160 + HF; }
-// backward A additionally stages the int64 transposed slot of every edge of the chunk (first, 8-byte aligned)
-__host__ __device__ inline int gat_warp_floats_bwd(int SE, int H, int HF) {
-  return 2 * SE + SE * H + SE + 160 + ((HF + 1) & ~1);
-}
-
 // W  = warps that share one row: 1 -> one warp per row (4 rows per CTA); 4 / 16 -> one CTA of W
 //      warps per row, the warps take alternate SE-edge chunks and merge (max, sum, acc) in warp order.
 // HT = compile-time head count (1, 8; must divide 32) or 0 for the generic run-time H.  With HT known
@@ -98,7 +139,7 @@ struct GatBlock {
   static constexpr int kWarps = (W == 1) ? kGatWarps : W;
 };
 
-template <typename T, int CPL, int W, int HT>
+template <typename T, int CPL, int W, int HT, int PK>
 __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const GatArgs a) {
   constexpr int BW = GatBlock<W>::kWarps;
   extern __shared__ float sm[];
@@ -123,7 +164,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
   float acc[CPL], l[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
-    const int ci = lane + 32 * c;
+    const int ci = col_of<PK>(lane, c);
     cv[c] = ci < a.HF;
     hc[c] = cv[c] ? ci / a.Fp : 0;
     acc[c] = 0.f;
@@ -139,7 +180,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
 #pragma unroll
       for (int c = 0; c < CPL; ++c)
         if (cv[c]) {
-          const int ci = lane + 32 * c;
+          const int ci = col_of<PK>(lane, c);
           stv(orow + ci, act_elu(a.col_mean ? a.col_mean[ci] : 0.f, a.elu));
           if (ci % a.Fp == 0) {
             if (a.row_max) a.row_max[i * H + hc[c]] = 0.f;
@@ -242,13 +283,13 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
     __syncwarp();
     // C: weighted accumulation, one lane per output column, 8 row gathers in flight
     for (int k0 = 0; k0 < ne; k0 += 8) {
-      float x[8][CPL];
+      typename RawOf<T>::type x[8][CPL / PK];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const bool ok = k0 + u < ne;
         const T* wr = reinterpret_cast<const T*>(a.Wh) + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? ldv<T>(wr + lane + 32 * c) : 0.f;
+        for (int q = 0; q < CPL / PK; ++q) x[u][q] = (ok && cv[q * PK]) ? ld_stage<T, PK>(wr, lane, q) : 0;
       }
       const float* pk = logit + k0 * H;
 #pragma unroll
@@ -260,7 +301,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
               const float p = pk[u * H + hc[c]];
               if (!HT) l[c] += p;
               const float w = a.keep ? p * __ldg(a.keep + (e0 + c0 + k0 + u) * H + hc[c]) : p;
-              acc[c] = fmaf(w, x[u][c], acc[c]);
+              acc[c] = fmaf(w, stage_elem<T, PK>(x[u][c / PK], c), acc[c]);
             }
         }
       }
@@ -276,7 +317,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
 #pragma unroll
     for (int c = 0; c < CPL; ++c)
       if (cv[c]) {
-        const int ci = lane + 32 * c;
+        const int ci = col_of<PK>(lane, c);
         stv(orow + ci, act_elu(acc[c] / l[c], a.elu));
         if (ci % a.Fp == 0) {
           if (a.row_max) a.row_max[i * H + hc[c]] = mh[hc[c]];
@@ -297,7 +338,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
 #pragma unroll
     for (int c = 0; c < CPL; ++c)
       if (cv[c]) {
-        const int ci = lane + 32 * c;
+        const int ci = col_of<PK>(lane, c);
         float M = -INFINITY;
         for (int w = 0; w < BW; ++w) M = fmaxf(M, marr[w * 32 + hc[c]]);
         float L = 0.f, A = 0.f;
@@ -336,10 +377,16 @@ __global__ void __launch_bounds__(256) gat_scores_kernel(const float* __restrict
   }
 }
 
+// ---- backward ------------------------------------------------------------------------------------
+// Per-row statistics packed for the backward passes: rowstat[i] = [s_i | m_i | 1/l_i | D_i], H floats each, with
+// D_i[h] = <d_out_i[h,:], out_pre_i[h,:]> (the softmax-Jacobian term).  One 128-byte record per node (H = 8): the
+// transposed pass gathers it with one access per edge.
 template <typename T>
-__global__ void __launch_bounds__(256) gat_rowdot_kernel(const T* __restrict__ d_out,
-                                                         const T* __restrict__ out_pre, int64_t ldo, int64_t n,
-                                                         int H, int Fp, float* __restrict__ rowdot) {
+__global__ void __launch_bounds__(256) gat_rowstat_kernel(const T* __restrict__ d_out, const T* __restrict__ out_pre,
+                                                          int64_t ldo, const float* __restrict__ s,
+                                                          const float* __restrict__ row_max,
+                                                          const float* __restrict__ row_sum, int64_t n, int H, int Fp,
+                                                          float* __restrict__ rowstat) {
   const int64_t total = n * H;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(p % H);
@@ -348,255 +395,235 @@ __global__ void __launch_bounds__(256) gat_rowdot_kernel(const T* __restrict__ d
     const T* b = out_pre + i * ldo + h * Fp;
     float acc = 0.f;
     for (int f = 0; f < Fp; ++f) acc = fmaf(ldv<T>(a + f), ldv<T>(b + f), acc);
-    rowdot[p] = acc;
+    const float l = __ldg(row_sum + p);
+    float* rs = rowstat + i * 4 * H;
+    rs[h] = __ldg(s + p);
+    rs[H + h] = __ldg(row_max + p);
+    rs[2 * H + h] = l > 0.f ? 1.f / l : 0.f;
+    rs[3 * H + h] = acc;
   }
 }
 
-// Phase 1 of backward A for one staged chunk: dots dOut_i . Wh_j per head.  FPT = head width
-// (power of two <= 32: aligned lane groups, segmented xor-shuffle) or 0 (single head: full warp).
-template <typename T, int CPL, int FPT>
-__device__ __forceinline__ void bwd_head_dots(const GatArgs& a, const int* cols, int ne, const float (&dcol)[CPL],
-                                              const bool (&cv)[CPL], const bool (&lead)[CPL], const int (&hc)[CPL],
-                                              float* dot_s, int H, int lane) {
-  for (int k0 = 0; k0 < ne; k0 += 4) {
-    float x[4][CPL];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool ok = k0 + u < ne;
-      const T* wr = reinterpret_cast<const T*>(a.Wh) + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) x[u][c] = (ok && cv[c]) ? ldv<T>(wr + lane + 32 * c) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (k0 + u < ne) {  // uniform
-        if (FPT == 0) {
-          float pr = 0.f;
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) pr = fmaf(dcol[c], x[u][c], pr);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
-          if (lane == 0) dot_s[k0 + u] = pr;
-        } else {
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) {
-            float pr = dcol[c] * x[u][c];
-#pragma unroll
-            for (int o = 1; o < FPT; o <<= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
-            if (lead[c]) dot_s[(k0 + u) * H + hc[c]] = pr;
-          }
-        }
-      }
-    }
-  }
+// floats of shared memory per warp: w2 [SE*H], q [SE*H], (TR) w1 [SE*H], cols [SE]
+// (at least HF: the finalize step reuses the warp's area as an [HF] scratch)
+__host__ __device__ inline int gat_bwd_warp_floats(int SE, int H, int HF, bool tr) {
+  const int f = (tr ? 3 : 2) * SE * H + SE;
+  return f > HF ? f : HF;
 }
 
-// Backward A (forward CSR rows): per-edge attention weight w = keep*alpha_ij, edge gradient dz,
-// and d_s[i,h] = sum_j dz.  SEG == true: Fp is a power of two <= 32 (the head groups of the
-// lane->column map are aligned lane groups, reduced by segmented shuffle) or H == 1 (full-warp
-// reduce).  SEG == false: generic lane-per-edge dot (any H, Fp).
-template <typename T, int CPL, int W, bool SEG, int HT>
-__global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_rows_kernel(const GatArgs a) {
+// Both backward passes are the FORWARD kernel's shape — lane-per-edge weights staged in shared memory, then
+// lane-per-column FMAs over coalesced row gathers — because the edge gradient factorises:
+//     dz_ij = a_ij * slope_ij * (keep_ij * <dOut_i, Wh_j> - D_i)                 (per head)
+//     d_s[i]  = sum_j dz_ij = <dOut_i, sum_j w2_ij Wh_j>  - D_i * sum_j a_ij slope_ij          (TR = false)
+//     d_t[j]  = sum_i dz_ij = <Wh_j,  sum_i w2_ij dOut_i> -       sum_i a_ij slope_ij D_i      (TR = true)
+//     d_Wh[j] =               sum_i w1_ij dOut_i                                               (TR = true)
+// with w1 = keep*a, w2 = w1*slope.  No per-edge dot product (the first build reduced 64-wide dots by segmented
+// shuffle for every edge: 71 warp instructions per edge, ncu r02), no per-edge stash between the passes (the first
+// build wrote 64 bytes per edge and read them back: 6.9 GB each way on the Reddit shape), nothing but ordered sums.
+//   TR = false: rows of the forward CSR (destination i); gathers Wh_j and t_j.
+//   TR = true : rows of the transposed CSR (source j); gathers dOut_i and rowstat_i; `perm` maps its slots to the
+//               forward edge slots for the dropout factors.
+template <typename T, int CPL, int W, int HT, bool TR, int PK>
+__global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(const GatArgs a) {
   constexpr int BW = GatBlock<W>::kWarps;
+  constexpr int NA = TR ? 2 : 1;  // accumulators per column
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp
+  const int64_t r = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp
                              : (a.row_list ? __ldg(a.row_list + blockIdx.x) : (int64_t)blockIdx.x);
   const int wsub = (W == 1) ? 0 : warp;
-  if (W == 1 && i >= a.n) return;
-  if (W == 1 && a.skip_deg_gt > 0 && __ldg(a.rowptr + i + 1) - __ldg(a.rowptr + i) > a.skip_deg_gt) return;
-  const int H = HT ? HT : a.H, Hp = HT ? HT : a.Hp, SE = a.SE, HF = a.HF, Fp = a.Fp;
-  const int PW = gat_warp_floats_bwd(SE, H, HF);
-  int64_t* tsl = reinterpret_cast<int64_t*>(sm + (size_t)warp * PW);  // [SE]: stash slot of every staged edge
-  float* dot_s = sm + (size_t)warp * PW + 2 * SE;                     // [SE*H]: head dots, then dz in place
-  int* cols = reinterpret_cast<int*>(dot_s + SE * H);
-  float* cst = reinterpret_cast<float*>(cols + SE);  // [4][32]: s_i, m_i, 1/l_i, D_i
-  float* dout_s = cst + 128;                    // [HF] (generic path)
-  float* dsarr = sm + (size_t)BW * PW;          // [BW][32]
-
-  int hc[CPL];
-  bool cv[CPL], lead[CPL];
-  float dcol[CPL];
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    const int ci = lane + 32 * c;
-    cv[c] = ci < HF;
-    hc[c] = cv[c] ? ci / Fp : 0;
-    lead[c] = cv[c] && (ci % Fp) == 0;
-    dcol[c] = cv[c] ? ldv<T>(reinterpret_cast<const T*>(a.d_out) + i * a.ldo + ci) : 0.f;
-    if (!SEG && cv[c]) dout_s[ci] = dcol[c];
-  }
-  if (lane < H) {
-    cst[lane] = __ldg(a.s + i * H + lane);
-    cst[32 + lane] = __ldg(a.row_max + i * H + lane);
-    const float l = __ldg(a.row_sum + i * H + lane);
-    cst[64 + lane] = l > 0.f ? 1.f / l : 0.f;
-    cst[96 + lane] = __ldg(a.rowdot + i * H + lane);
-  }
-  __syncwarp();
-  const int64_t e0 = __ldg(a.rowptr + i), e1 = __ldg(a.rowptr + i + 1);
+  if (W == 1 && r >= a.n) return;
+  const int64_t e0 = __ldg(a.rowptr + r), e1 = __ldg(a.rowptr + r + 1);
   const int64_t d = e1 - e0;
-  const int ngrp = 32 / Hp;
-  const int hsub = lane % Hp, g = lane / Hp;
-  float dsum = 0.f;
-  (void)e1;
-  for (int64_t c0 = (int64_t)wsub * SE; c0 < d; c0 += (int64_t)W * SE) {
-    const int ne = (int)((d - c0) < SE ? (d - c0) : SE);
-    for (int k = lane; k < ne; k += 32) {
-      cols[k] = __ldg(a.col + e0 + c0 + k);
-      tsl[k] = a.tslot ? __ldg(a.tslot + e0 + c0 + k) : (e0 + c0 + k);
-    }
-    __syncwarp();
-    // phase 1: per-head dots dOut_i . Wh_j
-    if (SEG) {
-      // the head-group reduction is unrolled for the common widths; `lead` marks the lane that
-      // owns a head's first column (no run-time modulo or loop in the per-edge path)
-      switch (H == 1 ? 0 : Fp) {
-        case 0: bwd_head_dots<T, CPL, 0>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 1: bwd_head_dots<T, CPL, 1>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 2: bwd_head_dots<T, CPL, 2>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 4: bwd_head_dots<T, CPL, 4>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 8: bwd_head_dots<T, CPL, 8>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        case 16: bwd_head_dots<T, CPL, 16>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-        default: bwd_head_dots<T, CPL, 32>(a, cols, ne, dcol, cv, lead, hc, dot_s, H, lane); break;
-      }
-    } else {
-      for (int k = lane; k < ne; k += 32) {
-        const T* wr = reinterpret_cast<const T*>(a.Wh) + (int64_t)cols[k] * a.ldw;
-        for (int h = 0; h < H; ++h) {
-          float dot = 0.f;
-          for (int f = 0; f < Fp; ++f) dot = fmaf(dout_s[h * Fp + f], ldv<T>(wr + h * Fp + f), dot);
-          dot_s[k * H + h] = dot;
-        }
-      }
-    }
-    __syncwarp();
-    // phase 2: one lane per (edge, head): attention weight and dz, stashed per edge (coalesced)
-    for (int idx = lane; idx < ne * H; idx += 32) {
-      const int k = idx / H, h = idx - k * H;  // H is a compile-time constant when HT != 0
-      const int64_t e = e0 + c0 + k;
-      const float z = cst[h] + __ldg(a.t + (int64_t)cols[k] * H + h);
-      float slope = z > 0.f ? 1.f : a.alpha;
-      float ee = z * slope;
-      if (a.mode == GNN_GAT_EXPNEG) {
-        ee = -ee;
-        slope = -slope;
-      }
-      const float al = __expf(ee - cst[32 + h]) * cst[64 + h];
-      const float kp = a.keep ? __ldg(a.keep + e * H + h) : 1.f;
-      const float dz = al * (kp * dot_s[idx] - cst[96 + h]) * slope;
-      // the stash is written in the order kernel B walks it (scattered 32-byte stores here, no stall;
-      // sequential reads there instead of a random 32-byte read per edge through the permutation)
-      float* stp = a.edge_st + tsl[k] * (2 * H);
-      stp[h] = kp * al;
-      stp[H + h] = dz;
-      dot_s[idx] = dz;
-    }
-    __syncwarp();
-    if (hsub < H)
-      for (int k = g; k < ne; k += ngrp) dsum += dot_s[k * H + hsub];
-    __syncwarp();
-  }
-  for (int o = Hp; o < 32; o <<= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-  if (W == 1) {
-    if (lane < H) a.d_s[i * H + lane] = dsum;
-    return;
-  }
-  if (lane < H) dsarr[warp * 32 + lane] = dsum;
-  __syncthreads();
-  if (warp == 0 && lane < H) {
-    float tot = 0.f;
-    for (int w = 0; w < BW; ++w) tot += dsarr[w * 32 + lane];
-    a.d_s[i * H + lane] = tot;
-  }
-}
+  if (W == 1 && a.skip_deg_gt > 0 && d > a.skip_deg_gt) return;
+  const int H = HT ? HT : a.H, Hp = HT ? HT : a.Hp, SE = a.SE, HF = a.HF, Fp = a.Fp;
+  const int PW = gat_bwd_warp_floats(SE, H, HF, TR);
+  float* w2s = sm + (size_t)warp * PW;
+  float* qs = w2s + SE * H;
+  float* w1s = qs + SE * H;  // TR only
+  int* cols = reinterpret_cast<int*>(w2s + (TR ? 3 : 2) * SE * H);
+  float* qarr = sm + (size_t)BW * PW;           // [BW][32]
+  float* aarr = qarr + BW * 32;                 // [BW][NA*CPL*32]
 
-// Backward B: transposed CSR rows (source node j), sources of the forward edges ascending.
-template <typename T, int CPL, int W>
-__global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd_cols_kernel(const GatArgs a) {
-  constexpr int BW = GatBlock<W>::kWarps;
-  __shared__ float accarr[(W > 1) ? BW * CPL * 32 : 1];
-  __shared__ float dtarr[(W > 1) ? BW * 32 : 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t j = (W == 1) ? (int64_t)blockIdx.x * kGatWarps + warp
-                             : (a.row_list ? __ldg(a.row_list + blockIdx.x) : (int64_t)blockIdx.x);
-  const int wsub = (W == 1) ? 0 : warp;
-  if (W == 1 && j >= a.n) return;
-  if (W == 1 && a.skip_deg_gt > 0 && __ldg(a.rowptr + j + 1) - __ldg(a.rowptr + j) > a.skip_deg_gt) return;
-  const int H = a.H, Hp = a.Hp;
   int hc[CPL];
   bool cv[CPL];
-  float acc[CPL];
+  float acc2[CPL], acc1[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
-    const int ci = lane + 32 * c;
-    cv[c] = ci < a.HF;
-    hc[c] = cv[c] ? ci / a.Fp : 0;
-    acc[c] = 0.f;
+    const int ci = col_of<PK>(lane, c);
+    cv[c] = ci < HF;
+    hc[c] = cv[c] ? ci / Fp : 0;
+    acc2[c] = 0.f;
+    acc1[c] = 0.f;
   }
-  const int64_t e0 = __ldg(a.rowptr + j), e1 = __ldg(a.rowptr + j + 1);
+  // constants of this row, per head, for the lane-per-edge phase
+  float c0r[HT ? HT : 1], c1r[HT ? HT : 1], c2r[HT ? HT : 1];
+  const float* rs_own = a.rowstat + r * 4 * H;
+  if (HT) {
+#pragma unroll
+    for (int h = 0; h < (HT ? HT : 1); ++h) {
+      if (TR) {
+        c0r[h] = __ldg(a.t + r * H + h);
+      } else {
+        c0r[h] = __ldg(rs_own + h);
+        c1r[h] = __ldg(rs_own + H + h);
+        c2r[h] = __ldg(rs_own + 2 * H + h);
+      }
+    }
+  }
+  const bool vec4 = HT && (HT % 4 == 0) && aligned_to_dev(TR ? (const void*)a.rowstat : (const void*)a.t, 16);
   const int ngrp = 32 / Hp;
   const int hsub = lane % Hp, g = lane / Hp;
-  float dtsum = 0.f;
-  for (int64_t c0 = e0 + (int64_t)wsub * 32; c0 < e1; c0 += (int64_t)W * 32) {
-    const int ne = (int)((e1 - c0) < 32 ? (e1 - c0) : 32);
-    int il = 0;
-    int64_t pl = 0;
-    if (lane < ne) {
-      il = __ldg(a.col + c0 + lane);
-      pl = a.perm ? __ldg(a.perm + c0 + lane) : (c0 + lane);
-    }
-    for (int k0 = 0; k0 < ne; k0 += ngrp) {
-      const int kk = k0 + g;
-      const int64_t p = __shfl_sync(0xffffffffu, pl, kk & 31);
-      if (kk < ne && hsub < H) dtsum += __ldg(a.edge_st + p * (2 * H) + H + hsub);
-    }
-    for (int k0 = 0; k0 < ne; k0 += 8) {
-      float w[8][CPL], x[8][CPL];
+  float qsum = 0.f;
+
+  for (int64_t c0 = (int64_t)wsub * SE; c0 < d; c0 += (int64_t)W * SE) {
+    const int ne = (int)((d - c0) < SE ? (d - c0) : SE);
+    // A: one lane per edge: attention weight, slope, the two FMA weights and the correction term, per head
+    for (int k = lane; k < ne; k += 32) {
+      const int64_t e = e0 + c0 + k;
+      const int o = __ldg(a.col + e);
+      cols[k] = o;
+      const float* ot = TR ? a.rowstat + (int64_t)o * 4 * H : a.t + (int64_t)o * H;
+      const int64_t kslot = (TR && a.perm) ? __ldg(a.perm + e) : e;
+      if (HT) {
+        float v0[HT ? HT : 1], v1[HT ? HT : 1], v2[HT ? HT : 1], v3[HT ? HT : 1];
+        if (vec4) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = __shfl_sync(0xffffffffu, il, (k0 + u) & 31);
-        const int64_t p = __shfl_sync(0xffffffffu, pl, (k0 + u) & 31);
-        const bool ok = k0 + u < ne;
-        const T* dr = reinterpret_cast<const T*>(a.d_out) + (int64_t)i * a.ldo;
+          for (int q = 0; q < (HT ? HT : 1) / 4; ++q) {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(ot) + q);
+            v0[4 * q] = x0.x; v0[4 * q + 1] = x0.y; v0[4 * q + 2] = x0.z; v0[4 * q + 3] = x0.w;
+            if (TR) {
+              const float4 x1 = __ldg(reinterpret_cast<const float4*>(ot + H) + q);
+              const float4 x2 = __ldg(reinterpret_cast<const float4*>(ot + 2 * H) + q);
+              const float4 x3 = __ldg(reinterpret_cast<const float4*>(ot + 3 * H) + q);
+              v1[4 * q] = x1.x; v1[4 * q + 1] = x1.y; v1[4 * q + 2] = x1.z; v1[4 * q + 3] = x1.w;
+              v2[4 * q] = x2.x; v2[4 * q + 1] = x2.y; v2[4 * q + 2] = x2.z; v2[4 * q + 3] = x2.w;
+              v3[4 * q] = x3.x; v3[4 * q + 1] = x3.y; v3[4 * q + 2] = x3.z; v3[4 * q + 3] = x3.w;
+            }
+          }
+        } else {
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-          const bool on = ok && cv[c];
-          w[u][c] = on ? __ldg(a.edge_st + p * (2 * H) + hc[c]) : 0.f;
-          x[u][c] = on ? ldv<T>(dr + lane + 32 * c) : 0.f;
+          for (int h = 0; h < (HT ? HT : 1); ++h) {
+            v0[h] = __ldg(ot + h);
+            if (TR) {
+              v1[h] = __ldg(ot + H + h);
+              v2[h] = __ldg(ot + 2 * H + h);
+              v3[h] = __ldg(ot + 3 * H + h);
+            }
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < (HT ? HT : 1); ++h) {
+          const float z = c0r[h] + v0[h];  // s_i + t_j either way
+          const float m = TR ? v1[h] : c1r[h];
+          const float li = TR ? v2[h] : c2r[h];
+          float slope = z > 0.f ? 1.f : a.alpha;
+          float ee = z * slope;
+          if (a.mode == GNN_GAT_EXPNEG) {
+            ee = -ee;
+            slope = -slope;
+          }
+          const float al = __expf(ee - m) * li;
+          const float kp = a.keep ? __ldg(a.keep + kslot * H + h) : 1.f;
+          const float w1 = kp * al;
+          w2s[k * H + h] = w1 * slope;
+          if (TR) w1s[k * H + h] = w1;
+          qs[k * H + h] = TR ? al * slope * v3[h] : al * slope;
+        }
+      } else {
+        for (int h = 0; h < H; ++h) {
+          const float z = TR ? __ldg(ot + h) + __ldg(a.t + r * H + h) : __ldg(rs_own + h) + __ldg(ot + h);
+          const float m = TR ? __ldg(ot + H + h) : __ldg(rs_own + H + h);
+          const float li = TR ? __ldg(ot + 2 * H + h) : __ldg(rs_own + 2 * H + h);
+          float slope = z > 0.f ? 1.f : a.alpha;
+          float ee = z * slope;
+          if (a.mode == GNN_GAT_EXPNEG) {
+            ee = -ee;
+            slope = -slope;
+          }
+          const float al = __expf(ee - m) * li;
+          const float kp = a.keep ? __ldg(a.keep + kslot * H + h) : 1.f;
+          const float w1 = kp * al;
+          w2s[k * H + h] = w1 * slope;
+          if (TR) w1s[k * H + h] = w1;
+          qs[k * H + h] = TR ? al * slope * __ldg(ot + 3 * H + h) : al * slope;
         }
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) acc[c] = fmaf(w[u][c], x[u][c], acc[c]);
     }
-  }
-  for (int o = Hp; o < 32; o <<= 1) dtsum += __shfl_xor_sync(0xffffffffu, dtsum, o);
-  if (W == 1) {
+    __syncwarp();
+    // Q: per-head sum of the correction terms of this chunk (fixed lane -> edge assignment: deterministic)
+    if (hsub < H)
+      for (int k = g; k < ne; k += ngrp) qsum += qs[k * H + hsub];
+    // C: one lane per column, 8 row gathers in flight
+    const T* base = reinterpret_cast<const T*>(TR ? a.d_out : a.Wh);
+    const int64_t ldb = TR ? a.ldo : a.ldw;
+    for (int k0 = 0; k0 < ne; k0 += 8) {
+      typename RawOf<T>::type x[8][CPL / PK];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c)
-      if (cv[c]) stv(reinterpret_cast<T*>(a.d_Wh) + j * a.ld_dwh + lane + 32 * c, acc[c]);
-    if (lane < H) a.d_t[j * H + lane] = dtsum;
-    return;
-  }
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = k0 + u < ne;
+        const T* xr = base + (int64_t)(ok ? cols[k0 + u] : 0) * ldb;
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) accarr[(warp * CPL + c) * 32 + lane] = acc[c];
-  if (lane < H) dtarr[warp * 32 + lane] = dtsum;
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int c = 0; c < CPL; ++c)
-      if (cv[c]) {
-        float tot = 0.f;
-        for (int w = 0; w < BW; ++w) tot += accarr[(w * CPL + c) * 32 + lane];
-        stv(reinterpret_cast<T*>(a.d_Wh) + j * a.ld_dwh + lane + 32 * c, tot);
+        for (int q = 0; q < CPL / PK; ++q) x[u][q] = (ok && cv[q * PK]) ? ld_stage<T, PK>(xr, lane, q) : 0;
       }
-    if (lane < H) {
-      float tot = 0.f;
-      for (int w = 0; w < BW; ++w) tot += dtarr[w * 32 + lane];
-      a.d_t[j * H + lane] = tot;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k0 + u < ne) {
+#pragma unroll
+          for (int c = 0; c < CPL; ++c)
+            if (cv[c]) {
+              const float xv = stage_elem<T, PK>(x[u][c / PK], c);
+              acc2[c] = fmaf(w2s[(k0 + u) * H + hc[c]], xv, acc2[c]);
+              if (TR) acc1[c] = fmaf(w1s[(k0 + u) * H + hc[c]], xv, acc1[c]);
+            }
+        }
+      }
     }
+    __syncwarp();
+  }
+  for (int o = Hp; o < 32; o <<= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+
+  if (W > 1) {
+    // merge the warps' partials in warp order
+    if (lane < Hp) qarr[warp * 32 + lane] = qsum;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      aarr[(warp * NA * CPL + c) * 32 + lane] = acc2[c];
+      if (TR) aarr[(warp * NA * CPL + CPL + c) * 32 + lane] = acc1[c];
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    qsum = 0.f;
+    if (lane < Hp)
+      for (int w = 0; w < BW; ++w) qsum += qarr[w * 32 + lane];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      float t2 = 0.f, t1 = 0.f;
+      for (int w = 0; w < BW; ++w) {
+        t2 += aarr[(w * NA * CPL + c) * 32 + lane];
+        if (TR) t1 += aarr[(w * NA * CPL + CPL + c) * 32 + lane];
+      }
+      acc2[c] = t2;
+      acc1[c] = t1;
+    }
+  }
+  // finalize (one warp): the head-wise contraction of the accumulated vector with this row's own vector
+  float* buf = w2s;  // [HF] scratch (this warp's staging area is free now)
+  __syncwarp();
+  const T* own = reinterpret_cast<const T*>(TR ? a.Wh : a.d_out) + r * (TR ? a.ldw : a.ldo);
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+    if (cv[c]) {
+      const int ci = col_of<PK>(lane, c);
+      buf[ci] = acc2[c] * ldv<T>(own + ci);
+      if (TR) stv(reinterpret_cast<T*>(a.d_Wh) + r * a.ld_dwh + ci, acc1[c]);
+    }
+  __syncwarp();
+  if (lane < H) {
+    float tot = 0.f;
+    for (int f = 0; f < Fp; ++f) tot += buf[lane * Fp + f];
+    if (TR) a.d_t[r * H + lane] = tot - qsum;
+    else a.d_s[r * H + lane] = tot - __ldg(rs_own + 3 * H + lane) * qsum;
   }
 }
 
@@ -628,9 +655,9 @@ bool cooperative(int64_t n, int64_t nnz) {
 }
 
 template <int W>
-size_t gat_smem_bytes(int SE, int H, int HF, int cpl, bool bwd = false) {
+size_t gat_smem_bytes(int SE, int H, int HF, int cpl) {
   constexpr int BW = GatBlock<W>::kWarps;
-  size_t f = (size_t)BW * (bwd ? gat_warp_floats_bwd(SE, H, HF) : gat_warp_floats(SE, H, HF));
+  size_t f = (size_t)BW * gat_warp_floats(SE, H, HF);
   if (W > 1) f += (size_t)BW * 32 + 2 * (size_t)BW * cpl * 32;
   return f * sizeof(float);
 }
@@ -639,24 +666,35 @@ size_t gat_smem_bytes(int SE, int H, int HF, int cpl, bool bwd = false) {
 template <typename T, int CPL, int W>
 int gat_fwd_launch(const GatArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
   constexpr int thr = GatBlock<W>::kWarps * 32;
-#define GNN_GAT_FWD(HT)                                                                                         \
+#define GNN_GAT_FWD_PK(HT, PKV)                                                                                 \
   do {                                                                                                          \
     if (smem > 48 * 1024)                                                                                       \
-      GNN_CUDA(cudaFuncSetAttribute(gat_fwd_kernel<T, CPL, W, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)smem));                                                                \
-    gat_fwd_kernel<T, CPL, W, HT><<<grid, thr, smem, st>>>(a);                                                  \
+      GNN_CUDA(cudaFuncSetAttribute(gat_fwd_kernel<T, CPL, W, HT, PKV>,                                         \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+    gat_fwd_kernel<T, CPL, W, HT, PKV><<<grid, thr, smem, st>>>(a);                                             \
+  } while (0)
+#define GNN_GAT_FWD(HT)                                              \
+  do {                                                               \
+    if constexpr (sizeof(T) == 2 && CPL >= 2) {                      \
+      if (a.packed) GNN_GAT_FWD_PK(HT, 2);                           \
+      else GNN_GAT_FWD_PK(HT, 1);                                    \
+    } else {                                                         \
+      GNN_GAT_FWD_PK(HT, 1);                                         \
+    }                                                                \
   } while (0)
   if (a.H == 8) GNN_GAT_FWD(8);
   else if (a.H == 1) GNN_GAT_FWD(1);
   else GNN_GAT_FWD(0);
 #undef GNN_GAT_FWD
+#undef GNN_GAT_FWD_PK
   GNN_LAUNCH_CHECK();
   return GNN_OK;
 }
 
 template <typename T, int W>
 int gat_fwd_dispatch(const GatArgs& a, int cpl, unsigned grid, cudaStream_t st) {
-  const int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
+  int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
+  if (a.packed && cplr < 2) cplr = 2;  // a packed lane owns column pairs
   const size_t smem = gat_smem_bytes<W>(a.SE, a.H, a.HF, cplr);
   switch (cplr) {
     case 1: return gat_fwd_launch<T, 1, W>(a, grid, smem, st);
@@ -701,6 +739,7 @@ int gat_fwd_impl(const int64_t* rowptr, const int32_t* col, const T* Wh, int64_t
   a.row_max = row_max;
   a.row_sum = row_sum;
   a.SE = stage_edges(H);
+  a.packed = sizeof(T) == 2 && Fp % 2 == 0 && ldw % 2 == 0 && aligned_to(Wh, 4);
   const int cpl = (HF + 31) / 32;
   GNN_REQUIRE(n_long == 0 || (long_rows && long_threshold > 0), GNN_ERR_BAD_ARG, "inconsistent long-row list");
   if (cooperative(n, nnz)) return gat_fwd_dispatch<T, kGatWarps>(a, cpl, (unsigned)n, st);
@@ -714,66 +753,63 @@ int gat_fwd_impl(const int64_t* rowptr, const int32_t* col, const T* Wh, int64_t
   return gat_fwd_dispatch<T, 1>(a, cpl, (unsigned)((n + kGatWarps - 1) / kGatWarps), st);
 }
 
-// rows kernel launch for one (CPL, W): picks SEG / HT
-template <typename T, int CPLV, int WV>
-int gat_bwd_rows_launch(const GatArgs& a, bool seg, unsigned grid, cudaStream_t st) {
-  const size_t smem = gat_smem_bytes<WV>(a.SE, a.H, a.HF, CPLV, true);
-  constexpr int thrv = GatBlock<WV>::kWarps * 32;
-#define GNN_ROWS(SEGV, HTV)                                                                                 \
-  do {                                                                                                      \
-    if (smem > 48 * 1024)                                                                                   \
-      GNN_CUDA(cudaFuncSetAttribute(gat_bwd_rows_kernel<T, CPLV, WV, SEGV, HTV>,                            \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-    gat_bwd_rows_kernel<T, CPLV, WV, SEGV, HTV><<<grid, thrv, smem, st>>>(a);                               \
+template <typename T, int CPLV, int WV, bool TR>
+int gat_bwd2_launch(const GatArgs& a, unsigned grid, cudaStream_t st) {
+  constexpr int BW = GatBlock<WV>::kWarps;
+  size_t f = (size_t)BW * gat_bwd_warp_floats(a.SE, a.H, a.HF, TR);
+  if (WV > 1) f += (size_t)BW * 32 + (size_t)BW * (TR ? 2 : 1) * CPLV * 32;
+  const size_t smem = f * sizeof(float);
+  constexpr int thrv = BW * 32;
+#define GNN_BWD2_PK(HTV, PKV)                                                                                  \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      GNN_CUDA(cudaFuncSetAttribute(gat_bwd2_kernel<T, CPLV, WV, HTV, TR, PKV>,                                \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+    gat_bwd2_kernel<T, CPLV, WV, HTV, TR, PKV><<<grid, thrv, smem, st>>>(a);                                   \
   } while (0)
-  if (!seg) GNN_ROWS(false, 0);
-  else if (a.H == 8) GNN_ROWS(true, 8);
-  else if (a.H == 1) GNN_ROWS(true, 1);
-  else GNN_ROWS(true, 0);
-#undef GNN_ROWS
+#define GNN_BWD2(HTV)                                                \
+  do {                                                               \
+    if constexpr (sizeof(T) == 2 && CPLV >= 2) {                     \
+      if (a.packed) GNN_BWD2_PK(HTV, 2);                             \
+      else GNN_BWD2_PK(HTV, 1);                                      \
+    } else {                                                         \
+      GNN_BWD2_PK(HTV, 1);                                           \
+    }                                                                \
+  } while (0)
+  if (a.H == 8) GNN_BWD2(8);
+  else if (a.H == 1) GNN_BWD2(1);
+  else GNN_BWD2(0);
+#undef GNN_BWD2
+#undef GNN_BWD2_PK
   GNN_LAUNCH_CHECK();
   return GNN_OK;
 }
 
-template <typename T, int WV>
-int gat_bwd_rows_dispatch(const GatArgs& a, int cplr, bool seg, unsigned grid, cudaStream_t st) {
+template <typename T, int WV, bool TR>
+int gat_bwd2_dispatch(const GatArgs& a, int cplr, unsigned grid, cudaStream_t st) {
   switch (cplr) {
-    case 1: return gat_bwd_rows_launch<T, 1, WV>(a, seg, grid, st);
-    case 2: return gat_bwd_rows_launch<T, 2, WV>(a, seg, grid, st);
-    case 4: return gat_bwd_rows_launch<T, 4, WV>(a, seg, grid, st);
-    default: return gat_bwd_rows_launch<T, 8, WV>(a, seg, grid, st);
+    case 1: return gat_bwd2_launch<T, 1, WV, TR>(a, grid, st);
+    case 2: return gat_bwd2_launch<T, 2, WV, TR>(a, grid, st);
+    case 4: return gat_bwd2_launch<T, 4, WV, TR>(a, grid, st);
+    default: return gat_bwd2_launch<T, 8, WV, TR>(a, grid, st);
   }
-}
-
-template <typename T, int WV>
-int gat_bwd_cols_dispatch(const GatArgs& a, int cplr, unsigned grid, cudaStream_t st) {
-  constexpr int thrv = GatBlock<WV>::kWarps * 32;
-  switch (cplr) {
-    case 1: gat_bwd_cols_kernel<T, 1, WV><<<grid, thrv, 0, st>>>(a); break;
-    case 2: gat_bwd_cols_kernel<T, 2, WV><<<grid, thrv, 0, st>>>(a); break;
-    case 4: gat_bwd_cols_kernel<T, 4, WV><<<grid, thrv, 0, st>>>(a); break;
-    default: gat_bwd_cols_kernel<T, 8, WV><<<grid, thrv, 0, st>>>(a); break;
-  }
-  GNN_LAUNCH_CHECK();
-  return GNN_OK;
 }
 
 template <typename T>
 int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
-                 const int64_t* perm_t, const int64_t* edge_to_tslot, const T* Wh, int64_t ldw, const float* s,
-                 const float* t, const float* row_max, const float* row_sum, const T* out_pre, const T* d_out,
-                 int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode, const float* edge_keep, T* d_Wh,
-                 int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot, float* edge_scratch, int64_t nnz,
-                 const int64_t* long_rows, int64_t n_long, const int64_t* long_rows_t, int64_t n_long_t,
-                 int64_t long_threshold, cudaStream_t st) {
+                 const int64_t* perm_t, const T* Wh, int64_t ldw, const float* s, const float* t, const float* row_max,
+                 const float* row_sum, const T* out_pre, const T* d_out, int64_t ldo, int64_t n, int32_t H, int32_t Fp,
+                 float alpha, int mode, const float* edge_keep, T* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
+                 float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long, const int64_t* long_rows_t,
+                 int64_t n_long_t, int64_t long_threshold, cudaStream_t st) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
   GNN_REQUIRE(rowptr && rowptr_t && Wh && s && t && row_max && row_sum && out_pre && d_out && d_Wh && d_s && d_t &&
-                  d_rowdot,
+                  row_scratch,
               GNN_ERR_BAD_ARG, "null pointer");
-  GNN_REQUIRE(nnz >= 0 && (nnz == 0 || (col && col_t && (perm_t || edge_to_tslot) && edge_scratch)), GNN_ERR_BAD_ARG,
-              "null edge pointer (col/col_t/perm_t|edge_to_tslot/edge_scratch)");
+  GNN_REQUIRE(nnz >= 0 && (nnz == 0 || (col && col_t)), GNN_ERR_BAD_ARG, "null edge pointer (col/col_t)");
+  GNN_REQUIRE(!edge_keep || perm_t || nnz == 0, GNN_ERR_BAD_ARG, "edge_keep needs perm_t (transposed slot -> edge slot)");
   GNN_REQUIRE(mode == GNN_GAT_SOFTMAX || mode == GNN_GAT_EXPNEG, GNN_ERR_BAD_ARG, "unknown mode %d", mode);
   const int HF = H * Fp;
   GNN_REQUIRE(ldw >= HF && ldo >= HF && ld_dwh >= HF, GNN_ERR_BAD_ARG, "leading dimension smaller than H*Fp");
@@ -791,65 +827,64 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
   a.mode = mode;
   a.keep = edge_keep;
   a.ldo = ldo;
-  a.row_max = const_cast<float*>(row_max);
-  a.row_sum = const_cast<float*>(row_sum);
-  a.SE = stage_edges(H);
+  a.SE = tuning("gat.bwd_stage_edges", 64);
+  while (a.SE > 32 && a.SE * H > 1024) a.SE >>= 1;
   a.out_pre = out_pre;
   a.d_out = d_out;
-  a.rowdot = d_rowdot;
+  a.rowstat = row_scratch;
   a.d_Wh = d_Wh;
   a.ld_dwh = ld_dwh;
   a.d_s = d_s;
   a.d_t = d_t;
-  a.edge_st = edge_scratch;
-  a.tslot = edge_to_tslot;
   {
     int64_t grid = (n * H + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 16;
     grid = grid > cap ? cap : grid;
-    gat_rowdot_kernel<T><<<(unsigned)grid, 256, 0, st>>>(d_out, out_pre, ldo, n, H, Fp, d_rowdot);
+    gat_rowstat_kernel<T><<<(unsigned)grid, 256, 0, st>>>(d_out, out_pre, ldo, s, row_max, row_sum, n, H, Fp,
+                                                         row_scratch);
     GNN_LAUNCH_CHECK();
   }
+  a.packed = sizeof(T) == 2 && Fp % 2 == 0 && ldw % 2 == 0 && ldo % 2 == 0 && aligned_to(Wh, 4) && aligned_to(d_out, 4);
   const int cpl = (HF + 31) / 32;
-  const int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
+  int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
+  if (a.packed && cplr < 2) cplr = 2;
   const bool coop = cooperative(n, nnz);
-  const bool seg = (H == 1) || (Fp <= 32 && (Fp & (Fp - 1)) == 0);
   const unsigned grid1 = (unsigned)((n + kGatWarps - 1) / kGatWarps);
   GNN_REQUIRE((n_long == 0 || long_rows) && (n_long_t == 0 || long_rows_t) &&
                   ((n_long == 0 && n_long_t == 0) || long_threshold > 0),
               GNN_ERR_BAD_ARG, "inconsistent long-row lists");
-  // kernel A over the forward CSR.  W: 1 warp per row, 4 = every row a CTA (dense graphs), 16 = the listed hub rows
+  // pass 1 over the forward CSR: d_s.  W: 1 warp per row, 4 = every row a CTA (dense graphs), 16 = listed hub rows
   a.rowptr = rowptr;
   a.col = col;
   if (coop) {
-    rc = gat_bwd_rows_dispatch<T, 4>(a, cplr, seg, (unsigned)n, st);
+    rc = gat_bwd2_dispatch<T, 4, false>(a, cplr, (unsigned)n, st);
     if (rc != GNN_OK) return rc;
   } else {
     if (n_long > 0) {
       a.row_list = long_rows;
-      rc = gat_bwd_rows_dispatch<T, 16>(a, cplr, seg, (unsigned)n_long, st);
+      rc = gat_bwd2_dispatch<T, 16, false>(a, cplr, (unsigned)n_long, st);
       if (rc != GNN_OK) return rc;
       a.row_list = nullptr;
       a.skip_deg_gt = long_threshold;
     }
-    rc = gat_bwd_rows_dispatch<T, 1>(a, cplr, seg, grid1, st);
+    rc = gat_bwd2_dispatch<T, 1, false>(a, cplr, grid1, st);
     if (rc != GNN_OK) return rc;
   }
-  // kernel B over the transposed CSR (the stash is in its own slot order when edge_to_tslot was given)
+  // pass 2 over the transposed CSR: d_Wh and d_t
   a.rowptr = rowptr_t;
   a.col = col_t;
-  a.perm = edge_to_tslot ? nullptr : perm_t;
+  a.perm = perm_t;
   a.row_list = nullptr;
   a.skip_deg_gt = 0;
-  if (coop) return gat_bwd_cols_dispatch<T, 4>(a, cplr, (unsigned)n, st);
+  if (coop) return gat_bwd2_dispatch<T, 4, true>(a, cplr, (unsigned)n, st);
   if (n_long_t > 0) {
     a.row_list = long_rows_t;
-    rc = gat_bwd_cols_dispatch<T, 16>(a, cplr, (unsigned)n_long_t, st);
+    rc = gat_bwd2_dispatch<T, 16, true>(a, cplr, (unsigned)n_long_t, st);
     if (rc != GNN_OK) return rc;
     a.row_list = nullptr;
     a.skip_deg_gt = long_threshold;
   }
-  return gat_bwd_cols_dispatch<T, 1>(a, cplr, grid1, st);
+  return gat_bwd2_dispatch<T, 1, true>(a, cplr, grid1, st);
 }
 
 }  // namespace
@@ -891,32 +926,28 @@ int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void
 }
 
 int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
-                          const int64_t* perm_t, const int64_t* edge_to_tslot, const float* Wh, int64_t ldw,
-                          const float* s, const float* t, const float* row_max, const float* row_sum,
-                          const float* out_pre, const float* d_out, int64_t ldo, int64_t n, int32_t H, int32_t Fp,
-                          float alpha, int mode, const float* edge_keep, float* d_Wh, int64_t ld_dwh, float* d_s,
-                          float* d_t, float* d_rowdot, float* edge_scratch, int64_t nnz, const int64_t* long_rows,
-                          int64_t n_long, const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
-                          gnn_stream_t stream) {
-  return gat_bwd_impl<float>(rowptr, col, rowptr_t, col_t, perm_t, edge_to_tslot, Wh, ldw, s, t, row_max, row_sum,
-                             out_pre, d_out, ldo, n, H, Fp, alpha, mode, edge_keep, d_Wh, ld_dwh, d_s, d_t, d_rowdot,
-                             edge_scratch, nnz, long_rows, n_long, long_rows_t, n_long_t, long_threshold,
-                             (cudaStream_t)stream);
+                          const int64_t* perm_t, const float* Wh, int64_t ldw, const float* s, const float* t,
+                          const float* row_max, const float* row_sum, const float* out_pre, const float* d_out,
+                          int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
+                          const float* edge_keep, float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
+                          float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
+                          const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, gnn_stream_t stream) {
+  return gat_bwd_impl<float>(rowptr, col, rowptr_t, col_t, perm_t, Wh, ldw, s, t, row_max, row_sum, out_pre, d_out, ldo,
+                             n, H, Fp, alpha, mode, edge_keep, d_Wh, ld_dwh, d_s, d_t, row_scratch, nnz, long_rows,
+                             n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream);
 }
 
 int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
-                           const int64_t* perm_t, const int64_t* edge_to_tslot, const void* Wh, int64_t ldw,
-                           const float* s, const float* t, const float* row_max, const float* row_sum,
-                           const void* out_pre, const void* d_out, int64_t ldo, int64_t n, int32_t H, int32_t Fp,
-                           float alpha, int mode, const float* edge_keep, void* d_Wh, int64_t ld_dwh, float* d_s,
-                           float* d_t, float* d_rowdot, float* edge_scratch, int64_t nnz, const int64_t* long_rows,
-                           int64_t n_long, const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
-                           gnn_stream_t stream) {
-  return gat_bwd_impl<__nv_bfloat16>(rowptr, col, rowptr_t, col_t, perm_t, edge_to_tslot, (const __nv_bfloat16*)Wh, ldw,
-                                     s, t, row_max, row_sum, (const __nv_bfloat16*)out_pre, (const __nv_bfloat16*)d_out,
-                                     ldo, n, H, Fp, alpha, mode, edge_keep, (__nv_bfloat16*)d_Wh, ld_dwh, d_s, d_t,
-                                     d_rowdot, edge_scratch, nnz, long_rows, n_long, long_rows_t, n_long_t,
-                                     long_threshold, (cudaStream_t)stream);
+                           const int64_t* perm_t, const void* Wh, int64_t ldw, const float* s, const float* t,
+                           const float* row_max, const float* row_sum, const void* out_pre, const void* d_out,
+                           int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
+                           const float* edge_keep, void* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
+                           float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
+                           const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, gnn_stream_t stream) {
+  return gat_bwd_impl<__nv_bfloat16>(rowptr, col, rowptr_t, col_t, perm_t, (const __nv_bfloat16*)Wh, ldw, s, t, row_max,
+                                     row_sum, (const __nv_bfloat16*)out_pre, (const __nv_bfloat16*)d_out, ldo, n, H, Fp,
+                                     alpha, mode, edge_keep, (__nv_bfloat16*)d_Wh, ld_dwh, d_s, d_t, row_scratch, nnz,
+                                     long_rows, n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream);
 }
 
 }  // extern "C"

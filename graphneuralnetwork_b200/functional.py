@@ -537,7 +537,6 @@ class _GatFn(torch.autograd.Function):
         fn = lib.gnn_gat_fused_bwd_f32 if Wh.dtype == torch.float32 else lib.gnn_gat_fused_bwd_bf16
         groups = list(_gat_groups(H, Fp))
         esz = Wh.element_size()
-        tslot = g.perm_t_inv
         for gi, (h0, h1, f0, f1) in enumerate(groups):
             whole = len(groups) == 1
             Hg, Fg = h1 - h0, f1 - f0
@@ -549,12 +548,11 @@ class _GatFn(torch.autograd.Function):
             rs = row_sum if whole else row_sum[:, h0:h1].contiguous()
             ds = d_s if whole else torch.empty((n, Hg), dtype=torch.float32, device=dev)
             dt = d_t if whole else torch.empty((n, Hg), dtype=torch.float32, device=dev)
-            rowdot = torch.empty((n, Hg), dtype=torch.float32, device=dev)
-            scratch = torch.empty((max(g.nnz, 1), 2, Hg), dtype=torch.float32, device=dev)
-            _lib.check(fn(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t), _p(tslot),
+            row_scratch = torch.empty((n, 4, Hg), dtype=torch.float32, device=dev)
+            _lib.check(fn(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t) if kg is not None else None,
                           Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), _p(rm), _p(rs), out.data_ptr() + c0 * esz,
                           d_out.data_ptr() + c0 * esz, _ld(out), n, Hg, Fg, alpha, mode, _p(kg),
-                          d_Wh.data_ptr() + c0 * esz, _ld(d_Wh), _p(ds), _p(dt), _p(rowdot), _p(scratch), g.nnz, _p(lr),
+                          d_Wh.data_ptr() + c0 * esz, _ld(d_Wh), _p(ds), _p(dt), _p(row_scratch), g.nnz, _p(lr),
                           lr.numel(), _p(lrt), lrt.numel(), thr, _stream_ptr()), "gnn_gat_fused_bwd")
             if not whole:
                 # dz is linear in (head dot, row dot): the tiles of one head add up (first tile assigns)

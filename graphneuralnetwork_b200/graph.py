@@ -97,17 +97,6 @@ class CSRGraph:
         self.transpose()
         return self._perm_t
 
-    @property
-    def perm_t_inv(self) -> torch.Tensor:
-        """int64 [nnz]: slot of the transposed CSR that holds forward edge slot e (the inverse of perm_t);
-        cached with the pattern.  The attention backward writes its per-edge stash through it."""
-        if getattr(self, "_perm_t_inv", None) is None:
-            pt = self.perm_t
-            inv = torch.empty_like(pt)
-            inv[pt] = torch.arange(pt.numel(), dtype=torch.int64, device=pt.device)
-            self._perm_t_inv = inv
-        return self._perm_t_inv
-
     def long_rows(self) -> torch.Tensor:
         """Rows whose nnz exceeds the spmm.long_row knob (host-side plan, cached)."""
         if self._long_rows is None:

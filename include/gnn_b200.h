@@ -288,33 +288,34 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
                           float* row_max, float* row_sum,
                           const int64_t* long_rows /*nullable*/, int64_t n_long, int64_t long_threshold,
                           gnn_stream_t stream);
-/* Backward.  d_out is the gradient w.r.t. the PRE-activation aggregate (the wrapper
- * applies the ELU derivative); out_pre is that aggregate.  Produces
- *   d_s [n,H]   (row-parallel over the CSR),
- *   d_Wh [n,H*Fp] and d_t [n,H] (row-parallel over the transposed CSR: rowptr_t/col_t,
- *   with perm_t mapping transposed slots to the forward edge slots of edge_scratch).
- * Both passes are ordered reductions — the edge-gradient SDDMM (layers.py:59-61) and the
- * transpose SpMM (layers.py:63) without the dense N×N intermediate and without atomics.
- * edge_to_tslot (the inverse of perm_t: forward edge slot -> transposed slot; CSRGraph.perm_t_inv):
- * when given, the first pass writes its per-edge stash (attention weight, dz) straight into the
- * order the second pass walks, which then streams it instead of chasing perm_t with one random
- * 32-byte read per edge (r01: 26.5 ms backward vs 7.6 ms forward on the full Reddit shape). */
+/* Backward.  d_out is the gradient w.r.t. the PRE-activation aggregate (the wrapper applies the ELU
+ * derivative); out_pre is that aggregate.  Produces
+ *   d_s [n,H]                       (pass 1, row-parallel over the CSR),
+ *   d_Wh [n,H*Fp] and d_t [n,H]     (pass 2, row-parallel over the transposed CSR rowptr_t/col_t).
+ * Both passes have the forward kernel's shape, because the edge gradient
+ *   dz_ij = a_ij * slope_ij * (keep_ij * <dOut_i, Wh_j> - D_i),  D_i = <dOut_i, out_pre_i>   (per head)
+ * factorises into weighted row sums: d_s[i] = <dOut_i, sum_j w2_ij Wh_j> - D_i sum_j a_ij slope_ij,
+ * d_t[j] = <Wh_j, sum_i w2_ij dOut_i> - sum_i a_ij slope_ij D_i, d_Wh[j] = sum_i w1_ij dOut_i (w1 = keep*a,
+ * w2 = w1*slope).  This is the edge-gradient SDDMM (GAT/models/layers.py:59-61) and the transpose SpMM
+ * (layers.py:63) without the dense N x N intermediate, without per-edge dot products, without a per-edge
+ * stash between the passes and without atomics: ordered sums only.
+ * perm_t (transposed slot -> forward edge slot) is read only when edge_keep is given.
+ * row_scratch: [n,4,H] fp32 scratch (per-row s, max, 1/sum, D packed for the transposed pass). */
 int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
-                          const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t,
-                          const int64_t* edge_to_tslot /*nullable [nnz]: inverse of perm_t*/,
+                          const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t /*nullable*/,
                           const float* Wh, int64_t ldw, const float* s, const float* t,
                           const float* row_max, const float* row_sum,
                           const float* out_pre, const float* d_out, int64_t ldo,
                           int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
                           const float* edge_keep,
-                          float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot /*[n,H] scratch*/,
-                          float* edge_scratch /*[nnz,2,H]: per-edge attention weight and dz*/, int64_t nnz,
+                          float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* row_scratch /*[n,4,H]*/,
+                          int64_t nnz,
                           const int64_t* long_rows, int64_t n_long /*forward CSR*/,
                           const int64_t* long_rows_t, int64_t n_long_t /*transposed CSR*/, int64_t long_threshold,
                           gnn_stream_t stream);
 /* bf16-feature variants (north_star: "bf16-feature variants within 1e-2"): Wh, out, out_pre, d_out and
- * d_Wh are bf16; the scores s/t, the softmax statistics, the per-edge stash and every accumulation
- * stay fp32.  Same reference call site (GAT/models/layers.py:22-37). */
+ * d_Wh are bf16; the scores s/t, the softmax statistics and every accumulation stay fp32.
+ * Same reference call site (GAT/models/layers.py:22-37). */
 int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw,
                            const float* s, const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp,
                            float alpha, int mode, int apply_elu, const float* col_mean,
@@ -324,14 +325,13 @@ int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void
                            gnn_stream_t stream);
 int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col,
                            const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t,
-                           const int64_t* edge_to_tslot,
                            const void* Wh, int64_t ldw, const float* s, const float* t,
                            const float* row_max, const float* row_sum,
                            const void* out_pre, const void* d_out, int64_t ldo,
                            int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
                            const float* edge_keep,
-                           void* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* d_rowdot,
-                           float* edge_scratch, int64_t nnz,
+                           void* d_Wh, int64_t ld_dwh, float* d_s, float* d_t, float* row_scratch,
+                           int64_t nnz,
                            const int64_t* long_rows, int64_t n_long,
                            const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
                            gnn_stream_t stream);

@@ -130,3 +130,11 @@ def sage_data_utils():
     with folder("GraphSAGE_Pytorch"):
         importlib.import_module("sample_utils")
         return load_file("GraphSAGE_Pytorch/data_utils.py", "ref_sage_data_utils")
+
+
+def gtn():
+    """GTN/models package (GTN_Model, norm, GTLayer, GTConv)."""
+    with folder("GTN"):
+        m = importlib.import_module("models.GTN")
+        return {"GTN": m, "GTLayer": importlib.import_module("models.GTLayer"),
+                "GTConv": importlib.import_module("models.GTConv")}

@@ -233,14 +233,41 @@ def make_special_spmm():
          out=out.detach().numpy(), grad_values=values.grad.numpy(), grad_b=b.grad.numpy(), shape=np.array([n, m]))
 
 
+def make_gtn():
+    """GTN_Model forward + backward (GTN/models/GTN.py) on a small 4-edge-type graph: the learned adjacency the final
+    gcn_conv aggregates over is the output of two dense metapath compositions."""
+    g = R.gtn()
+    n, E, C, w_in, w_out, classes = 60, 4, 2, 12, 8, 3
+    rng = np.random.default_rng(21)
+    A = (rng.random((n, n, E)) < 0.08).astype(np.float32)
+    A[:, :, E - 1] = np.eye(n, dtype=np.float32)  # the identity edge type GTN appends
+    X = rng.standard_normal((n, w_in)).astype(np.float32)
+    target = rng.choice(n, size=20, replace=False).astype(np.int64)
+    labels = rng.integers(0, classes, size=20)
+    torch.manual_seed(5)
+    model = g["GTN"].GTN_Model(E, C, w_in, w_out, classes, 2, True)
+    for m in model.modules():
+        if isinstance(m, g["GTConv"].GTConv):
+            torch.nn.init.normal_(m.weight, std=0.5)  # the reference leaves GTConv.weight uninitialised (GTConv.py:11)
+    y, _ = model(torch.from_numpy(A), torch.from_numpy(X), torch.from_numpy(target))
+    torch.nn.functional.cross_entropy(y, torch.from_numpy(labels)).backward()
+    H_in = torch.rand(n, n, generator=torch.Generator().manual_seed(3)) * (torch.rand(n, n, generator=torch.Generator().manual_seed(4)) < 0.2)
+    H_in.requires_grad_(True)
+    out = model.gcn_conv(torch.from_numpy(X), H_in)
+    Gout = torch.from_numpy(rng.standard_normal(out.shape).astype(np.float32))
+    (dH,) = torch.autograd.grad((out * Gout).sum(), H_in)
+    save("gtn_small.npz", A=A, X=X, target=target, labels=labels, y=y.detach().numpy(),
+         norm_false=g["GTN"].norm(H_in.detach(), False).numpy(), norm_true=g["GTN"].norm(H_in.detach(), True).numpy(),
+         H_in=H_in.detach().numpy(), conv_out=out.detach().numpy(), conv_gout=Gout.numpy(), conv_dH=dH.numpy(),
+         **{"param." + k: v for k, v in params_np(model).items()}, **grads_np(model))
+
+
 if __name__ == "__main__":
     assert R.available(), "reference not found"
     torch.set_num_threads(8)
-    make_gcn()
-    make_gat_small()
-    make_gat_cora()
-    make_sage()
-    make_sage_v2()
-    make_han()
-    make_gatne()
-    make_special_spmm()
+    makers = {"gcn": make_gcn, "gat_small": make_gat_small, "gat_cora": make_gat_cora, "sage": make_sage,
+              "sage_v2": make_sage_v2, "han": make_han, "gatne": make_gatne, "special_spmm": make_special_spmm,
+              "gtn": make_gtn}
+    # `python make_golden.py [name ...]`: only the named fixtures (the committed ones are not rewritten otherwise)
+    for name in (sys.argv[1:] or list(makers)):
+        makers[name]()

@@ -25,7 +25,7 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 1
     assert d["config"]["workload"].startswith("sage_reddit") and d["config"]["edges_per_step"] == 281600
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "minibatch" in cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "minibatch" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # same `config` object as the B200 arm prints (the driver compares them key by key)
     sys.path.insert(0, ROOT)

@@ -962,6 +962,33 @@ def test_spmm_values_learned_adjacency(lib):
 
 
 # ---------------------------------------------------------------- GATNE
+def test_gtn_dropin_vs_reference_golden(lib):
+    """GTN's `norm` (bit-exact) and `gcn_conv` over a LEARNED dense adjacency — pattern to CSR on
+    the device, O(nnz) normalisation, SpMM with gradients into the edge values — and the whole drop-in GTN_Model,
+    forward + every gradient, against the fixture of the unmodified reference (GTN/models/GTN.py:7-19, 49-52)."""
+    from graphneuralnetwork_b200.layers import gtn as lgtn
+    g = load_golden("gtn_small.npz")
+    H = cuda(g["H_in"]).requires_grad_(True)
+    # (bit-identical to the reference on the CPU: tests/test_oracle_vs_reference_live.py; on the device the
+    # reciprocal of `deg.pow(-1)` may round the last bit differently from the CPU's)
+    assert rel_err(lgtn.norm(H.detach(), False).cpu().numpy(), g["norm_false"]) < 1e-6
+    assert rel_err(lgtn.norm(H.detach(), True).cpu().numpy(), g["norm_true"]) < 1e-6
+    assert np.array_equal(lgtn.norm(H.detach().cpu(), True).numpy(), g["norm_true"])
+    W = cuda(g["param.weight"])
+    before = lib.gnn_launch_count()
+    out = lgtn.gcn_conv(cuda(g["X"]), H, W)
+    assert lib.gnn_launch_count() > before  # the aggregation ran in libgnn_b200.so, not as a dense torch.mm
+    assert rel_err(out.detach().cpu().numpy(), g["conv_out"]) < TOL32
+    (out * cuda(g["conv_gout"])).sum().backward()
+    assert rel_err(H.grad.cpu().numpy(), g["conv_dH"]) < TOL32  # edge-gradient SDDMM scattered back into dense H
+    model = layers.GTN_Model(4, 2, 12, 8, 3, 2, True)
+    load_params(model, g, "param.")
+    y, Ws = model(cuda(g["A"]), cuda(g["X"]), cuda(g["target"]))
+    assert rel_err(y.detach().cpu().numpy(), g["y"]) < TOL32 and len(Ws) == 2
+    torch.nn.functional.cross_entropy(y, cuda(g["labels"])).backward()
+    check_grads(model, g, tol=2e-5)
+
+
 def test_typed_gather_reduce_vs_oracle(lib):
     from oracle import gatne as ogatne
     rng = np.random.default_rng(4)

@@ -142,3 +142,18 @@ def test_special_spmm_forward_and_edge_gradients():
     g = load_golden("special_spmm.npz")
     out, gv, gb = ogat.special_spmm(g["indices"], g["values"], g["shape"], g["b"], g["G"])
     assert rel_err(out, g["out"]) < TOL and rel_err(gv, g["grad_values"]) < TOL and rel_err(gb, g["grad_b"]) < TOL
+
+
+def test_gtn_oracle_vs_reference_golden():
+    """GTN `norm` bit-exact, `gcn_conv` and the whole GTN_Model forward of the restatement against the fixture the
+    unmodified reference produced (GTN/models/GTN.py:7-19, 49-52, 62-88)."""
+    import torch
+    from oracle import gtn as ogtn
+    g = load_golden("gtn_small.npz")
+    H = torch.from_numpy(g["H_in"])
+    assert np.array_equal(ogtn.norm(H, False).numpy(), g["norm_false"])
+    assert np.array_equal(ogtn.norm(H, True).numpy(), g["norm_true"])
+    P = {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")}
+    assert rel_err(ogtn.gcn_conv(torch.from_numpy(g["X"]), H, P["weight"]).numpy(), g["conv_out"]) < 1e-6
+    y = ogtn.gtn_forward(torch.from_numpy(g["A"]), torch.from_numpy(g["X"]), torch.from_numpy(g["target"]), P, 2, 2)
+    assert rel_err(y.numpy(), g["y"]) < 1e-6

@@ -107,3 +107,24 @@ def test_gatne_encoders(seed):
         model = ctor()
         params = {k: v.detach() for k, v in model.state_dict().items()}
         assert _rel(ogatne.encoder_forward(params, inputs, types, neigh, f, agg), model(inputs, types, neigh).detach()) < TOL
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_gtn_norm_and_gcn_conv(seed):
+    """GTN/models/GTN.py:7-19 (norm, both modes, bit-exact) and :49-52 (gcn_conv) on fresh learned adjacencies,
+    including empty columns (deg 0 -> inf -> 0); the drop-in's element-wise `norm` is bit-identical too."""
+    from oracle import gtn as ogtn
+    from graphneuralnetwork_b200.layers import gtn as lgtn
+    ref = R.gtn()["GTN"]
+    g = torch.Generator().manual_seed(seed)
+    n = 50 + 7 * seed
+    H = torch.rand(n, n, generator=g) * (torch.rand(n, n, generator=g) < 0.15)
+    H[:, 3] = 0  # an empty column
+    for add in (False, True):
+        want = ref.norm(H, add)
+        assert torch.equal(ogtn.norm(H, add), want)
+        assert torch.equal(lgtn.norm(H, add), want)
+    torch.manual_seed(seed)
+    model = ref.GTN_Model(3, 2, 10, 6, 3, 1, True)
+    X = torch.randn(n, 10, generator=g)
+    assert _rel(ogtn.gcn_conv(X, H, model.weight.detach()), model.gcn_conv(X, H).detach()) < 1e-6

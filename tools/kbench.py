@@ -105,16 +105,24 @@ def bench_gat(args):
         Wh = torch.randn(n, H * Fp, device=DEV).to(fdt).requires_grad_(True)
         s = torch.randn(n, H, device=DEV, requires_grad=True)
         t = torch.randn(n, H, device=DEV, requires_grad=True)
+        for knobs in args.knobs:
+            for k, v in knobs.items():
+                _lib.set_tuning(k, v)
+            bench_gat_one(args, csr, Wh, s, t, H, Fp, n, tag, fdt, knobs)
+
+
+def bench_gat_one(args, csr, Wh, s, t, H, Fp, n, tag, fdt, knobs):
+    if True:
         med, best = timeit(lambda: Fn.gat_fwd_raw(csr, Wh.detach(), s.detach(), t.detach(), H, Fp, 0.2, elu=1), reps=args.reps)
         es = Wh.element_size()
         B = csr.nnz * (4 + H * Fp * es + H * 4) + n * (H * 4 + H * Fp * es) + (n + 1) * 8
-        emit(bench="gat_fwd", graph=tag, dtype=str(fdt), n=n, nnz=csr.nnz, ms=med, ms_best=best, gather_gbs=B / med / 1e6,
+        emit(bench="gat_fwd", graph=tag, dtype=str(fdt), knobs=knobs, n=n, nnz=csr.nnz, ms=med, ms_best=best, gather_gbs=B / med / 1e6,
              edges_per_s=csr.nnz / med * 1e3)
         csr.transpose()
         out = Fn.gat_aggregate(csr, Wh, s, t, H, Fp, 0.2)
         g = torch.randn_like(out)
         med, best = timeit(lambda: torch.autograd.grad(out, (Wh, s, t), g, retain_graph=True), reps=args.reps)
-        emit(bench="gat_bwd", graph=tag, dtype=str(fdt), n=n, nnz=csr.nnz, ms=med, ms_best=best, edges_per_s=csr.nnz / med * 1e3)
+        emit(bench="gat_bwd", graph=tag, dtype=str(fdt), knobs=knobs, n=n, nnz=csr.nnz, ms=med, ms_best=best, edges_per_s=csr.nnz / med * 1e3)
 
 
 if __name__ == "__main__":

@@ -26,7 +26,7 @@ FILES = {
     "HAN": ["models"],
     "GATNE_Pytorch": ["models/GATNE.py"],
     "GATNE": ["models/GATNE.py"],
-    "GTN": ["models/GTN.py"],
+    "GTN": ["models"],
 }
 
 
