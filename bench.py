@@ -670,7 +670,6 @@ def run_other_configs_cpu():
 # configs[4]: papers100M-shaped SpMM, 1-D row partition + NVLink halo exchange
 # ------------------------------------------------------------------------------------------
 PAPERS = dict(n=111_059_956, deg=13.55, F=128)
-PART_WAVES = 4  # row chunks / exchange waves of the partitioned SpMM (partition.py)
 GRAPHS = {
     "random": dict(p_local=0.0, window=0, scatter=True,
                    note="power-law, hub-skewed targets spread over the id range, NO locality: the worst case for "
@@ -715,7 +714,7 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("random", "locality"
         del deg_all
         rows = S.spmm_check_rows(csr, 4096, 17 + rank)
         ref_rows, ref_mag = S.spmm_sampled_reference(csr, rows, F, with_abs=True)
-        plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world, waves=PART_WAVES, F=F)
+        plan = build_halo_plan(csr.rowptr, csr.col, csr.val, bounds, rank, world, waves=None, F=F)  # automatic schedule
         del csr
         torch.cuda.empty_cache()
         op = PartitionedSpmm(plan, F, dev, transport="p2p")
@@ -749,8 +748,9 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("random", "locality"
                "schedule": {"waves": plan.waves, "two_pass_chunks": plan.two_pass_chunks,
                             "model_ms": {k: round(v, 2) for k, v in plan.model.items()
                                          if k.startswith("c0=") or k == "exchange_ms"}} if world > 1 else None,
-               "transport": "gnn_halo_push (TMA mover, one warp per SM) + per-wave arrival flags, overlapped with the "
-                            "local-column SpMM" if world > 1 else "none (single GPU)"}
+               "transport": ("gnn_halo_push_waves: single-launch TMA mover (%d CTAs x %d warps), arrival flags raised "
+                             "per wave from inside the kernel, overlapped with the local-column SpMM"
+                             % (op.mover_ctas, op.mover_warps)) if world > 1 else "none (single GPU)"}
         if world == 1:
             res["roofline"] = {"bound": "hbm", "achieved": B / ms / 1e6, "peak": peak, "unit": "GB/s",
                                "frac": B / ms / 1e6 / peak, "algorithmic_bytes": B,

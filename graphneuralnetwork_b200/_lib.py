@@ -53,11 +53,17 @@ SIGNATURES = {
     "gnn_gat_fused_fwd_f32": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr, ptr,
                                      i64, ptr, ptr, ptr, i64, i64, ptr]),
     "gnn_gat_fused_bwd_f32": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
-                                     i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64, ptr]),
+                                     i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64, cint,
+                                     ptr, ptr, ptr]),
+    "gnn_gat_fused_fwd_train_f32": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr,
+                                           ptr, ptr, ptr, i64, ptr, ptr, ptr, i64, i64, ptr]),
+    "gnn_gat_fused_fwd_train_bf16": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr,
+                                            ptr, ptr, ptr, i64, ptr, ptr, ptr, i64, i64, ptr]),
     "gnn_gat_fused_fwd_bf16": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr, ptr,
                                       i64, ptr, ptr, ptr, i64, i64, ptr]),
     "gnn_gat_fused_bwd_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
-                                      i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64, ptr]),
+                                      i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64, cint,
+                                      ptr, ptr, ptr]),
     "gnn_synth_powerlaw_degrees": (cint, [i64, i64, f64, f64, i64, u64, ptr, ptr]),
     "gnn_synth_powerlaw_fill": (cint, [i64, i64, i64, ptr, f64, f64, i64, u64, ptr, ptr]),
     "gnn_synth_gcn_values": (cint, [i64, i64, ptr, ptr, ptr, ptr, ptr]),
@@ -83,6 +89,11 @@ class SpmmOpts(C.Structure):
                 ("relu", i32), ("bias", ptr), ("row_map", ptr), ("X2", ptr), ("ldx2", i64), ("split", i64),
                 ("long_rows", ptr), ("n_long", i64), ("long_threshold", i64), ("chunk_off", ptr), ("n_chunks", i64),
                 ("chunk_edges", i32), ("exclusion_smem_bytes", i32), ("workspace", ptr), ("workspace_bytes", size_t)]
+
+
+class GatDropout(C.Structure):
+    """gnn_gat_dropout of include/gnn_b200.h."""
+    _fields_ = [("struct_size", i32), ("p", f32), ("seed", u64), ("seed_dev", ptr)]
 
 
 class HaloOpts(C.Structure):

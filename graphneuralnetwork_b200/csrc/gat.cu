@@ -39,8 +39,14 @@ struct GatArgs {
   int mode;
   int elu;
   const float* col_mean;
-  const float* keep;
-  void* out;             // T [n, ldo]
+  const float* keep;     // explicit post-softmax dropout factors [nnz, H] (parity tests); else the seeded stream below
+  float keep_prob;       // > 0 with drop_seed: keep an (edge, head) with this probability, scaled by drop_scale
+  float drop_scale;      // 1 / keep_prob
+  uint64_t drop_seed;    // host half of the seed
+  const int64_t* drop_seed_dev;  // device half (nullable): a captured CUDA graph draws a fresh mask per replay
+  void* out;             // T [n, ldo]: the aggregate (activated unless out_act is given)
+  void* out_act;         // T [n, ldo], nullable (training): out keeps the PRE-activation aggregate for the backward,
+                         //   out_act receives the activated one — the ELU(s) never run as separate launches
   int64_t ldo;
   float* row_max;
   float* row_sum;
@@ -117,8 +123,30 @@ __device__ __forceinline__ float stage_elem(typename RawOf<T>::type v, int c) {
   }
 }
 
+template <typename T>
+__device__ __forceinline__ float round_as(float v) {
+  if constexpr (sizeof(T) == 2) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
 __device__ __forceinline__ void stv(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stv(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// Counter-based dropout stream (splitmix64 of seed + (edge slot, head)): the SAME factor is recomputed by the
+// forward and by both backward passes from the forward edge slot, so no [nnz, H] mask is ever materialised
+// (layers.py:31 applies F.dropout to the dense N x N attention; parity is semantic — and bit-exact against
+// functional.attention_keep_mask_from_seed, the torch restatement of this hash).
+__device__ __forceinline__ uint64_t drop_seed_of(const GatArgs& a) {
+  uint64_t s = a.drop_seed;
+  if (a.drop_seed_dev) s ^= (uint64_t)__ldg(a.drop_seed_dev) * 0xD6E8FEB86659FD93ULL;
+  return s;
+}
+__device__ __forceinline__ float keep_factor(uint64_t seed, int64_t e, int h, int H, uint32_t thresh24, float scale) {
+  uint64_t z = seed + (uint64_t)(e * H + h + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 40) < thresh24 ? scale : 0.f;
+}
 
 __device__ __forceinline__ float act_elu(float x, int elu) {
   if (elu >= 1) x = elu1(x);
@@ -174,6 +202,10 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
   const int64_t d = e1 - e0;
   if (W == 1 && a.skip_deg_gt > 0 && d > a.skip_deg_gt) return;  // a long row: the CTA-per-row launch owns it
   T* orow = reinterpret_cast<T*>(a.out) + i * a.ldo;
+  T* arow = a.out_act ? reinterpret_cast<T*>(a.out_act) + i * a.ldo : nullptr;
+  const bool seeded = a.keep == nullptr && a.keep_prob > 0.f;
+  const uint64_t dseed = seeded ? drop_seed_of(a) : 0;
+  const uint32_t thresh24 = (uint32_t)(a.keep_prob * 16777216.f);
   if (d == 0) {
     // GAT/models/layers.py:28-30: an all -9e15 row soft-maxes to the uniform 1/N over ALL nodes
     if (wsub == 0) {
@@ -181,7 +213,9 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
       for (int c = 0; c < CPL; ++c)
         if (cv[c]) {
           const int ci = col_of<PK>(lane, c);
-          stv(orow + ci, act_elu(a.col_mean ? a.col_mean[ci] : 0.f, a.elu));
+          const float v0 = a.col_mean ? a.col_mean[ci] : 0.f;
+          stv(orow + ci, arow ? v0 : act_elu(v0, a.elu));
+          if (arow) stv(arow + ci, act_elu(v0, a.elu));
           if (ci % a.Fp == 0) {
             if (a.row_max) a.row_max[i * H + hc[c]] = 0.f;
             if (a.row_sum) a.row_sum[i * H + hc[c]] = 0.f;
@@ -272,8 +306,11 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
       float ps = 0.f;
       for (int idx = lane; idx < ne * H; idx += 32) {
         const float p = __expf(logit[idx] - mymax);
-        logit[idx] = p;
-        ps += p;
+        ps += p;  // the row sum is taken before the dropout (softmax first, layers.py:30-31)
+        float w = p;
+        if (a.keep) w *= __ldg(a.keep + (e0 + c0) * H + idx);
+        else if (seeded) w *= keep_factor(dseed, e0 + c0 + idx / (HT ? HT : 1), hsub, HT, thresh24, a.drop_scale);
+        logit[idx] = w;
       }
       for (int o = Hp; o < 32; o <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
       if (lane < H) lh[lane] += ps;
@@ -299,8 +336,12 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
           for (int c = 0; c < CPL; ++c)
             if (cv[c]) {
               const float p = pk[u * H + hc[c]];
-              if (!HT) l[c] += p;
-              const float w = a.keep ? p * __ldg(a.keep + (e0 + c0 + k0 + u) * H + hc[c]) : p;
+              float w = p;  // HT path: the dropout factor was folded into the staged weight in phase B2
+              if (!HT) {
+                l[c] += p;
+                if (a.keep) w *= __ldg(a.keep + (e0 + c0 + k0 + u) * H + hc[c]);
+                else if (seeded) w *= keep_factor(dseed, e0 + c0 + k0 + u, hc[c], H, thresh24, a.drop_scale);
+              }
               acc[c] = fmaf(w, stage_elem<T, PK>(x[u][c / PK], c), acc[c]);
             }
         }
@@ -318,7 +359,9 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
     for (int c = 0; c < CPL; ++c)
       if (cv[c]) {
         const int ci = col_of<PK>(lane, c);
-        stv(orow + ci, act_elu(acc[c] / l[c], a.elu));
+        const float v = acc[c] / l[c];
+        stv(orow + ci, arow ? v : act_elu(v, a.elu));
+        if (arow) stv(arow + ci, act_elu(v, a.elu));
         if (ci % a.Fp == 0) {
           if (a.row_max) a.row_max[i * H + hc[c]] = mh[hc[c]];
           if (a.row_sum) a.row_sum[i * H + hc[c]] = l[c];
@@ -348,7 +391,9 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
           L = fmaf(larr[(w * CPL + c) * 32 + lane], f, L);
           A = fmaf(aarr[(w * CPL + c) * 32 + lane], f, A);
         }
-        stv(orow + ci, act_elu(A / L, a.elu));
+        const float v = A / L;
+        stv(orow + ci, arow ? v : act_elu(v, a.elu));
+        if (arow) stv(arow + ci, act_elu(v, a.elu));
         if (ci % a.Fp == 0) {
           if (a.row_max) a.row_max[i * H + hc[c]] = M;
           if (a.row_sum) a.row_sum[i * H + hc[c]] = L;
@@ -381,12 +426,17 @@ __global__ void __launch_bounds__(256) gat_scores_kernel(const float* __restrict
 // Per-row statistics packed for the backward passes: rowstat[i] = [s_i | m_i | 1/l_i | D_i], H floats each, with
 // D_i[h] = <d_out_i[h,:], out_pre_i[h,:]> (the softmax-Jacobian term).  One 128-byte record per node (H = 8): the
 // transposed pass gathers it with one access per edge.
+// When the forward applied its ELU(s) in the kernel epilogue (apply_elu > 0), d_out is the gradient w.r.t. the
+// ACTIVATED output: the ELU derivative chain is applied here from the saved pre-activation (elu'(x) = 1 for x > 0,
+// exp(x) otherwise; the second ELU is evaluated at elu(x)) and the pre-activation gradient is written to d_pre,
+// which the two passes then gather — the activations' backward never runs as separate launches either.
 template <typename T>
 __global__ void __launch_bounds__(256) gat_rowstat_kernel(const T* __restrict__ d_out, const T* __restrict__ out_pre,
                                                           int64_t ldo, const float* __restrict__ s,
                                                           const float* __restrict__ row_max,
                                                           const float* __restrict__ row_sum, int64_t n, int H, int Fp,
-                                                          float* __restrict__ rowstat) {
+                                                          float* __restrict__ rowstat, int apply_elu,
+                                                          T* __restrict__ d_pre) {
   const int64_t total = n * H;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(p % H);
@@ -394,7 +444,20 @@ __global__ void __launch_bounds__(256) gat_rowstat_kernel(const T* __restrict__ 
     const T* a = d_out + i * ldo + h * Fp;
     const T* b = out_pre + i * ldo + h * Fp;
     float acc = 0.f;
-    for (int f = 0; f < Fp; ++f) acc = fmaf(ldv<T>(a + f), ldv<T>(b + f), acc);
+    for (int f = 0; f < Fp; ++f) {
+      float g = ldv<T>(a + f);
+      const float x = ldv<T>(b + f);
+      if (apply_elu > 0) {
+        if (apply_elu >= 2) {
+          const float y1 = elu1(x);
+          g *= y1 > 0.f ? 1.f : __expf(y1);
+        }
+        g *= x > 0.f ? 1.f : __expf(x);
+        stv(d_pre + i * ldo + h * Fp + f, g);
+        g = round_as<T>(g);  // the passes read the ROUNDED value (bf16): keep D consistent with them
+      }
+      acc = fmaf(g, x, acc);
+    }
     const float l = __ldg(row_sum + p);
     float* rs = rowstat + i * 4 * H;
     rs[h] = __ldg(s + p);
@@ -472,6 +535,9 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
     }
   }
   const bool vec4 = HT && (HT % 4 == 0) && aligned_to_dev(TR ? (const void*)a.rowstat : (const void*)a.t, 16);
+  const bool seeded = a.keep == nullptr && a.keep_prob > 0.f;
+  const uint64_t dseed = seeded ? drop_seed_of(a) : 0;
+  const uint32_t thresh24 = (uint32_t)(a.keep_prob * 16777216.f);
   const int ngrp = 32 / Hp;
   const int hsub = lane % Hp, g = lane / Hp;
   float qsum = 0.f;
@@ -484,7 +550,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
       const int o = __ldg(a.col + e);
       cols[k] = o;
       const float* ot = TR ? a.rowstat + (int64_t)o * 4 * H : a.t + (int64_t)o * H;
-      const int64_t kslot = (TR && a.perm) ? __ldg(a.perm + e) : e;
+      const int64_t kslot = (TR && a.perm && (a.keep || seeded)) ? __ldg(a.perm + e) : e;  // forward edge slot
       if (HT) {
         float v0[HT ? HT : 1], v1[HT ? HT : 1], v2[HT ? HT : 1], v3[HT ? HT : 1];
         if (vec4) {
@@ -524,7 +590,8 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
             slope = -slope;
           }
           const float al = __expf(ee - m) * li;
-          const float kp = a.keep ? __ldg(a.keep + kslot * H + h) : 1.f;
+          const float kp = a.keep ? __ldg(a.keep + kslot * H + h)
+                                  : (seeded ? keep_factor(dseed, kslot, h, H, thresh24, a.drop_scale) : 1.f);
           const float w1 = kp * al;
           w2s[k * H + h] = w1 * slope;
           if (TR) w1s[k * H + h] = w1;
@@ -542,7 +609,8 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
             slope = -slope;
           }
           const float al = __expf(ee - m) * li;
-          const float kp = a.keep ? __ldg(a.keep + kslot * H + h) : 1.f;
+          const float kp = a.keep ? __ldg(a.keep + kslot * H + h)
+                                  : (seeded ? keep_factor(dseed, kslot, h, H, thresh24, a.drop_scale) : 1.f);
           const float w1 = kp * al;
           w2s[k * H + h] = w1 * slope;
           if (TR) w1s[k * H + h] = w1;
@@ -704,11 +772,27 @@ int gat_fwd_dispatch(const GatArgs& a, int cpl, unsigned grid, cudaStream_t st) 
   }
 }
 
+inline int set_dropout(GatArgs& a, const float* edge_keep, const gnn_gat_dropout* d) {
+  a.keep = edge_keep;
+  if (d && d->p > 0.f) {
+    GNN_REQUIRE(d->struct_size == (int32_t)sizeof(gnn_gat_dropout), GNN_ERR_BAD_ARG,
+                "gnn_gat_dropout struct_size mismatch (header/library version skew)");
+    GNN_REQUIRE(d->p < 1.f, GNN_ERR_BAD_ARG, "dropout probability must be below 1");
+    GNN_REQUIRE(!edge_keep, GNN_ERR_BAD_ARG, "give either an explicit keep mask or a seeded dropout, not both");
+    a.keep_prob = 1.f - d->p;
+    a.drop_scale = 1.f / a.keep_prob;
+    a.drop_seed = d->seed;
+    a.drop_seed_dev = d->seed_dev;
+  }
+  return GNN_OK;
+}
+
 template <typename T>
 int gat_fwd_impl(const int64_t* rowptr, const int32_t* col, const T* Wh, int64_t ldw, const float* s, const float* t,
                  int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode, int apply_elu,
                  const float* col_mean, const float* edge_keep, T* out, int64_t ldo, float* row_max, float* row_sum,
-                 const int64_t* long_rows, int64_t n_long, int64_t long_threshold, cudaStream_t st) {
+                 const int64_t* long_rows, int64_t n_long, int64_t long_threshold, cudaStream_t st,
+                 T* out_act = nullptr, const gnn_gat_dropout* drop = nullptr) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
@@ -733,8 +817,10 @@ int gat_fwd_impl(const int64_t* rowptr, const int32_t* col, const T* Wh, int64_t
   a.mode = mode;
   a.elu = apply_elu;
   a.col_mean = col_mean;
-  a.keep = edge_keep;
+  rc = set_dropout(a, edge_keep, drop);
+  if (rc != GNN_OK) return rc;
   a.out = out;
+  a.out_act = out_act;
   a.ldo = ldo;
   a.row_max = row_max;
   a.row_sum = row_sum;
@@ -801,7 +887,8 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
                  const float* row_sum, const T* out_pre, const T* d_out, int64_t ldo, int64_t n, int32_t H, int32_t Fp,
                  float alpha, int mode, const float* edge_keep, T* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
                  float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long, const int64_t* long_rows_t,
-                 int64_t n_long_t, int64_t long_threshold, cudaStream_t st) {
+                 int64_t n_long_t, int64_t long_threshold, cudaStream_t st, int apply_elu = 0, T* d_pre = nullptr,
+                 const gnn_gat_dropout* drop = nullptr) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
@@ -809,7 +896,10 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
                   row_scratch,
               GNN_ERR_BAD_ARG, "null pointer");
   GNN_REQUIRE(nnz >= 0 && (nnz == 0 || (col && col_t)), GNN_ERR_BAD_ARG, "null edge pointer (col/col_t)");
-  GNN_REQUIRE(!edge_keep || perm_t || nnz == 0, GNN_ERR_BAD_ARG, "edge_keep needs perm_t (transposed slot -> edge slot)");
+  GNN_REQUIRE(!(edge_keep || (drop && drop->p > 0.f)) || perm_t || nnz == 0, GNN_ERR_BAD_ARG,
+              "attention dropout needs perm_t (transposed slot -> forward edge slot)");
+  GNN_REQUIRE(apply_elu >= 0 && apply_elu <= 2 && (apply_elu == 0 || d_pre), GNN_ERR_BAD_ARG,
+              "apply_elu must be 0..2 and needs the d_pre scratch when > 0");
   GNN_REQUIRE(mode == GNN_GAT_SOFTMAX || mode == GNN_GAT_EXPNEG, GNN_ERR_BAD_ARG, "unknown mode %d", mode);
   const int HF = H * Fp;
   GNN_REQUIRE(ldw >= HF && ldo >= HF && ld_dwh >= HF, GNN_ERR_BAD_ARG, "leading dimension smaller than H*Fp");
@@ -825,12 +915,13 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
   a.HF = HF;
   a.alpha = alpha;
   a.mode = mode;
-  a.keep = edge_keep;
+  rc = set_dropout(a, edge_keep, drop);
+  if (rc != GNN_OK) return rc;
   a.ldo = ldo;
   a.SE = tuning("gat.bwd_stage_edges", 64);
   while (a.SE > 32 && a.SE * H > 1024) a.SE >>= 1;
   a.out_pre = out_pre;
-  a.d_out = d_out;
+  a.d_out = apply_elu > 0 ? d_pre : d_out;  // the passes gather the PRE-activation gradient
   a.rowstat = row_scratch;
   a.d_Wh = d_Wh;
   a.ld_dwh = ld_dwh;
@@ -841,10 +932,11 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
     const int64_t cap = (int64_t)num_sms() * 16;
     grid = grid > cap ? cap : grid;
     gat_rowstat_kernel<T><<<(unsigned)grid, 256, 0, st>>>(d_out, out_pre, ldo, s, row_max, row_sum, n, H, Fp,
-                                                         row_scratch);
+                                                         row_scratch, apply_elu, d_pre);
     GNN_LAUNCH_CHECK();
   }
-  a.packed = sizeof(T) == 2 && Fp % 2 == 0 && ldw % 2 == 0 && ldo % 2 == 0 && aligned_to(Wh, 4) && aligned_to(d_out, 4);
+  a.packed = sizeof(T) == 2 && Fp % 2 == 0 && ldw % 2 == 0 && ldo % 2 == 0 && aligned_to(Wh, 4) &&
+             aligned_to(a.d_out, 4);
   const int cpl = (HF + 31) / 32;
   int cplr = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 4 ? 4 : 8;
   if (a.packed && cplr < 2) cplr = 2;
@@ -925,16 +1017,43 @@ int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void
                                      long_rows, n_long, long_threshold, (cudaStream_t)stream);
 }
 
+int gnn_gat_fused_fwd_train_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw,
+                                const float* s, const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp,
+                                float alpha, int mode, int apply_elu, const float* col_mean, const float* edge_keep,
+                                const gnn_gat_dropout* dropout, float* out_pre, float* out_act, int64_t ldo,
+                                float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
+                                int64_t long_threshold, gnn_stream_t stream) {
+  GNN_REQUIRE(out_act || apply_elu == 0, GNN_ERR_BAD_ARG, "apply_elu > 0 needs out_act");
+  return gat_fwd_impl<float>(rowptr, col, Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode, apply_elu, col_mean, edge_keep,
+                             out_pre, ldo, row_max, row_sum, long_rows, n_long, long_threshold, (cudaStream_t)stream,
+                             apply_elu > 0 ? out_act : nullptr, dropout);
+}
+
+int gnn_gat_fused_fwd_train_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw,
+                                 const float* s, const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp,
+                                 float alpha, int mode, int apply_elu, const float* col_mean, const float* edge_keep,
+                                 const gnn_gat_dropout* dropout, void* out_pre, void* out_act, int64_t ldo,
+                                 float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
+                                 int64_t long_threshold, gnn_stream_t stream) {
+  GNN_REQUIRE(out_act || apply_elu == 0, GNN_ERR_BAD_ARG, "apply_elu > 0 needs out_act");
+  return gat_fwd_impl<__nv_bfloat16>(rowptr, col, (const __nv_bfloat16*)Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode,
+                                     apply_elu, col_mean, edge_keep, (__nv_bfloat16*)out_pre, ldo, row_max, row_sum,
+                                     long_rows, n_long, long_threshold, (cudaStream_t)stream,
+                                     apply_elu > 0 ? (__nv_bfloat16*)out_act : nullptr, dropout);
+}
+
 int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
                           const int64_t* perm_t, const float* Wh, int64_t ldw, const float* s, const float* t,
                           const float* row_max, const float* row_sum, const float* out_pre, const float* d_out,
                           int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
                           const float* edge_keep, float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
                           float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
-                          const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, gnn_stream_t stream) {
+                          const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, int apply_elu,
+                          float* d_pre, const gnn_gat_dropout* dropout, gnn_stream_t stream) {
   return gat_bwd_impl<float>(rowptr, col, rowptr_t, col_t, perm_t, Wh, ldw, s, t, row_max, row_sum, out_pre, d_out, ldo,
                              n, H, Fp, alpha, mode, edge_keep, d_Wh, ld_dwh, d_s, d_t, row_scratch, nnz, long_rows,
-                             n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream);
+                             n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream, apply_elu, d_pre,
+                             dropout);
 }
 
 int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
@@ -943,11 +1062,13 @@ int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col, const int6
                            int64_t ldo, int64_t n, int32_t H, int32_t Fp, float alpha, int mode,
                            const float* edge_keep, void* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
                            float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
-                           const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, gnn_stream_t stream) {
+                           const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, int apply_elu,
+                           void* d_pre, const gnn_gat_dropout* dropout, gnn_stream_t stream) {
   return gat_bwd_impl<__nv_bfloat16>(rowptr, col, rowptr_t, col_t, perm_t, (const __nv_bfloat16*)Wh, ldw, s, t, row_max,
                                      row_sum, (const __nv_bfloat16*)out_pre, (const __nv_bfloat16*)d_out, ldo, n, H, Fp,
                                      alpha, mode, edge_keep, (__nv_bfloat16*)d_Wh, ld_dwh, d_s, d_t, row_scratch, nnz,
-                                     long_rows, n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream);
+                                     long_rows, n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream,
+                                     apply_elu, (__nv_bfloat16*)d_pre, dropout);
 }
 
 }  // extern "C"

@@ -237,8 +237,24 @@ __global__ void halo_move_tma_waves_kernel(const WaveMoveArgs a) {
   const int64_t n_chunks = a.n_chunks;
   const int64_t w = (int64_t)blockIdx.x * n_warps + warp;
   const int64_t nw = (int64_t)gridDim.x * n_warps;
-  auto seek = [&](int& slot, int64_t c) {  // chunk ids only grow along a warp's walk
-    while (slot + 1 < a.n_segs && c >= __ldg(a.seg + (slot + 1) * 5 + 3)) ++slot;
+  // segment of chunk c: chunk ids only grow along a warp's walk, so a galloping step from the previous segment
+  // and a binary search inside the bracket (an interleaved table has tens of thousands of short segments and a
+  // warp skips gridDim * warps chunks per step)
+  auto seek = [&](int& slot, int64_t c) {
+    int lo = slot, step = 1;
+    int hi = lo + 1;
+    while (hi < a.n_segs && c >= __ldg(a.seg + hi * 5 + 3)) {
+      lo = hi;
+      hi += step;
+      step <<= 1;
+    }
+    if (hi > a.n_segs) hi = a.n_segs;
+    // invariant: first chunk of lo <= c, and (hi == n_segs or first chunk of hi > c)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (c >= __ldg(a.seg + mid * 5 + 3)) lo = mid; else hi = mid;
+    }
+    slot = lo;
   };
   int slot_l = 0, slot_i = 0, slot_s = 0;
   auto load_id = [&](int64_t c) -> int64_t {

@@ -34,6 +34,8 @@ struct RowArgs {
   int32_t F;
   int64_t skip_deg_gt;   // >0: rows with more edges are left to the long-row kernel
   int32_t* argmax;       // max only, nullable, [n_rows, ldy]
+  int32_t n_src_rows;    // >0: source ids >= n_src_rows contribute nothing (like negative ids) instead of reading
+                         //     out of bounds; the reference raises IndexError there (an id block is caller input)
 };
 
 constexpr int kRowReduceThreads = 256;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kRowReduceThreads) row_reduce_kernel(const Row
         const int jj = j0 + u;
         const int32_t cj = __shfl_sync(gmask, c, jj, GROUP);
         const float vj = __shfl_sync(gmask, v, jj, GROUP);
-        const bool ok = (jj < cnt) && (cj >= 0);
+        const bool ok = (jj < cnt) && (cj >= 0) && (a.n_src_rows <= 0 || cj < a.n_src_rows);
         vv[u] = ok ? vj : 0.f;
         const T* xr = a.X + (int64_t)(ok ? cj : 0) * a.ldx;
 #pragma unroll

@@ -46,6 +46,7 @@ struct SageArgs {
   int32_t stage_rows;                // ring stage capacity in rows (max kc)
   int32_t stages;
   int32_t nvec;                      // 16-byte vectors per row
+  int64_t n_table_rows;              // ids outside [0, n_table_rows) are skipped like negative (padding) ids
 };
 
 // Two fp32 adds in one instruction (SASS FADD2, sm_100): same round-to-nearest result as two
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
         rq[d] = load_id(look);
         if (look.g < total_src) cursor_next(look, a);
         mbar_wait(empty + stage, par ^ 1u);
-        const bool valid = r >= 0;
+        const bool valid = r >= 0 && r < a.n_table_rows;
         const unsigned m = __ballot_sync(0xffffffffu, valid);
         if (lane == 0) {
           mask[stage] = m;
@@ -377,6 +378,7 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, int32_t
     a.table = table;
     a.ld = ld;
     a.F = F;
+    a.n_table_rows = n_table_rows;
     a.row_bytes = row_bytes;
     a.nvec = row_bytes / 16;
     const int E = 16 / esz;
@@ -432,6 +434,7 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, int32_t
     r.val = nullptr;
     r.src_div = 0;
     r.scale = (reduce == GNN_REDUCE_MEAN) ? 1.0f / (float)k.fanout : 1.0f;
+    r.n_src_rows = (int32_t)n_table_rows;
     r.X = table;
     r.ldx = ld;
     r.Y = k.out;
@@ -532,6 +535,7 @@ int gnn_gather_reduce_typed_f32(const float* table, int64_t ld_row, int64_t n_no
   r.src_div = 0;
   r.src_mul = n_types;
   r.scale = (reduce == GNN_REDUCE_MEAN) ? 1.0f / (float)fanout : 1.0f;
+  r.n_src_rows = (int32_t)(n_nodes * (int64_t)n_types);
   r.X = table;
   r.ldx = ld_row;
   r.Y = out;

@@ -54,9 +54,9 @@ int spmm_impl(const int64_t* rowptr, const int32_t* col, const float* val, const
       GNN_REQUIRE(!(bias || relu), GNN_ERR_BAD_ARG, "two-table form has no bias/ReLU epilogue");
       GNN_REQUIRE(ex->split >= 0 && ex->split <= n_cols && ex->ldx2 >= F, GNN_ERR_BAD_ARG, "bad split / ldx2");
       GNN_REQUIRE(aligned_to(ex->X2, sizeof(T)), GNN_ERR_MISALIGNED, "X2 not element aligned");
-      a.X2 = (const T*)ex->X2;
       a.ldx2 = ex->ldx2;
       a.split = (int32_t)ex->split;
+      a.X2 = (const T*)ex->X2 - ex->split * ex->ldx2;  // pre-offset: column c >= split reads X2 + c * ldx2
     }
   }
   if (n_long > 0) {

@@ -37,8 +37,8 @@ struct SpmmArgs {
   // ---- row-subset / two-table form (gnn_spmm_csr_ex_*; the partitioned SpMM's wave consumers) ----
   const int32_t* row_map;  // nullable: the CSR is COMPACT (n_rows selected rows); row r writes Y row row_map[r]
   int64_t acc_prefix;      // compact rows [0, acc_prefix) accumulate into Y even when accumulate == 0
-  const T* X2;             // SPLIT kernels: a column id c >= split reads row (c - split) of X2 (the halo buffer)
-  int64_t ldx2;
+  const T* X2;             // SPLIT kernels: a column id c >= split reads row (c - split) of X2 (the halo buffer);
+  int64_t ldx2;            //   the host passes X2 pre-offset by -split rows, so the row is X2 + c * ldx2
   int32_t split;
   int32_t excl_smem;       // host only: token dynamic shared memory per CTA (keeps CTAs off SMs a mover filled)
 };
@@ -46,7 +46,11 @@ struct SpmmArgs {
 // source row of column id c (SPLIT: two tables, [0, split) -> X, [split, ...) -> X2)
 template <typename T, bool SPLIT>
 __device__ __forceinline__ const T* spmm_src_row(const SpmmArgs<T>& a, int32_t c) {
-  if (SPLIT) return (c < a.split) ? a.X + (int64_t)c * a.ldx : a.X2 + (int64_t)(c - a.split) * a.ldx2;
+  if (SPLIT) {
+    // one select of (base, stride) and one multiply-add: X2 arrives pre-offset by -split rows
+    const bool loc = c < a.split;
+    return (loc ? a.X : a.X2) + (int64_t)c * (loc ? a.ldx : a.ldx2);
+  }
   return a.X + (int64_t)c * a.ldx;
 }
 
@@ -379,7 +383,7 @@ inline void spmm_rbs_launch(const SpmmArgs<T>& a, cudaStream_t st) {
   // dedicated halo push has claimed (peer.cu); 0 outside the partitioned SpMM's local pass
   const size_t sm = (size_t)(a.excl_smem > 0 ? a.excl_smem : 0);
   constexpr int MINB_DEF = (CHUNKS == 1) ? 4 : ((CHUNKS <= 5) ? 3 : 1);
-  if (a.X2) {
+  if (a.split != 0x7fffffff) {
     // two-table form (never combined with the bias/ReLU epilogue: spmm_impl rejects that)
     spmm_rbs_kernel<T, VEC, GROUP, CHUNKS, U, false, MINB_DEF, true><<<(unsigned)grid, kSpmmThreads, sm, st>>>(a);
   } else if (a.bias || a.relu) {
@@ -398,7 +402,7 @@ inline int spmm_main_vec(const SpmmArgs<T>& a0, cudaStream_t st) {
   for (int c0 = 0; c0 < a0.F; c0 += tile_cols) {
     SpmmArgs<T> a = a0;
     a.X = a0.X + c0;
-    a.X2 = a0.X2 ? a0.X2 + c0 : nullptr;
+    a.X2 = (a0.split != 0x7fffffff) ? a0.X2 + c0 : nullptr;
     a.Y = a0.Y + c0;
     a.bias = a0.bias ? a0.bias + c0 : nullptr;
     a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
@@ -421,7 +425,7 @@ inline int spmm_main_vec(const SpmmArgs<T>& a0, cudaStream_t st) {
 template <typename T>
 inline int spmm_main(const SpmmArgs<T>& a, cudaStream_t st) {
   GNN_REQUIRE(a.n_rows < (1LL << 33), GNN_ERR_UNSUPPORTED, "too many rows");  // grid <= n_rows / 8
-  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F, a.X2, a.ldx2);
+  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F, (a.split != 0x7fffffff) ? a.X2 : nullptr, a.ldx2);
   if (sizeof(T) == 2 && vec == 8) return spmm_main_vec<T, (sizeof(T) == 2 ? 8 : 4)>(a, st);
   if (vec >= 4) return spmm_main_vec<T, 4>(a, st);
   if (vec == 2) return spmm_main_vec<T, 2>(a, st);
@@ -436,14 +440,14 @@ inline int spmm_long_vec(const SpmmArgs<T>& a0, const int64_t* long_rows, int64_
   for (int c0 = 0; c0 < a0.F; c0 += tile_cols) {
     SpmmArgs<T> a = a0;
     a.X = a0.X + c0;
-    a.X2 = a0.X2 ? a0.X2 + c0 : nullptr;
+    a.X2 = (a0.split != 0x7fffffff) ? a0.X2 + c0 : nullptr;
     a.F = (a0.F - c0) < tile_cols ? (a0.F - c0) : tile_cols;
     const int nvec = (a.F + VEC - 1) / VEC;
     const unsigned grid = (unsigned)n_chunks;
     const int thr = kLongChunkWarps * 32;
 #define GNN_LONG(G, C)                                                                                               \
   do {                                                                                                               \
-    if (a.X2)                                                                                                        \
+    if (a.split != 0x7fffffff)                                                                                       \
       spmm_long_chunk_kernel<T, VEC, G, C, true><<<grid, thr, 0, st>>>(a, long_rows, chunk_off, n_long, chunk_edges, \
                                                                        partial, ldp);                                \
     else                                                                                                             \
@@ -469,7 +473,7 @@ inline int spmm_long_vec(const SpmmArgs<T>& a0, const int64_t* long_rows, int64_
 template <typename T>
 inline int spmm_long(const SpmmArgs<T>& a, const int64_t* long_rows, int64_t n_long, const int64_t* chunk_off,
                      int64_t n_chunks, int chunk_edges, float* partial, cudaStream_t st) {
-  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F, a.X2, a.ldx2);
+  const int vec = spmm_pick_vec<T>(a.X, a.ldx, a.Y, a.ldy, a.F, (a.split != 0x7fffffff) ? a.X2 : nullptr, a.ldx2);
   if (sizeof(T) == 2 && vec == 8)
     return spmm_long_vec<T, (sizeof(T) == 2 ? 8 : 4)>(a, long_rows, n_long, chunk_off, n_chunks, chunk_edges, partial, st);
   if (vec >= 4) return spmm_long_vec<T, 4>(a, long_rows, n_long, chunk_off, n_chunks, chunk_edges, partial, st);

@@ -461,11 +461,87 @@ def _gat_groups(H: int, Fp: int):
                 yield h, h + 1, f0, min(Fp, f0 + 256)
 
 
+class AttentionDropout:
+    """Seeded post-softmax attention dropout (GAT/models/layers.py:31) for the fused kernels: probability `p`, a host
+    seed and a device int64 tensor mixed into it (so a captured CUDA graph draws a fresh mask per replay).  The
+    kernels recompute the keep factor of every (edge, head) from the stream — no [nnz, H] mask is materialised."""
+
+    def __init__(self, p: float, seed: int, seed_dev: Optional[torch.Tensor] = None):
+        self.p, self.seed, self.seed_dev = float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, seed_dev
+        assert seed_dev is None or (seed_dev.dtype == torch.int64 and seed_dev.is_cuda and seed_dev.numel() == 1)
+
+    def c_struct(self):
+        import ctypes as C
+        d = _lib.GatDropout()
+        d.struct_size = C.sizeof(_lib.GatDropout)
+        d.p, d.seed, d.seed_dev = self.p, self.seed, _p(self.seed_dev)
+        return d
+
+
+_drop_counters = {}
+
+
+def next_attention_dropout(p: float, device) -> AttentionDropout:
+    """A fresh dropout stream: host seed from torch's CPU generator (so torch.manual_seed controls it), device half =
+    a private copy of a per-device counter that is incremented IN PLACE on the stream — under CUDA-graph capture
+    the increment and the copy are replayed, hence a new mask per replay, and the forward and the backward of one
+    call see the same value."""
+    dev = torch.device(device)
+    ctr = _drop_counters.get(dev)
+    if ctr is None:
+        ctr = _drop_counters[dev] = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctr.add_(1)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator: no device synchronisation
+    return AttentionDropout(p, seed, ctr.clone())
+
+
+def attention_keep_mask_from_seed(g: CSRGraph, H: int, drop: AttentionDropout) -> torch.Tensor:
+    """The [nnz, H] keep factors the kernels derive from `drop` (torch restatement of keep_factor in csrc/gat.cu:
+    splitmix64 of seed + (edge slot * H + head + 1)), for tests and for inspecting a mask."""
+    M64 = (1 << 64) - 1
+
+    def s64(x):  # python int (mod 2^64) -> signed int64 value
+        x &= M64
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    def lsr(z, k):  # logical shift right on int64 tensors
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    seed = drop.seed
+    if drop.seed_dev is not None:
+        seed ^= (int(drop.seed_dev.item()) * 0xD6E8FEB86659FD93) & M64
+    idx = torch.arange(g.nnz * H, dtype=torch.int64, device=g.device) + 1
+    z = idx * s64(0x9E3779B97F4A7C15) + s64(seed)
+    z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    keep_prob = torch.tensor(1.0, dtype=torch.float32) - torch.tensor(drop.p, dtype=torch.float32)  # 1.f - p
+    thresh = int((keep_prob * 16777216.0).item())  # float32 arithmetic, as in the kernel
+    scale = float((1.0 / keep_prob).item())
+    keep = (lsr(z, 40) < thresh).to(torch.float32) * scale
+    return keep.view(g.nnz, H)
+
+
+def _gat_groups(H: int, Fp: int):
+    """Column groups one kernel call can take (H_g*Fp_g <= 256, H_g <= 32): whole heads when a head fits,
+    else column tiles of ONE head.  Yields (h0, h1, f0, f1): heads [h0,h1), columns [f0,f1) of each."""
+    if Fp <= 256:
+        per = max(1, min(32, 256 // Fp))
+        for h0 in range(0, H, per):
+            yield h0, min(H, h0 + per), 0, Fp
+    else:
+        for h in range(H):
+            for f0 in range(0, Fp, 256):
+                yield h, h + 1, f0, min(Fp, f0 + 256)
+
+
 def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=0, keep=None, save_stats=False,
-                out=None):
+                out=None, dropout: Optional[AttentionDropout] = None, out_act: Optional[torch.Tensor] = None):
     """Forward of the fused attention aggregation (no autograd).  Wh fp32 or bf16 ([n, H*Fp]); s, t fp32 [n,H];
     `out` has Wh's dtype.  Layers wider than one call's 256 columns (e.g. 8 heads x 64) are run as head groups /
-    column tiles of a head; the softmax statistics are per head, so a tiled head recomputes them per tile."""
+    column tiles of a head; the softmax statistics are per head, so a tiled head recomputes them per tile.
+    Training form (`out_act` given): `out` receives the PRE-activation aggregate and `out_act` the activated one
+    (elu applied `elu` times) in the same launch.  `dropout`: seeded attention dropout (or `keep`: explicit mask)."""
     _require_cuda(Wh, s, t, keep)
     lib = _lib.load()
     Wh = _rowmajor(Wh)
@@ -480,12 +556,30 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
         out = torch.empty((n, H * Fp), dtype=Wh.dtype, device=Wh.device)
     elif out.shape != (n, H * Fp) or out.dtype != Wh.dtype or out.stride(1) != 1 or not out.is_cuda:
         raise _lib.GnnError("gat: `out` must be a CUDA [n, H*Fp] view of Wh's dtype with unit column stride")
+    if out_act is not None and (out_act.shape != out.shape or out_act.dtype != out.dtype or
+                                out_act.stride() != out.stride()):
+        raise _lib.GnnError("gat: `out_act` must match `out` in shape, dtype and strides")
     row_max = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     row_sum = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     col_mean = Wh.float().mean(dim=0).contiguous() if g.has_empty_rows() else None
     lr, thr = g.gat_long_rows()
-    fn = lib.gnn_gat_fused_fwd_f32 if Wh.dtype == torch.float32 else lib.gnn_gat_fused_fwd_bf16
+    f32 = Wh.dtype == torch.float32
+    train = out_act is not None or (dropout is not None and dropout.p > 0.0)
+    pre_buf, act_buf = out, out_act
+    if train and out_act is None and elu > 0:
+        # seeded dropout without autograd (train mode under no_grad): the training entry point writes the
+        # activated aggregate to its second output; the pre-activation goes to a scratch buffer
+        pre_buf, act_buf = torch.empty_like(out), out
+    if train:
+        fn = lib.gnn_gat_fused_fwd_train_f32 if f32 else lib.gnn_gat_fused_fwd_train_bf16
+    else:
+        fn = lib.gnn_gat_fused_fwd_f32 if f32 else lib.gnn_gat_fused_fwd_bf16
     groups = list(_gat_groups(H, Fp))
+    if dropout is not None and dropout.p > 0.0 and len(groups) > 1:
+        # a head group restarts the head index at 0: materialise the stream once so every group sees its own heads
+        keep, dropout = attention_keep_mask_from_seed(g, H, dropout), None
+    dstruct = dropout.c_struct() if (dropout is not None and dropout.p > 0.0) else None
+    import ctypes as C
     for h0, h1, f0, f1 in groups:
         whole = len(groups) == 1
         Hg, Fg = h1 - h0, f1 - f0
@@ -497,9 +591,16 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
         rm = row_max if (whole or row_max is None) else torch.empty((n, Hg), dtype=torch.float32, device=Wh.device)
         rs = row_sum if (whole or row_sum is None) else torch.empty((n, Hg), dtype=torch.float32, device=Wh.device)
         esz = Wh.element_size()
-        _lib.check(fn(_p(g.rowptr), _p(g.col), Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), n, g.nnz, Hg, Fg,
-                      float(alpha), mode, elu, _p(cm), _p(kg), out.data_ptr() + c0 * esz, _ld(out), _p(rm), _p(rs),
-                      _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd")
+        if train:
+            _lib.check(fn(_p(g.rowptr), _p(g.col), Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), n, g.nnz, Hg, Fg,
+                          float(alpha), mode, elu if act_buf is not None else 0, _p(cm), _p(kg),
+                          C.byref(dstruct) if dstruct is not None else None, pre_buf.data_ptr() + c0 * esz,
+                          None if act_buf is None else act_buf.data_ptr() + c0 * esz, _ld(out), _p(rm), _p(rs),
+                          _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd_train")
+        else:
+            _lib.check(fn(_p(g.rowptr), _p(g.col), Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), n, g.nnz, Hg, Fg,
+                          float(alpha), mode, elu, _p(cm), _p(kg), out.data_ptr() + c0 * esz, _ld(out), _p(rm), _p(rs),
+                          _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd")
         if not whole and save_stats:
             row_max[:, h0:h1] = rm
             row_sum[:, h0:h1] = rs
@@ -507,23 +608,36 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
 
 
 class _GatFn(torch.autograd.Function):
+    """Fused attention aggregation with autograd.  Returns the ACTIVATED aggregate (elu applied `elu` times in the
+    kernel epilogue); the pre-activation aggregate is saved for the backward, which applies the ELU derivative
+    chain inside its first kernel — neither the activations nor their gradients are separate launches."""
+
     @staticmethod
-    def forward(ctx, Wh, s, t, g: CSRGraph, H, Fp, alpha, mode, keep):
+    def forward(ctx, Wh, s, t, g: CSRGraph, H, Fp, alpha, mode, keep, elu, dropout):
         Wh = _rowmajor(Wh)
-        out, row_max, row_sum = gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=0, keep=keep, save_stats=True)
-        ctx.g, ctx.cfg = g, (H, Fp, float(alpha), mode)
+        if dropout is not None and dropout.p > 0.0 and len(list(_gat_groups(H, Fp))) > 1:
+            keep, dropout = attention_keep_mask_from_seed(g, H, dropout), None
+        out_pre = torch.empty((g.n_rows, H * Fp), dtype=Wh.dtype, device=Wh.device)
+        out_act = torch.empty_like(out_pre) if elu > 0 else None
+        _, row_max, row_sum = gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep, save_stats=True,
+                                          out=out_pre, dropout=dropout, out_act=out_act)
+        ctx.g, ctx.cfg = g, (H, Fp, float(alpha), mode, int(elu))
+        ctx.dropout = dropout
         ctx.st_dtypes = (s.dtype, t.dtype)
-        ctx.save_for_backward(Wh, s.float().contiguous(), t.float().contiguous(), row_max, row_sum, out,
+        ctx.save_for_backward(Wh, s.float().contiguous(), t.float().contiguous(), row_max, row_sum, out_pre,
                               keep if keep is not None else torch.empty(0))
-        return out
+        return out_act if elu > 0 else out_pre
 
     @staticmethod
     def backward(ctx, d_out):
+        import ctypes as C
         Wh, s, t, row_max, row_sum, out, keep = ctx.saved_tensors
         g = ctx.g
-        H, Fp, alpha, mode = ctx.cfg
+        H, Fp, alpha, mode, elu = ctx.cfg
         lib = _lib.load()
         keep = keep if keep.numel() > 0 else None
+        drop = ctx.dropout if (ctx.dropout is not None and ctx.dropout.p > 0.0) else None
+        dstruct = drop.c_struct() if drop is not None else None
         n = g.n_rows
         d_out = d_out.to(Wh.dtype)
         if d_out.stride(1) != 1 or d_out.stride(0) != out.stride(0):
@@ -533,10 +647,12 @@ class _GatFn(torch.autograd.Function):
         d_Wh = torch.empty((n, H * Fp), dtype=Wh.dtype, device=dev)
         d_s = torch.empty((n, H), dtype=torch.float32, device=dev)
         d_t = torch.empty((n, H), dtype=torch.float32, device=dev)
+        d_pre = torch.empty_like(out) if elu > 0 else None
         (lr, thr), (lrt, _) = g.gat_long_rows(), gt.gat_long_rows()
         fn = lib.gnn_gat_fused_bwd_f32 if Wh.dtype == torch.float32 else lib.gnn_gat_fused_bwd_bf16
         groups = list(_gat_groups(H, Fp))
         esz = Wh.element_size()
+        need_perm = keep is not None or drop is not None
         for gi, (h0, h1, f0, f1) in enumerate(groups):
             whole = len(groups) == 1
             Hg, Fg = h1 - h0, f1 - f0
@@ -549,11 +665,13 @@ class _GatFn(torch.autograd.Function):
             ds = d_s if whole else torch.empty((n, Hg), dtype=torch.float32, device=dev)
             dt = d_t if whole else torch.empty((n, Hg), dtype=torch.float32, device=dev)
             row_scratch = torch.empty((n, 4, Hg), dtype=torch.float32, device=dev)
-            _lib.check(fn(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t) if kg is not None else None,
+            _lib.check(fn(_p(g.rowptr), _p(g.col), _p(gt.rowptr), _p(gt.col), _p(g.perm_t) if need_perm else None,
                           Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), _p(rm), _p(rs), out.data_ptr() + c0 * esz,
                           d_out.data_ptr() + c0 * esz, _ld(out), n, Hg, Fg, alpha, mode, _p(kg),
                           d_Wh.data_ptr() + c0 * esz, _ld(d_Wh), _p(ds), _p(dt), _p(row_scratch), g.nnz, _p(lr),
-                          lr.numel(), _p(lrt), lrt.numel(), thr, _stream_ptr()), "gnn_gat_fused_bwd")
+                          lr.numel(), _p(lrt), lrt.numel(), thr, elu,
+                          None if d_pre is None else d_pre.data_ptr() + c0 * esz,
+                          C.byref(dstruct) if dstruct is not None else None, _stream_ptr()), "gnn_gat_fused_bwd")
             if not whole:
                 # dz is linear in (head dot, row dot): the tiles of one head add up (first tile assigns)
                 if f0 == 0:
@@ -565,30 +683,26 @@ class _GatFn(torch.autograd.Function):
         if g.has_empty_rows():
             # rows without edges output the mean of all Wh rows (GAT/models/layers.py:28-30).  Sync-free
             # (no boolean-mask indexing): this runs inside CapturedTrainStep's CUDA-graph capture
-            d_Wh += ((d_out.float() * g.empty_row_mask().unsqueeze(1)).sum(dim=0, keepdim=True) / n).to(d_Wh.dtype)
-        return d_Wh, d_s.to(ctx.st_dtypes[0]), d_t.to(ctx.st_dtypes[1]), None, None, None, None, None, None
+            dpre = (d_pre if elu > 0 else d_out).float()
+            d_Wh += ((dpre * g.empty_row_mask().unsqueeze(1)).sum(dim=0, keepdim=True) / n).to(d_Wh.dtype)
+        return d_Wh, d_s.to(ctx.st_dtypes[0]), d_t.to(ctx.st_dtypes[1]), None, None, None, None, None, None, None, None
 
 
 def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tensor, H: int, Fp: int, alpha: float,
                   mode: int = _lib.GAT_SOFTMAX, elu: int = 0, keep: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Fused edge-score + LeakyReLU + edge-softmax + weighted aggregation over all H heads.
-
-    With gradients enabled the kernel returns the pre-activation aggregate and the ELU(s)
-    are applied by torch (elementwise, outside the hot path) so autograd can differentiate
-    them; without gradients the ELU is fused into the kernel's epilogue.
-    Wh may be fp32 or bf16 (the bf16-feature variant: bf16 rows, fp32 scores / softmax / accumulation)."""
+                  out: Optional[torch.Tensor] = None, dropout: Optional[AttentionDropout] = None) -> torch.Tensor:
+    """Fused edge-score + LeakyReLU + edge-softmax + weighted aggregation over all H heads, with the ELU(s) that
+    follow (elu = 0 | 1 | 2) in the kernel epilogue — with and without autograd.
+    Wh may be fp32 or bf16 (the bf16-feature variant: bf16 rows, fp32 scores / softmax / accumulation).
+    keep: explicit [nnz, H] post-softmax dropout factors (parity tests); dropout: seeded stream (training)."""
     need_grad = torch.is_grad_enabled() and (Wh.requires_grad or s.requires_grad or t.requires_grad)
     if not need_grad:
         # `out` (optional): a strided [n, H*Fp] view the kernel writes in place, e.g. one metapath's
         # slice of HAN's [N, M, H*Fp] semantic stack
-        return gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep, out=out)[0]
-    res = _GatFn.apply(Wh, s, t, g, H, Fp, alpha, mode, keep)
-    for _ in range(elu):
-        res = torch.nn.functional.elu(res)
+        return gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep, out=out, dropout=dropout)[0]
     if out is not None:
         raise _lib.GnnError("gat_aggregate: `out` is only supported without autograd")
-    return res
+    return _GatFn.apply(Wh, s, t, g, H, Fp, alpha, mode, keep, elu, dropout)
 
 
 def attention_keep_mask(g: CSRGraph, H: int, p: float, generator: Optional[torch.Generator] = None) -> torch.Tensor:

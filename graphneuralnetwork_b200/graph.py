@@ -165,14 +165,20 @@ class CSRGraph:
     # -- builders --------------------------------------------------------------------
     @staticmethod
     def from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int,
-                 return_perm: bool = False):
+                 return_perm: bool = False, validate: bool = True):
         """COO -> CSR, stable in row (gnn_build_csr_from_coo).  return_perm: also return the int64
-        input position of every CSR slot (values given in COO order are `val[perm]` in CSR order)."""
+        input position of every CSR slot (values given in COO order are `val[perm]` in CSR order).
+        validate: ids outside [0, n_rows) x [0, n_cols) raise IndexError here (one host read per graph build;
+        the reference's torch.spmm / indexing raises likewise) instead of becoming out-of-bounds accesses."""
         _require_cuda(row, col, val)
         lib = _lib.load()
         dev = row.device
         row = row.to(torch.int64).contiguous()
         col = col.to(torch.int64).contiguous()
+        if validate and row.numel():
+            bad = ((row < 0) | (row >= n_rows) | (col < 0) | (col >= n_cols)).any()
+            if bool(bad.item()):
+                raise IndexError(f"COO index out of range for a [{n_rows}, {n_cols}] adjacency")
         if val is not None:
             val = val.to(torch.float32).contiguous()
         nnz = int(row.numel())
@@ -259,10 +265,22 @@ class _AdjCache:
 adj_cache = _AdjCache()
 
 
-def index_block_transpose(idx: torch.Tensor, n_table_rows: int):
-    """Fixed-fanout index block -> (rowptr_t, pos_t) for the ordered gather backward."""
+_idx_transpose_cache = {}
+
+
+def index_block_transpose(idx: torch.Tensor, n_table_rows: int, cache: bool = True):
+    """Fixed-fanout index block -> (rowptr_t, pos_t) for the ordered gather backward.
+    cache: the transpose (a CUB sort) is kept per index TENSOR (identity + version guarded by a weakref, as the
+    adjacency caches are), so a block that is walked backward again — the same minibatch in the next epoch, or
+    several layers sharing one map — is sorted once."""
     _require_cuda(idx)
     lib = _lib.load()
+    key = (idx.data_ptr(), idx._version, tuple(idx.shape), idx.dtype, int(n_table_rows))
+    if cache:
+        hit = _idx_transpose_cache.get(key)
+        if hit is not None and hit[0]() is idx:
+            return hit[1]
+    src = idx
     idx = idx.contiguous().view(-1)
     bits = 32 if idx.dtype == torch.int32 else 64
     if idx.dtype not in (torch.int32, torch.int64):
@@ -275,4 +293,13 @@ def index_block_transpose(idx: torch.Tensor, n_table_rows: int):
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     _lib.check(lib.gnn_index_block_transpose(_p(idx), bits, n, n_table_rows, _p(rowptr_t), _p(pos_t), _p(ws), ws_bytes,
                                              _stream_ptr()), "gnn_index_block_transpose")
+    if cache:
+        for k in [k for k, (r, _) in _idx_transpose_cache.items() if r() is None]:
+            _idx_transpose_cache.pop(k)
+        if len(_idx_transpose_cache) >= 32:
+            _idx_transpose_cache.pop(next(iter(_idx_transpose_cache)))
+        try:
+            _idx_transpose_cache[key] = (weakref.ref(src), (rowptr_t, pos_t))
+        except TypeError:  # pragma: no cover
+            pass
     return rowptr_t, pos_t

@@ -13,8 +13,12 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from ..functional import attention_keep_mask, gat_aggregate, spmm_values
+from ..functional import attention_keep_mask, gat_aggregate, next_attention_dropout, spmm_values
 from ..graph import CSRGraph, adj_cache
+
+# True: draw the attention dropout as an explicit [nnz, H] mask (attention_keep_mask) instead of the seeded
+# in-kernel stream — the parity tests replay reference masks through this hook
+EXPLICIT_DROPOUT_MASK = False
 
 _pattern_cache = {}
 
@@ -73,10 +77,13 @@ def _fused_heads(x, adj, Ws, a_srcs, a_dsts, alpha, mode, elu, dropout, training
     # scores are fp32 even for bf16 features (the softmax statistics live in fp32)
     s = (Wh3.float() * a_src.float().unsqueeze(0)).sum(-1)  # [N,H] = Wh_i·a[:F']
     t = (Wh3.float() * a_dst.float().unsqueeze(0)).sum(-1)  # [N,H] = Wh_j·a[F':]
-    keep = None
-    if training and dropout > 0.0:
-        keep = attention_keep_mask(g, H, dropout)  # post-softmax dropout, layers.py:31
-    return gat_aggregate(g, Wh, s, t, H, Fp, alpha, mode=mode, elu=elu, keep=keep, out=out)
+    keep = drop = None
+    if training and dropout > 0.0:  # post-softmax dropout, layers.py:31
+        if EXPLICIT_DROPOUT_MASK:
+            keep = attention_keep_mask(g, H, dropout)
+        else:
+            drop = next_attention_dropout(dropout, Wh.device)  # seeded: no [nnz, H] mask is materialised
+    return gat_aggregate(g, Wh, s, t, H, Fp, alpha, mode=mode, elu=elu, keep=keep, out=out, dropout=drop)
 
 
 class GraphAttentionLayer(nn.Module):
@@ -168,7 +175,11 @@ class GATBase(nn.Module):
         x = _fused_heads(x, graph, [head.W for head in heads], [h[0] for h in halves], [h[1] for h in halves],
                          heads[0].alpha, self._mode, 1 if heads[0].concat else 0, p_att, self.training)
         x = F.dropout(x, self.dropout, training=self.training)
-        return F.elu(self.out_att(x, graph))
+        # `F.elu(self.out_att(x, adj))` (GAT.py:18): the ELU rides in the output layer's kernel epilogue
+        oa = self.out_att
+        a_src, a_dst = oa._halves()
+        p_out = oa.dropout.p if isinstance(oa.dropout, nn.Dropout) else oa.dropout
+        return _fused_heads(x, graph, [oa.W], [a_src], [a_dst], oa.alpha, self._mode, 1, p_out, self.training)
 
 
 class GAT(GATBase):

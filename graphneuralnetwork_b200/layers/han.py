@@ -55,7 +55,13 @@ class GATConv(nn.Module):
         if double_elu:
             return y
         y = F.dropout(y, self.dropout, training=self.training)
-        y = F.elu(y if self.num_class is None else self.out_att(y, graph))
+        if self.num_class is None:
+            y = F.elu(y)
+        else:  # F.elu(self.out_att(y, adj)) (NodeAttention.py:61): the ELU rides in the output head's epilogue
+            oa = self.out_att
+            a_src, a_dst = oa._halves()
+            y = _fused_heads(y, graph, [oa.W], [a_src], [a_dst], oa.alpha, _lib.GAT_SOFTMAX, 1, oa.dropout,
+                             self.training)
         if out is not None:
             out.copy_(y)
             return out

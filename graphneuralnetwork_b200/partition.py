@@ -44,8 +44,19 @@ import torch.distributed as dist
 
 from . import _lib
 
-NVLINK_BPS = 650e9   # byte model of the overlap: achieved NVLink rate per direction while the SpMM runs
-HBM_BPS = 5.6e12     # gather-model bytes per second of the SpMM alone (r01: 0.87-0.95 of the measured peak)
+# Byte model of the overlap (choose_two_pass_chunks / the automatic schedule), calibrated on r02 measurements
+# (papers100M-shaped, F=128 fp32): the all-to-all rate the movers sustain per direction WHILE the SpMM runs
+# (2 GPUs 640 GB/s, 8 GPUs 480 GB/s; the exchange alone reaches 575-610), the gather-model rate of the SpMM alone
+# (0.87-1.0 of the measured HBM peak), and the cost of one more wave (a flag wait + a short consumer launch).
+NVLINK_BPS_BY_WORLD = {2: 640e9, 3: 600e9, 4: 560e9}
+NVLINK_BPS_LARGE = 480e9
+HBM_BPS = 5.6e12
+WAVE_OVERHEAD_S = 0.3e-3
+AUTO_MAX_WAVES = 8
+
+
+def nvlink_bps(world: int) -> float:
+    return NVLINK_BPS_BY_WORLD.get(int(world), NVLINK_BPS_LARGE)
 
 
 def balanced_bounds(rowptr_or_deg_prefix: torch.Tensor, world: int) -> List[int]:
@@ -158,17 +169,18 @@ class HaloPlan:
 
 
 def choose_two_pass_chunks(K: int, F: int, elem: int, nnz_p1_base: int, rows_interior: int, m_rows, m_nnz_loc, m_nnz_rem,
-                           wave_bytes) -> (int, Dict[str, float]):
+                           wave_bytes, world: int = 2) -> (int, Dict[str, float]):
     """Byte model of the overlap: for every c0 in [0, K] simulate the main stream (P1, then the wave
     consumers, each gated by its wave's arrival; the SpMM runs slower while the exchange shares the HBM)
     and return the c0 with the earliest finish.  All quantities are this rank's own."""
     row_b, edge_b = F * elem, 8 + F * elem
     arrival, t = [], 0.0
+    link = nvlink_bps(world)
     for w in range(K):
-        t += wave_bytes[w] / NVLINK_BPS
+        t += wave_bytes[w] / link
         arrival.append(t)
     t_x = arrival[-1] if K else 0.0
-    slow = max(HBM_BPS - 2 * NVLINK_BPS, 0.3 * HBM_BPS)  # exchange reads X here and lands the peers' rows here
+    slow = max(HBM_BPS - 2 * link, 0.3 * HBM_BPS)  # exchange reads X here and lands the peers' rows here
 
     def run(t0, nbytes):
         if t0 >= t_x:
@@ -185,7 +197,7 @@ def choose_two_pass_chunks(K: int, F: int, elem: int, nnz_p1_base: int, rows_int
         p1_nnz = nnz_p1_base + sum(m_nnz_loc[:c0])
         t = run(0.0, p1_nnz * edge_b + p1_rows * row_b)
         for w in range(K):
-            t = max(t, arrival[w])
+            t = max(t, arrival[w]) + WAVE_OVERHEAD_S
             if w < c0:
                 t = run(t, m_nnz_rem[w] * edge_b + m_rows[w] * 2 * row_b)
             else:
@@ -197,14 +209,82 @@ def choose_two_pass_chunks(K: int, F: int, elem: int, nnz_p1_base: int, rows_int
     return best[0], report
 
 
+def _auto_schedule(rowptr, col, bounds, rank, world, group, F, elem_size):
+    """(K, c0) for all ranks: statistics at the finest wave count, coarsened for the smaller K (the chunk
+    boundaries are nested), one all_reduce of the modelled step times."""
+    dev = col.device
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n_loc = hi - lo
+    col = col.to(torch.int64)
+    KM = AUTO_MAX_WAVES
+    is_loc = (col >= lo) & (col < hi)
+    csum = torch.zeros(col.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(is_loc.to(torch.int64), 0, out=csum[1:])
+    loc_deg = csum[rowptr[1:]] - csum[rowptr[:-1]]
+    deg = rowptr[1:] - rowptr[:-1]
+    rem_deg = deg - loc_deg
+    del csum
+    total = int(rowptr[-1].item())
+    tg = torch.tensor([total * k // KM for k in range(1, KM)], dtype=torch.int64, device=dev)
+    cuts = [0] + torch.searchsorted(rowptr, tg).clamp_(0, n_loc).tolist() + [n_loc]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    mixed = rem_deg > 0
+    m_rows, m_loc, m_rem = [], [], []
+    for w in range(KM):
+        a, b = cuts[w], cuts[w + 1]
+        mw = mixed[a:b]
+        m_rows.append(int(mw.sum().item()))
+        m_loc.append(int(loc_deg[a:b][mw].sum().item()))
+        m_rem.append(int(rem_deg[a:b].sum().item()))
+    rows_interior = n_loc - sum(m_rows)
+    nnz_interior = int(loc_deg.sum().item()) - sum(m_loc)
+    # halo rows per finest wave (first chunk that needs them)
+    col_rem = col[~is_loc]
+    del is_loc
+    uniq, inverse = torch.unique(col_rem, sorted=True, return_inverse=True)
+    wave_rows = [0] * KM
+    if uniq.numel():
+        row_of_rem = torch.repeat_interleave(torch.arange(n_loc, dtype=torch.int64, device=dev), rem_deg,
+                                             output_size=int(col_rem.numel()))
+        chunk_of_rem = torch.bucketize(row_of_rem, torch.tensor(cuts[1:-1], dtype=torch.int64, device=dev), right=True)
+        first = torch.full((uniq.numel(),), KM, dtype=torch.int64, device=dev)
+        first.scatter_reduce_(0, inverse, chunk_of_rem, reduce="amin", include_self=True)
+        wave_rows = torch.bincount(first, minlength=KM).tolist()[:KM]
+        del row_of_rem, chunk_of_rem, first
+    del uniq, inverse, col_rem
+    ks = [k for k in (1, 2, 4, 8) if k <= KM]
+    times = torch.full((len(ks), KM + 1), 1e9, dtype=torch.float64, device=dev)
+    for ki, K in enumerate(ks):
+        gsz = KM // K
+        merge = lambda v: [sum(v[w * gsz:(w + 1) * gsz]) for w in range(K)]
+        _, rep_k = choose_two_pass_chunks(K, F, elem_size, nnz_interior, rows_interior, merge(m_rows), merge(m_loc),
+                                          merge(m_rem), [r * F * elem_size for r in merge(wave_rows)], world)
+        for c0 in range(K + 1):
+            times[ki, c0] = rep_k[f"c0={c0}"]
+    dist.all_reduce(times, group=group)
+    best = int(torch.argmin(times).item())
+    K, c0 = ks[best // (KM + 1)], best % (KM + 1)
+    report = {f"K={ks[i]}": [round(float(x), 2) for x in times[i, :ks[i] + 1].tolist()] for i in range(len(ks))}
+    return K, c0, report
+
+
 def build_halo_plan(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], bounds: List[int],
-                    rank: int, world: int, group=None, waves: int = 1, two_pass_chunks: Optional[int] = None,
-                    F: int = 128, elem_size: int = 4, consumers: bool = True) -> HaloPlan:
+                    rank: int, world: int, group=None, waves: Optional[int] = 1,
+                    two_pass_chunks: Optional[int] = None, F: int = 128, elem_size: int = 4,
+                    consumers: bool = True) -> HaloPlan:
     """Plan for this rank's row block (rowptr over its own rows, GLOBAL column ids).
     Collective: every rank of `group` must call it with the same `waves` (exchanges the request lists).
+    waves: number of row chunks / exchange waves K; None = AUTOMATIC: the byte model is evaluated for
+      K in {1, 2, 4, 8} and every two-pass count on every rank, the modelled times are summed over the ranks
+      and the (K, c0) with the smallest sum is used by all of them.
     two_pass_chunks: c0 in [0, waves] (None: chosen by `choose_two_pass_chunks` for feature width F)."""
     dev = col.device
-    K = max(int(waves), 1) if world > 1 else 1
+    if waves is None and world > 1:
+        waves, two_pass_chunks, auto_report = _auto_schedule(rowptr, col, bounds, rank, world, group, F, elem_size)
+    else:
+        auto_report = None
+    K = max(int(waves or 1), 1) if world > 1 else 1
     lo, hi = bounds[rank], bounds[rank + 1]
     n_loc = hi - lo
     col = col.to(torch.int64)
@@ -293,7 +373,9 @@ def build_halo_plan(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch
     wave_bytes = [max(sum(recv_wave_counts[q][w] for q in range(world)), sum(send_wave_counts[p][w] for p in range(world)))
                   * row_b for w in range(K)]
     c0_model, report = choose_two_pass_chunks(K, F, elem_size, nnz_interior, rows_interior, m_rows, m_nnz_loc,
-                                              m_nnz_rem, wave_bytes)
+                                              m_nnz_rem, wave_bytes, world)
+    if auto_report is not None:
+        report["auto_schedule_ms_sum_over_ranks"] = auto_report
     c0 = c0_model if two_pass_chunks is None else max(0, min(int(two_pass_chunks), K))
     plan.two_pass_chunks = c0
     plan.model = dict(report, chosen=c0, model_choice=c0_model, rows_interior=rows_interior,
@@ -414,19 +496,24 @@ class PartitionedSpmm:
     (gnn_halo_opts / gnn_spmm_opts): nothing is routed through process-global knobs.
       transport      "p2p" | "ce" | "nccl"
       mover          "tma" | "vector" | "auto"  (p2p only)
-      mover_ctas     CTAs of the push kernel (0 = one per SM)
-      mover_warps    warps per push CTA (0 = default: TMA 1, vector 8)
+      mover_ctas     CTAs of the push kernel (0 = one per SM; -1 = measured default: 4-warp movers on 32 SMs when
+                     the step is single-pass / exchange-dominated, on 48 SMs otherwise — r02 sweeps at 2 and 8 GPUs:
+                     more mover CTAs take SpMM occupancy without raising the all-to-all rate, fewer starve it)
+      mover_warps    warps per push CTA (0 = default: TMA 1, vector 8; -1 = measured default 4)
       dedicated_sms  > 0: vector mover on that many SMs of its own (each CTA claims 200 KB of shared memory
                      and the concurrent P1 asks for 28 KB so that the block scheduler keeps them apart)
       timeout_ms     bound of every flag wait (a lost peer must not hang the GPU)
+      interleave     fused-signal mover: > 0 cuts every peer segment of a wave into pieces of that many ring stages
+                     and deals the pieces round-robin over the peers, so a sender feeds all its peers at once
+                     (uniform ingress load on every receiver); 0 = one peer after the other, rotated by rank
       fused_signal   p2p + TMA mover: all waves of a step in ONE launch, the arrival flags raised from inside
                      the kernel by the last warp that finishes a wave (gnn_halo_push_waves); False = one
                      mover launch + one signal launch per wave
     """
 
     def __init__(self, plan: HaloPlan, F: int, device, group=None, transport: str = "p2p",
-                 dtype: torch.dtype = torch.float32, mover: str = "auto", mover_ctas: int = 0, mover_warps: int = 0,
-                 dedicated_sms: int = 0, timeout_ms: int = 20000, fused_signal: bool = True):
+                 dtype: torch.dtype = torch.float32, mover: str = "auto", mover_ctas: int = -1, mover_warps: int = -1,
+                 dedicated_sms: int = 0, timeout_ms: int = 20000, fused_signal: bool = True, interleave: int = 0):
         from .graph import CSRGraph
         if dtype not in _TORCH_TYPESTR:
             raise _lib.GnnError(f"PartitionedSpmm: unsupported dtype {dtype}")
@@ -436,8 +523,13 @@ class PartitionedSpmm:
         if self.transport not in ("p2p", "ce", "nccl", "none"):
             raise ValueError(f"unknown transport {transport!r}")
         self.mover = {"auto": 0, "vector": 1, "tma": 2}[mover]
+        if int(mover_ctas) < 0:
+            mover_ctas = 32 if plan.two_pass_chunks == 0 else 48
+        if int(mover_warps) < 0:
+            mover_warps = 4
         self.mover_ctas, self.mover_warps, self.dedicated = int(mover_ctas), int(mover_warps), int(dedicated_sms)
         self.timeout_ms = int(timeout_ms)
+        self.interleave = int(interleave)
         n_loc, n_halo = plan.n_local, max(plan.n_halo, 1)
         per16 = 16 // self.elem
         # halo rows are contiguous (ld == F) when a row is a 16-byte multiple: one bulk store per ring stage
@@ -482,14 +574,26 @@ class PartitionedSpmm:
         plan, W = self.plan, self.plan.world
         row_bytes = self.ld * self.elem
         rows, chunk = [], 0
+        piece = self.interleave * R  # rows per interleaved piece (0: whole segments, one peer after the other)
         for w in range(plan.waves):
+            segs = []
             for s_i in range(1, W):
                 q = (plan.rank + s_i) % W
                 n = plan.send_wave_counts[q][w]
-                if n == 0:
-                    continue
-                b = self._wave_cum_send[q][w]
-                rows.append([self._send_off[q] + b, n, self._halo_buf.ptrs[q] + (plan.dst_off[q] + b) * row_bytes, chunk, w])
+                if n:
+                    b = self._wave_cum_send[q][w]
+                    segs.append((self._send_off[q] + b, n, self._halo_buf.ptrs[q] + (plan.dst_off[q] + b) * row_bytes))
+            if piece > 0:
+                pieces, k = [], 0
+                while any(k * piece < n for _, n, _ in segs):
+                    for src, n, dst in segs:  # round-robin over the peers, rotated order kept within a round
+                        if k * piece < n:
+                            m = min(piece, n - k * piece)
+                            pieces.append((src + k * piece, m, dst + k * piece * row_bytes))
+                    k += 1
+                segs = pieces
+            for src, n, dst in segs:
+                rows.append([src, n, dst, chunk, w])
                 chunk += (n + R - 1) // R
         table = torch.tensor(rows if rows else [[0, 0, 0, 0, 0]], dtype=torch.int64, device=self.dev)
         done = torch.zeros(max(plan.waves, 1), dtype=torch.int32, device=self.dev)

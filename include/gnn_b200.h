@@ -288,8 +288,44 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
                           float* row_max, float* row_sum,
                           const int64_t* long_rows /*nullable*/, int64_t n_long, int64_t long_threshold,
                           gnn_stream_t stream);
-/* Backward.  d_out is the gradient w.r.t. the PRE-activation aggregate (the wrapper applies the ELU
- * derivative); out_pre is that aggregate.  Produces
+/* Seeded attention dropout (GAT/models/layers.py:31, HAN/models/NodeAttention.py:31): instead of a materialised
+ * [nnz,H] mask the kernels recompute, from (seed, forward edge slot, head), whether an attention weight is kept
+ * (probability 1-p, kept weights scaled by 1/(1-p)) — identically in the forward and in both backward passes.
+ * seed_dev (nullable) is a device int64 mixed into the seed at run time, so a captured CUDA graph draws a fresh
+ * mask on every replay.  Semantically (not bit-) equal to F.dropout on the dense attention matrix; the explicit
+ * `edge_keep` mask remains for parity tests.  struct_size = sizeof(gnn_gat_dropout). */
+typedef struct gnn_gat_dropout {
+  int32_t struct_size;
+  float p;
+  uint64_t seed;
+  const int64_t* seed_dev;
+} gnn_gat_dropout;
+
+/* Training form of the forward: writes the PRE-activation aggregate to out_pre (saved for the backward) and, when
+ * apply_elu > 0, the activated aggregate to out_act in the same launch — the ELU after every concatenated head
+ * (layers.py:35) and HAN's second ELU (NodeAttention.py:62) are never separate launches, in training either.
+ * dropout (nullable) selects the seeded dropout above; edge_keep (nullable) an explicit mask; not both. */
+int gnn_gat_fused_fwd_train_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw,
+                                const float* s, const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp,
+                                float alpha, int mode, int apply_elu, const float* col_mean,
+                                const float* edge_keep, const gnn_gat_dropout* dropout,
+                                float* out_pre, float* out_act /*nullable when apply_elu == 0*/, int64_t ldo,
+                                float* row_max, float* row_sum,
+                                const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
+                                gnn_stream_t stream);
+int gnn_gat_fused_fwd_train_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw,
+                                 const float* s, const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp,
+                                 float alpha, int mode, int apply_elu, const float* col_mean,
+                                 const float* edge_keep, const gnn_gat_dropout* dropout,
+                                 void* out_pre, void* out_act, int64_t ldo,
+                                 float* row_max, float* row_sum,
+                                 const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
+                                 gnn_stream_t stream);
+
+/* Backward.  out_pre is the pre-activation aggregate of the forward.  d_out is the gradient w.r.t. the
+ * pre-activation aggregate when apply_elu == 0; with apply_elu > 0 it is the gradient w.r.t. the ACTIVATED
+ * output of gnn_gat_fused_fwd_train_* and the ELU derivative chain is applied inside (d_pre: [n, ldo] scratch of
+ * the feature type that receives the pre-activation gradient the two passes gather).  Produces
  *   d_s [n,H]                       (pass 1, row-parallel over the CSR),
  *   d_Wh [n,H*Fp] and d_t [n,H]     (pass 2, row-parallel over the transposed CSR rowptr_t/col_t).
  * Both passes have the forward kernel's shape, because the edge gradient
@@ -299,7 +335,7 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
  * w2 = w1*slope).  This is the edge-gradient SDDMM (GAT/models/layers.py:59-61) and the transpose SpMM
  * (layers.py:63) without the dense N x N intermediate, without per-edge dot products, without a per-edge
  * stash between the passes and without atomics: ordered sums only.
- * perm_t (transposed slot -> forward edge slot) is read only when edge_keep is given.
+ * perm_t (transposed slot -> forward edge slot) is read only when a dropout (edge_keep or seeded) is given.
  * row_scratch: [n,4,H] fp32 scratch (per-row s, max, 1/sum, D packed for the transposed pass). */
 int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
                           const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t /*nullable*/,
@@ -312,6 +348,8 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
                           int64_t nnz,
                           const int64_t* long_rows, int64_t n_long /*forward CSR*/,
                           const int64_t* long_rows_t, int64_t n_long_t /*transposed CSR*/, int64_t long_threshold,
+                          int apply_elu, float* d_pre /*nullable when apply_elu == 0*/,
+                          const gnn_gat_dropout* dropout /*nullable*/,
                           gnn_stream_t stream);
 /* bf16-feature variants (north_star: "bf16-feature variants within 1e-2"): Wh, out, out_pre, d_out and
  * d_Wh are bf16; the scores s/t, the softmax statistics and every accumulation stay fp32.
@@ -334,6 +372,7 @@ int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col,
                            int64_t nnz,
                            const int64_t* long_rows, int64_t n_long,
                            const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
+                           int apply_elu, void* d_pre, const gnn_gat_dropout* dropout,
                            gnn_stream_t stream);
 
 /* ---- synthetic graphs for the benchmark shapes ---------------- */

@@ -5,8 +5,30 @@ import torch
 import torch.nn.functional as F
 
 
-def dense_head(h, W, a, adj, alpha, concat=True, materialise_pairs=False):
-    """GAT/models/layers.py:22-37 (== HAN/models/NodeAttention.py:22-38), eval mode.
+class replay_dropout:
+    """Deterministic stand-in for F.dropout (same signature): call k draws its keep mask from torch's CPU generator
+    seeded with base + k.  tests/golden/make_golden.py patches it into the reference while a train-mode fixture
+    is made; the oracle and the GPU tests replay the same masks (`mask(k, shape, p)`)."""
+
+    def __init__(self, base_seed):
+        self.base, self.k = int(base_seed), 0
+
+    @staticmethod
+    def mask(seed, shape, p):
+        g = torch.Generator().manual_seed(int(seed))
+        return torch.bernoulli(torch.full(tuple(shape), 1.0 - p), generator=g) / (1.0 - p)
+
+    def __call__(self, x, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return x
+        keep = self.mask(self.base + self.k, x.shape, p).to(x.device)
+        self.k += 1
+        return x * keep
+
+
+def dense_head(h, W, a, adj, alpha, concat=True, materialise_pairs=False, dropout=None, p=0.0):
+    """GAT/models/layers.py:22-37 (== HAN/models/NodeAttention.py:22-38); eval mode unless `dropout`
+    (an F.dropout-like callable, e.g. replay_dropout) is given: then layers.py:31 is applied to the attention.
     materialise_pairs=True follows the reference literally (the [N,N,2F'] tensor, :25-26);
     False uses the exact decomposition a·[Wh_i||Wh_j] = a[:F']·Wh_i + a[F':]·Wh_j so larger N
     fit in memory — same masked softmax and dense product after that."""
@@ -20,6 +42,8 @@ def dense_head(h, W, a, adj, alpha, concat=True, materialise_pairs=False):
     zero_vec = -9e15 * torch.ones_like(e)
     attention = torch.where(adj > 0, e, zero_vec)
     attention = F.softmax(attention, dim=1)
+    if dropout is not None:
+        attention = dropout(attention, p, True)
     h_prime = torch.matmul(attention, Wh)
     return F.elu(h_prime) if concat else h_prime
 
@@ -38,13 +62,20 @@ def sparse_head(x, W, a, adj, alpha, concat=True):
     return F.elu(h_prime) if concat else h_prime
 
 
-def gat_model(x, params, adj, alpha, nheads, sparse=False):
-    """GAT/models/GAT.py:14-18 eval mode: cat of heads -> elu(out_att)."""
+def gat_model(x, params, adj, alpha, nheads, sparse=False, dropout=None, p=0.0):
+    """GAT/models/GAT.py:14-18: cat of heads -> elu(out_att).  Eval mode unless `dropout` is given (dense heads
+    only): then the four dropout sites of the train-mode forward (GAT.py:15,17 and layers.py:31) are applied in
+    the reference's call order."""
     head = sparse_head if sparse else dense_head
-    xs = [head(x, params[f"attentions.AttentionHead{k}.W"], params[f"attentions.AttentionHead{k}.a"], adj, alpha, True)
+    kw = {} if (dropout is None or sparse) else {"dropout": dropout, "p": p}
+    if dropout is not None:
+        x = dropout(x, p, True)
+    xs = [head(x, params[f"attentions.AttentionHead{k}.W"], params[f"attentions.AttentionHead{k}.a"], adj, alpha, True, **kw)
           for k in range(nheads)]
     x = torch.cat(xs, dim=1)
-    return F.elu(head(x, params["out_att.W"], params["out_att.a"], adj, alpha, False))
+    if dropout is not None:
+        x = dropout(x, p, True)
+    return F.elu(head(x, params["out_att.W"], params["out_att.a"], adj, alpha, False, **kw))
 
 
 def gatconv(x, params, prefix, adj, alpha, nheads, num_class=None):

@@ -233,6 +233,51 @@ def make_special_spmm():
          out=out.detach().numpy(), grad_values=values.grad.numpy(), grad_b=b.grad.numpy(), shape=np.array([n, m]))
 
 
+def make_gat_cora_train():
+    """Cora-sized GAT in TRAIN mode, dropout 0.6 (GAT/run.py:9) on features and on the attention matrices
+    (layers.py:31), forward + every gradient, with the dropout masks replayed from seeds on both sides."""
+    gat_mod, _ = R.gat_models()
+    n = S.CORA["n"]
+    edges, adj = _gat_adj(n, S.CORA["undirected_pairs"], seed=0)
+    X = S.row_normalised_features(n, S.CORA["feats"], seed=1)
+    labels = np.random.default_rng(2).integers(0, S.CORA["classes"], size=n)
+    torch.manual_seed(2)
+    model = gat_mod.GAT(S.CORA["feats"], 8, S.CORA["classes"], 0.6, 0.2, 8)
+    model.train()
+    import torch.nn.functional as Fnn
+    from oracle.gat import replay_dropout
+    orig, Fnn.dropout = Fnn.dropout, replay_dropout(1000)
+    try:
+        out = model(torch.from_numpy(X), torch.from_numpy(adj))
+        calls = Fnn.dropout.k
+    finally:
+        Fnn.dropout = orig
+    loss = torch.nn.functional.cross_entropy(out[:140], torch.from_numpy(labels)[:140])
+    loss.backward()
+    save("gat_cora_train.npz", edges=edges, adj_sha=np.array(sha(adj)), x_seed=np.int64(1), x_sha=np.array(sha(X)),
+         labels=labels.astype(np.int64), dropout_base_seed=np.int64(1000), dropout_calls=np.int64(calls),
+         out=out.detach().numpy(), loss=np.float64(loss.item()), **params_np(model), **grads_np(model))
+
+
+def make_han_acm():
+    """ACM-sized HAN (N=3025, 1870 features, 3 metapaths incl. a 24 %-dense one, 8 heads x 8), forward + every
+    gradient, dropout 0: the CTA-per-row schedule of the attention kernels at the size BASELINE configs[3] names.
+    Inputs are regenerated from seeds on the test side (checksums stored)."""
+    ref = R.han()
+    n, fin, M = S.ACM["n"], S.ACM["feats"], 3
+    gs = [S.symmetric_mask(n, t, seed=11 + i) for i, t in enumerate(S.ACM["metapath_nnz"])]
+    X = np.random.default_rng(14).standard_normal((n, fin), dtype=np.float32)
+    labels = np.random.default_rng(15).integers(0, S.ACM["classes"], size=n)
+    torch.manual_seed(5)
+    model = ref["HAN"].HANModel(M, fin, 8, S.ACM["classes"], [8], 0.0)
+    model.train()
+    out = model([torch.from_numpy(g) for g in gs], torch.from_numpy(X))
+    loss = torch.nn.functional.cross_entropy(out, torch.from_numpy(labels))
+    loss.backward()
+    save("han_acm.npz", mask_sha=np.array([sha(g) for g in gs]), x_sha=np.array(sha(X)), labels=labels.astype(np.int64),
+         out=out.detach().numpy(), loss=np.float64(loss.item()), **params_np(model), **grads_np(model))
+
+
 def make_gtn():
     """GTN_Model forward + backward (GTN/models/GTN.py) on a small 4-edge-type graph: the learned adjacency the final
     gcn_conv aggregates over is the output of two dense metapath compositions."""
@@ -267,7 +312,7 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     makers = {"gcn": make_gcn, "gat_small": make_gat_small, "gat_cora": make_gat_cora, "sage": make_sage,
               "sage_v2": make_sage_v2, "han": make_han, "gatne": make_gatne, "special_spmm": make_special_spmm,
-              "gtn": make_gtn}
+              "gtn": make_gtn, "gat_cora_train": make_gat_cora_train, "han_acm": make_han_acm}
     # `python make_golden.py [name ...]`: only the named fixtures (the committed ones are not rewritten otherwise)
     for name in (sys.argv[1:] or list(makers)):
         makers[name]()

@@ -843,6 +843,123 @@ def test_han_small_vs_reference_golden(lib):
         assert rel_err(model(gs, cuda(g["X"])).cpu().numpy(), g["out"]) < TOL32
 
 
+def test_han_acm_size_vs_reference_golden(lib):
+    """BASELINE configs[3] at its own size: N=3025, 1870 features, 3 metapaths (29 k / 2.2 M / 300 k non-zeros),
+    8 heads x 8 — the CTA-per-row attention schedule on the 24 %-dense metapath, forward + every gradient against
+    the fixture of the unmodified reference (only N=160 was pinned)."""
+    g = load_golden("han_acm.npz")
+    n = S.ACM["n"]
+    masks = [S.symmetric_mask(n, t, seed=11 + i) for i, t in enumerate(S.ACM["metapath_nnz"])]
+    X = np.random.default_rng(14).standard_normal((n, S.ACM["feats"]), dtype=np.float32)
+    model = load_params(layers.HANModel(3, S.ACM["feats"], 8, S.ACM["classes"], [8], 0.0), g)
+    model.train()
+    out = model([cuda(m) for m in masks], cuda(X))
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < TOL32
+    loss = torch.nn.functional.cross_entropy(out, cuda(g["labels"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    check_grads(model, g, tol=2e-5)
+
+
+def test_gat_cora_train_mode_vs_reference_golden(lib, monkeypatch):
+    """Cora-sized GAT in TRAIN mode with dropout 0.6 (GAT/run.py:9), forward + every gradient: the reference's
+    dropout masks (features: GAT.py:15,17; attention matrices: layers.py:31) are replayed from the fixture's seeds —
+    the dense [N,N] attention masks are read at the edge positions into the kernel's per-edge keep factors."""
+    from graphneuralnetwork_b200.layers import gat as lgat
+    g = load_golden("gat_cora_train.npz")
+    n, p, H = S.CORA["n"], 0.6, 8
+    row, col, val = ogcn.build_adjacency(g["edges"], n)
+    dense = np.zeros((n, n), np.float32)
+    dense[row, col] = val
+    X = S.row_normalised_features(n, S.CORA["feats"], seed=int(g["x_seed"]))
+    base = int(g["dropout_base_seed"])
+    # reference call order: 0 = features, 1..8 = attention of head k, 9 = hidden features, 10 = out_att attention
+    feature_calls = iter([0, 9])
+    monkeypatch.setattr(lgat.F, "dropout", lambda x, pp=0.5, training=True, inplace=False:
+                        x * ogat.replay_dropout.mask(base + next(feature_calls), x.shape, pp).to(x.device))
+    att_calls = iter([list(range(1, 9)), [10]])
+
+    def keep_from_dense_masks(graph, heads, pp, generator=None):
+        ks = next(att_calls)
+        assert len(ks) == heads
+        rows = graph.edge_rows().long().cpu()
+        cols = graph.col.long().cpu()
+        keep = torch.stack([ogat.replay_dropout.mask(base + k, (n, n), pp)[rows, cols] for k in ks], dim=1)
+        return keep.contiguous().to(DEV)
+
+    monkeypatch.setattr(lgat, "attention_keep_mask", keep_from_dense_masks)
+    monkeypatch.setattr(lgat, "EXPLICIT_DROPOUT_MASK", True)
+    model = load_params(layers.GAT(S.CORA["feats"], 8, S.CORA["classes"], p, 0.2, H), g)
+    model.train()
+    out = model(cuda(X), cuda(dense))
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < TOL32
+    loss = torch.nn.functional.cross_entropy(out[:140], cuda(g["labels"])[:140])
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    check_grads(model, g, tol=2e-5)
+
+
+@pytest.mark.parametrize("H,Fp,deg,elu", [(8, 8, 30, 1), (8, 8, 300, 2), (1, 7, 12, 1), (3, 5, 20, 0), (8, 64, 9, 1)])
+def test_gat_seeded_dropout_and_fused_train_epilogue(lib, H, Fp, deg, elu):
+    """f2: (1) the ELU(s) run in the kernel epilogue in TRAINING too (the backward applies their derivative chain
+    inside its first kernel); (2) attention dropout from a seeded in-kernel stream — bit-identical, forward and all
+    gradients, to the same call with the stream's mask materialised (attention_keep_mask_from_seed) and to float64
+    autograd with that mask; the stream keeps ~(1-p) of the weights and differs from call to call."""
+    n, p = 400, 0.6
+    rowptr, col, _ = random_csr(n, n, deg, seed=H + Fp + deg, empty_every=n + 1)
+    rng = np.random.default_rng(elu + H)
+    Wh = rng.standard_normal((n, H, Fp)).astype(np.float32)
+    s = rng.standard_normal((n, H)).astype(np.float32)
+    t = rng.standard_normal((n, H)).astype(np.float32)
+    G = rng.standard_normal((n, H * Fp)).astype(np.float32)
+    csr = CSRGraph(cuda(rowptr), cuda(col), None, n, n)
+    drop = Fn.AttentionDropout(p, seed=1234567, seed_dev=torch.tensor([7], dtype=torch.int64, device=DEV))
+    keep = Fn.attention_keep_mask_from_seed(csr, H, drop)
+    frac = float((keep > 0).float().mean())
+    assert abs(frac - (1 - p)) < 0.02 and float(keep.max()) == pytest.approx(1 / (1 - p), rel=1e-6)
+
+    def run(**kw):
+        Wh_d = cuda(Wh).view(n, -1).requires_grad_(True)
+        s_d, t_d = cuda(s).requires_grad_(True), cuda(t).requires_grad_(True)
+        out = Fn.gat_aggregate(csr, Wh_d, s_d, t_d, H, Fp, 0.2, elu=elu, **kw)
+        out.backward(cuda(G))
+        return out.detach(), Wh_d.grad, s_d.grad, t_d.grad
+
+    seeded = run(dropout=drop)
+    explicit = run(keep=keep)
+    for a, b in zip(seeded, explicit):
+        assert torch.equal(a, b)
+    # float64 autograd with the same mask and the ELUs outside
+    Wh_t = torch.tensor(Wh, dtype=torch.float64, requires_grad=True)
+    s_t = torch.tensor(s, dtype=torch.float64, requires_grad=True)
+    t_t = torch.tensor(t, dtype=torch.float64, requires_grad=True)
+    rows = torch.repeat_interleave(torch.arange(n), torch.from_numpy(np.diff(rowptr)))
+    cols = torch.from_numpy(col.astype(np.int64))
+    e = torch.nn.functional.leaky_relu(s_t[rows] + t_t[cols], 0.2)
+    m = torch.full((n, H), -float("inf"), dtype=torch.float64).scatter_reduce(0, rows[:, None].expand(-1, H), e.detach(), "amax")
+    w = torch.exp(e - m[rows])
+    att = w / torch.zeros((n, H), dtype=torch.float64).index_add(0, rows, w)[rows] * keep.cpu().double()
+    ref = torch.zeros((n, H, Fp), dtype=torch.float64).index_add(0, rows, att[:, :, None] * Wh_t[cols])
+    empty = torch.from_numpy(np.diff(rowptr) == 0)
+    ref = torch.where(empty[:, None, None], Wh_t.mean(dim=0, keepdim=True).expand(n, H, Fp), ref).reshape(n, H * Fp)
+    for _ in range(elu):
+        ref = torch.nn.functional.elu(ref)
+    (ref * torch.from_numpy(G).double()).sum().backward()
+    assert rel_err(seeded[0].cpu().numpy(), ref.detach().numpy()) < TOL32
+    assert rel_err(seeded[1].cpu().numpy(), Wh_t.grad.reshape(n, -1).numpy()) < 2e-5
+    assert rel_err(seeded[2].cpu().numpy(), s_t.grad.numpy()) < 2e-5
+    assert rel_err(seeded[3].cpu().numpy(), t_t.grad.numpy()) < 2e-5
+    # a new stream per call at the layer level, reproducible under torch.manual_seed
+    torch.manual_seed(5)
+    d1 = Fn.next_attention_dropout(p, DEV)
+    d2 = Fn.next_attention_dropout(p, DEV)
+    k1, k2 = Fn.attention_keep_mask_from_seed(csr, H, d1), Fn.attention_keep_mask_from_seed(csr, H, d2)
+    assert not torch.equal(k1, k2)
+    torch.manual_seed(5)
+    d3 = Fn.next_attention_dropout(p, DEV)
+    assert d3.seed == d1.seed
+
+
 def test_gat_deterministic(lib):
     rowptr, col, _ = random_csr(2000, 2000, 50, seed=7)
     csr = CSRGraph(cuda(rowptr), cuda(col), None, 2000, 2000)
@@ -1070,6 +1187,26 @@ def test_captured_train_step_matches_eager(lib, which):
     assert np.allclose(cap, eager[warm:], rtol=2e-4, atol=1e-6), (cap, eager)
     for (k, a), b in zip(model.state_dict().items(), twin.state_dict().values()):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-3, k
+
+
+def test_out_of_range_ids_are_contained(lib):
+    """index validation was one-sided.  A sampled id >= n_table_rows contributes nothing (like the -1
+    padding ids) on both gather paths instead of reading out of bounds; COO ids outside the adjacency raise."""
+    table = torch.randn(100, 602, device=DEV)
+    padded = Fn.pad_table(table)
+    idx = torch.randint(0, 100, (64 * 5,), device=DEV)
+    ref_idx = idx.clone()
+    bad = torch.tensor([3, 77, 200, 319], device=DEV)
+    idx[bad] = torch.tensor([100, 2 ** 31 - 7, 100000, 101], device=DEV)
+    ref_idx[bad] = -1
+    for tab in (padded, table):  # TMA ring / vector-load kernel
+        got = Fn.gather_reduce_raw(tab, idx, 64, 5, "sum")
+        want = Fn.gather_reduce_raw(tab, ref_idx, 64, 5, "sum")
+        assert torch.equal(got, want)
+    with pytest.raises(IndexError):
+        CSRGraph.from_coo(torch.tensor([0, 5], device=DEV), torch.tensor([1, 9], device=DEV), None, 5, 10)
+    with pytest.raises(IndexError):
+        CSRGraph.from_coo(torch.tensor([0, 4], device=DEV), torch.tensor([1, -2], device=DEV), None, 5, 10)
 
 
 def test_cpu_tensors_raise(lib):

@@ -157,3 +157,34 @@ def test_gtn_oracle_vs_reference_golden():
     assert rel_err(ogtn.gcn_conv(torch.from_numpy(g["X"]), H, P["weight"]).numpy(), g["conv_out"]) < 1e-6
     y = ogtn.gtn_forward(torch.from_numpy(g["A"]), torch.from_numpy(g["X"]), torch.from_numpy(g["target"]), P, 2, 2)
     assert rel_err(y.numpy(), g["y"]) < 1e-6
+
+
+def test_gat_cora_train_mode_with_replayed_dropout():
+    """Cora-sized GAT in train mode (dropout 0.6 on features and attention, GAT/run.py:9): the oracle with the
+    fixture's dropout masks replayed from their seeds reproduces the reference's output and loss."""
+    import torch
+    from graphneuralnetwork_b200 import synthetic as S
+    from oracle import gat as ogat, gcn as ogcn
+    g = load_golden("gat_cora_train.npz")
+    n = S.CORA["n"]
+    row, col, val = ogcn.build_adjacency(g["edges"], n)
+    adj = np.zeros((n, n), np.float32)
+    adj[row, col] = val
+    X = S.row_normalised_features(n, S.CORA["feats"], seed=int(g["x_seed"]))
+    drop = ogat.replay_dropout(int(g["dropout_base_seed"]))
+    out = ogat.gat_model(torch.from_numpy(X), _params(g), torch.from_numpy(adj), 0.2, 8, dropout=drop, p=0.6)
+    assert drop.k == int(g["dropout_calls"]) == 11
+    assert rel_err(out.numpy(), g["out"]) < 1e-5
+
+
+def test_han_acm_size():
+    """ACM-sized HAN (N=3025, 24 %-dense metapath): the oracle against the reference's forward."""
+    import torch
+    from graphneuralnetwork_b200 import synthetic as S
+    from oracle import gat as ogat
+    g = load_golden("han_acm.npz")
+    n = S.ACM["n"]
+    gs = [torch.from_numpy(S.symmetric_mask(n, t, seed=11 + i)) for i, t in enumerate(S.ACM["metapath_nnz"])]
+    X = torch.from_numpy(np.random.default_rng(14).standard_normal((n, S.ACM["feats"]), dtype=np.float32))
+    out = ogat.han_model(gs, X, _params(g), [8])
+    assert rel_err(out.numpy(), g["out"]) < 1e-5

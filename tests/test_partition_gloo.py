@@ -50,7 +50,7 @@ def _worker(rank, world, port, n, seed, waves, c0, out_q):
         plan = build_halo_plan(rp, c, v, bounds, rank, world, waves=waves, two_pass_chunks=c0, F=X.shape[1])
         K = plan.waves
         # invariants of the plan
-        assert plan.n_local == hi - lo and K == waves
+        assert plan.n_local == hi - lo and (K == waves if waves is not None else K in (1, 2, 4, 8))
         h = plan.halo_ids.numpy()
         assert len(np.unique(h)) == len(h)                  # de-duplicated
         assert not np.any((h >= lo) & (h < hi))             # never asks for its own rows
@@ -134,12 +134,13 @@ def _worker(rank, world, port, n, seed, waves, c0, out_q):
         dX = A_loc.T @ dY[lo:hi]
         np.add.at(dX, plan.send_rows.numpy(), back.numpy())
         err_b = float(np.abs(dX - (A.T @ dY)[lo:hi]).max())
-        out_q.put((rank, max(err, err_b), len(h), bounds, plan.two_pass_chunks))
+        out_q.put((rank, max(err, err_b), len(h), bounds, plan.two_pass_chunks, plan.waves))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,waves,c0", [(2, 1, None), (2, 1, 0), (2, 3, None), (3, 1, 1), (3, 4, 2), (3, 3, 0)])
+@pytest.mark.parametrize("world,waves,c0", [(2, 1, None), (2, 1, 0), (2, 3, None), (3, 1, 1), (3, 4, 2), (3, 3, 0),
+                                            (2, None, None), (3, None, None)])
 def test_halo_plan_reproduces_global_spmm(world, waves, c0):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -151,10 +152,12 @@ def test_halo_plan_reproduces_global_spmm(world, waves, c0):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err, n_halo, bounds, chosen in results:
+    for rank, err, n_halo, bounds, chosen, k_used in results:
         assert err < 1e-9, (rank, err)
         assert n_halo > 0 and bounds[0] == 0 and bounds[-1] == 400
-        assert 0 <= chosen <= waves and (c0 is None or chosen == c0)
+        assert 0 <= chosen <= k_used and (c0 is None or chosen == c0)
+    if waves is None:  # the automatic schedule is a consensus: every rank runs the same (K, c0)
+        assert len({(r[5], r[4]) for r in results}) == 1
 
 
 def test_select_rows_compacts_csr():

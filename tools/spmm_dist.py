@@ -55,6 +55,7 @@ def main():
                          "launch per wave instead of the single-launch wave mover)")
     ap.add_argument("--backward", action="store_true")
     ap.add_argument("--phases", action="store_true")
+    ap.add_argument("--consumers", action="store_true", help="time every consumer launch of the step alone")
     ap.add_argument("--full-check", action="store_true", help="small graphs: compare every row with a 1-GPU SpMM")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -109,6 +110,7 @@ def main():
             mover, ctas, warps = parts[2], int(parts[3]), int(parts[4])
             dedicated = int(parts[5]) if len(parts) > 5 else 0
             fused = (parts[6] != "sep") if len(parts) > 6 else True
+            inter = int(parts[7]) if len(parts) > 7 else 0
             if transport == "nccl":
                 K, c0 = 1, (1 if c0 is None else min(c0, 1))
             key = (K, c0)
@@ -120,7 +122,7 @@ def main():
                                              two_pass_chunks=c0, F=a.F, elem_size=X.element_size())
             plan = plans[key]
             op = PartitionedSpmm(plan, a.F, dev, transport=transport, dtype=dtype, mover=mover, mover_ctas=ctas,
-                                 mover_warps=warps, dedicated_sms=dedicated, fused_signal=fused)
+                                 mover_warps=warps, dedicated_sms=dedicated, fused_signal=fused, interleave=inter)
             ms = timed(lambda: op.forward(X, out=Y), a.steps, a.warmup)
             op.check_status()
             err = reduce_max(float((Y[rows].double() - ref_rows).abs().max().item()) / max(ref_scale, 1e-30))
@@ -133,7 +135,7 @@ def main():
                 allstats = [stats]
             line = {"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F, "dtype": a.dtype,
                     "transport": transport, "waves": K, "two_pass_chunks": [int(s[3]) for s in allstats],
-                    "mover": mover, "fused_signal": bool(op._wave_table is not None) if world > 1 else None, "mover_ctas": ctas, "mover_warps": warps, "dedicated_sms": dedicated,
+                    "mover": mover, "fused_signal": bool(op._wave_table is not None) if world > 1 else None, "interleave": inter, "mover_ctas": ctas, "mover_warps": warps, "dedicated_sms": dedicated,
                     "ms": ms, "edges_per_s": nnz_total / ms * 1e3, "max_rel_err_sampled_rows": err, "ok": err < tol,
                     "p_local": a.p_local, "window": a.window,
                     "halo_gb_recv_max": max(int(s[0]) for s in allstats) * a.F * X.element_size() / 1e9,
@@ -151,6 +153,19 @@ def main():
                 line["adjoint_rel_err"] = abs(lhs - rhs) / max(norm, 1e-30)
                 line["backward_ok"] = line["adjoint_rel_err"] < (1e-6 if dtype == torch.float32 else 1e-2)
                 del dY, dX
+            if a.consumers and world > 1:
+                # each consumer launch alone (halo already in place): which pass runs below the 1-GPU SpMM rate?
+                rows_c = []
+                for name, c in [("P1", plan.p1)] + [(f"P2[{w}]", c) for w, c in enumerate(plan.p2)]:
+                    if c is None:
+                        continue
+                    ms_c = timed(lambda: op._run(c, X, op.halo, Y), 3, 1)
+                    acc = 2 if c.mode == "remote" else 1
+                    gb = (c.nnz * (8 + a.F * X.element_size()) + c.n_rows * a.F * X.element_size() * acc) / 1e9
+                    rows_c.append({"pass": name, "mode": c.mode, "rows": c.n_rows, "nnz": c.nnz, "ms": round(ms_c, 3),
+                                   "gather_model_gbs": round(gb / ms_c * 1e3, 1)})
+                line["consumers_alone"] = rows_c
+                op.forward(X, out=Y)  # leave Y complete again
             if a.phases and world > 1:
                 t_x = timed(lambda: op.exchange_only(X), 4, 1)
                 line["exchange_alone_ms"] = t_x
