@@ -304,6 +304,13 @@ def run_sage_b200(args, rank, world, dev):
     with torch.no_grad():
         eager = model.forward_sampled(table, dev_blocks[(args.warmup + args.steps - 1) % pool])
     e2e_check = float((runner.logits - eager).abs().max().item())
+    # layer 0's [self|pooled].[W_self;W_agg] product runs on the fp16 tensor cores (3 products on hi/lo-split
+    # operands): its distance from the plain fp32 product, relative to the output scale (tolerance 1e-5)
+    model.tensor_core_gemm = False
+    with torch.no_grad():
+        exact = model.forward_sampled(table, dev_blocks[(args.warmup + args.steps - 1) % pool])
+    model.tensor_core_gemm = True
+    gemm_rel_err = float(((eager - exact).abs().max() / exact.abs().max().clamp_min(1e-30)).item())
 
     if world > 1:
         t = torch.tensor([ms_total, e2e_ms, k2_ms, warm_ms_total, k2_warm_ms, wall_ms_incl_flush], device=dev,
@@ -353,7 +360,10 @@ def run_sage_b200(args, rank, world, dev):
                        "PCIe while step i computes); wall-clock over the K steps incl. the last result on the host",
                 "sync_ms_per_step": e2e_sync_ms / args.steps,
                 "sync_note": "same API, one minibatch at a time (submit + collect per step)",
-                "max_abs_diff_vs_eager": e2e_check},
+                "max_abs_diff_vs_eager": e2e_check,
+                "max_rel_err_vs_fp32_product": gemm_rel_err,
+                "gemm": "layer-0 X.W as Z_hi.W_hi + Z_lo.W_hi + Z_hi.W_lo on the fp16 tensor cores (fp32 accumulate), "
+                        "operands split to fp16 hi/lo planes (22 mantissa bits) in the gather's row flush; tolerance 1e-5"},
         "e2e_device_sampling": dev_sampling,
         # launches of OUR kernels (libgnn_b200.so's own counter) inside the two timed regions
         "gpu_launches": int(launches) + int(runner.kernel_launches_per_replay) * args.steps,

@@ -47,6 +47,13 @@ struct SageArgs {
   int32_t stages;
   int32_t nvec;                      // 16-byte vectors per row
   int64_t n_table_rows;              // ids outside [0, n_table_rows) are skipped like negative (padding) ids
+  // fp32 tables only: write every reduced value x as TWO fp16 planes, hi = fp16(x) at out[...] and
+  // lo = fp16(x - hi) lo_off[b] fp16 elements further (out / ldo then count fp16 elements).  hi + lo carries 22
+  // mantissa bits (x - hi is exact in fp32; a lo below fp16's normal range only costs < 3e-8 ABSOLUTE): the operand
+  // form of a 3-product fp16 tensor-core GEMM with fp32 accumulation that stands in for the fp32 X.W product at
+  // fp32-level accuracy.  The caller guarantees |x| < 65504 (fp16 range).
+  int32_t split[kMaxBlocks];
+  int64_t lo_off[kMaxBlocks];
 };
 
 // Two fp32 adds in one instruction (SASS FADD2, sm_100): same round-to-nearest result as two
@@ -271,7 +278,31 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
 #pragma unroll
             for (int i = 0; i < E; ++i) o[i] = (OP == GNN_REDUCE_MAX) ? acc[v][i] : acc[v][i] * scale;
             const int col0 = vi * E;
-            if (a.out_vec16[b]) {
+            if (sizeof(T) == 4 && a.split[b]) {
+              // E == 4 floats -> 4 + 4 fp16 (two 8-byte stores); columns >= F are padding and stay untouched
+              __half* hrow = reinterpret_cast<__half*>(a.out[b]) + cur.src * a.ldo[b] + col0;
+              uint32_t hw[2], lw[2];
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const __half h0 = __float2half_rn(o[2 * i]), h1 = __float2half_rn(o[2 * i + 1]);
+                const __half l0 = __float2half_rn(o[2 * i] - __half2float(h0));
+                const __half l1 = __float2half_rn(o[2 * i + 1] - __half2float(h1));
+                hw[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lw[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              }
+              if (col0 + 3 < a.F) {
+                *reinterpret_cast<uint2*>(hrow) = make_uint2(hw[0], hw[1]);
+                *reinterpret_cast<uint2*>(hrow + a.lo_off[b]) = make_uint2(lw[0], lw[1]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (col0 + i < a.F) {
+                    const __half h = __float2half_rn(o[i]);
+                    hrow[i] = h;
+                    hrow[a.lo_off[b] + i] = __float2half_rn(o[i] - __half2float(h));
+                  }
+              }
+            } else if (a.out_vec16[b]) {
               VecIO<T, E>::store(orow + col0, o);
             } else {
 #pragma unroll
@@ -344,6 +375,8 @@ struct GatherBlock {
   T* out;
   int64_t ldo;
   int32_t* argmax;
+  int32_t split = 0;     // fp32 only: out is an fp16 buffer, hi/lo planes (see SageArgs::split)
+  int64_t lo_off = 0;
 };
 
 template <typename T>
@@ -363,6 +396,9 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, int32_t
     GNN_REQUIRE(table && k.out, GNN_ERR_BAD_ARG, "null table/out");
     GNN_REQUIRE(k.idx == nullptr || k.idx_bits == 32 || k.idx_bits == 64, GNN_ERR_BAD_ARG, "idx_bits must be 32 or 64");
     GNN_REQUIRE(ld >= F && k.ldo >= F, GNN_ERR_BAD_ARG, "leading dimension smaller than F");
+    GNN_REQUIRE(!k.split || (sizeof(T) == 4 && reduce != GNN_REDUCE_MAX && k.lo_off >= F && k.ldo % 4 == 0 &&
+                             k.lo_off % 4 == 0 && aligned_to(k.out, 8)),
+                GNN_ERR_BAD_ARG, "hi/lo fp16 output needs an fp32 table, mean/sum, 8-byte aligned planes");
     GNN_REQUIRE(k.idx != nullptr || k.n_src * (int64_t)k.fanout <= n_table_rows, GNN_ERR_BAD_ARG,
                 "identity block needs n_src*fanout <= n_table_rows");
     total_src += k.n_src;
@@ -405,6 +441,8 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, int32_t
       a.ldo[nb] = k.ldo;
       a.argmax[nb] = (reduce == GNN_REDUCE_MAX) ? k.argmax : nullptr;
       a.out_vec16[nb] = aligned_to(k.out, 16) && ((k.ldo * esz) % 16 == 0) && ((int64_t)a.nvec * E <= k.ldo);
+      a.split[nb] = k.split;
+      a.lo_off[nb] = k.lo_off;
       a.src_off[nb + 1] = a.src_off[nb] + k.n_src;
       ++nb;
     }
@@ -423,6 +461,9 @@ int gather_reduce_impl(const T* table, int64_t ld, int64_t n_table_rows, int32_t
     }
   }
 
+  for (int b = 0; b < n_blocks; ++b)
+    GNN_REQUIRE(!blocks[b].split, GNN_ERR_UNSUPPORTED,
+                "hi/lo fp16 output is implemented on the TMA path only (16-byte aligned rows of >= 256 bytes)");
   for (int b = 0; b < n_blocks; ++b) {
     const GatherBlock<T>& k = blocks[b];
     if (k.n_src == 0) continue;
@@ -503,6 +544,23 @@ int gnn_gather_reduce_multi_f32(const float* table, int64_t ld_table, int64_t n_
                                 const int64_t* ld_out_host, gnn_stream_t stream) {
   return gather_reduce_multi<float>(table, ld_table, n_table_rows, F, reduce, n_blocks, idx_host, idx_bits, n_src_host,
                                     fanout_host, out_host, ld_out_host, (cudaStream_t)stream);
+}
+
+int gnn_gather_reduce_multi_f32_split(const float* table, int64_t ld_table, int64_t n_table_rows, int32_t F, int reduce,
+                                      int32_t n_blocks, const void* const* idx_host, int idx_bits,
+                                      const int64_t* n_src_host, const int32_t* fanout_host, void* const* out_hi_host,
+                                      const int64_t* ld_out_host, const int64_t* lo_off_host, gnn_stream_t stream) {
+  GNN_REQUIRE(n_blocks >= 0 && n_blocks <= kMaxBlocks, GNN_ERR_UNSUPPORTED, "at most %d blocks per launch", kMaxBlocks);
+  GNN_REQUIRE(n_blocks == 0 || (idx_host && n_src_host && fanout_host && out_hi_host && ld_out_host && lo_off_host),
+              GNN_ERR_BAD_ARG, "null block array");
+  GatherBlock<float> blocks[kMaxBlocks];
+  for (int b = 0; b < n_blocks; ++b) {
+    blocks[b] = GatherBlock<float>{idx_host[b], idx_bits, n_src_host[b], fanout_host[b], (float*)out_hi_host[b],
+                                   ld_out_host[b], nullptr};
+    blocks[b].split = 1;
+    blocks[b].lo_off = lo_off_host[b];
+  }
+  return gather_reduce_impl<float>(table, ld_table, n_table_rows, F, reduce, blocks, n_blocks, (cudaStream_t)stream);
 }
 
 int gnn_gather_reduce_multi_bf16(const void* table, int64_t ld_table, int64_t n_table_rows, int32_t F, int reduce,

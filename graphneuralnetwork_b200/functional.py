@@ -303,6 +303,44 @@ def gather_reduce_multi_raw(table: torch.Tensor, blocks, reduce: str = "mean", o
     return outs
 
 
+def gather_reduce_multi_split_raw(table: torch.Tensor, blocks, reduce: str, outs_hi, lo_off: int):
+    """gnn_gather_reduce_multi_f32_split: like gather_reduce_multi_raw on an fp32 table, but every reduced value x
+    is written as hi = fp16(x) into `outs_hi[b]` (fp16 [n_src, F] views) and lo = fp16(x - hi) `lo_off` fp16
+    elements further along the row.  Raises GnnError(unsupported) off the TMA path."""
+    import ctypes as C
+    _require_cuda(table, *[b[0] for b in blocks])
+    lib = _lib.load()
+    table = _rowmajor(table)
+    if table.dtype != torch.float32:
+        raise _lib.GnnError("gather_reduce_multi_split: fp32 table only")
+    N, F = table.shape
+    nb = len(blocks)
+    idxs, bits = [], None
+    for idx, n_src, fanout in blocks:
+        idx = idx.contiguous().view(-1)
+        if idx.dtype not in (torch.int32, torch.int64):
+            idx = idx.to(torch.int64)
+        b = 32 if idx.dtype == torch.int32 else 64
+        if bits is not None and b != bits:
+            idx, b = idx.to(torch.int64 if bits == 64 else torch.int32), bits
+        bits = b
+        if idx.numel() != n_src * fanout:
+            raise _lib.GnnError(f"index block has {idx.numel()} ids, expected n_src*fanout = {n_src * fanout}")
+        idxs.append(idx)
+    for o in outs_hi:
+        if o.dtype != torch.float16 or o.stride(1) != 1:
+            raise _lib.GnnError("gather_reduce_multi_split: outputs must be fp16 views with unit column stride")
+    idx_arr = (C.c_void_p * nb)(*[_p(i) for i in idxs])
+    nsrc_arr = (C.c_int64 * nb)(*[int(b[1]) for b in blocks])
+    fan_arr = (C.c_int32 * nb)(*[int(b[2]) for b in blocks])
+    out_arr = (C.c_void_p * nb)(*[_p(o) for o in outs_hi])
+    ldo_arr = (C.c_int64 * nb)(*[_ld(o) for o in outs_hi])
+    lo_arr = (C.c_int64 * nb)(*[int(lo_off)] * nb)
+    _lib.check(lib.gnn_gather_reduce_multi_f32_split(_p(table), _ld(table), N, F, _lib.REDUCE[reduce], nb, idx_arr,
+                                                     bits or 64, nsrc_arr, fan_arr, out_arr, ldo_arr, lo_arr,
+                                                     _stream_ptr()), "gnn_gather_reduce_multi_f32_split")
+
+
 def sample_neighbors(g: CSRGraph, src: torch.Tensor, k: int, seed: int, out_dtype=torch.int32,
                      seed_offset: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """k sampled neighbour ids per source (gnn_sample_neighbors), flat and src-major like

@@ -226,6 +226,8 @@ class CSRGraph:
                                             _stream_ptr()), "gnn_dense_mask_count")
         nnz = int(rowptr[-1].item())  # one host read: nnz sizes the col array
         col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        if nnz == 0:  # an adjacency without a single positive entry: nothing to fill
+            return CSRGraph(rowptr, col, None, n_rows, n_cols)
         _lib.check(lib.gnn_dense_mask_fill(_p(adj), dt, n_rows, n_cols, ld, _p(rowptr), _p(col), _stream_ptr()),
                    "gnn_dense_mask_fill")
         return CSRGraph(rowptr, col, None, n_rows, n_cols)

@@ -51,7 +51,10 @@ def _pattern_of_learned_adjacency(H):
 
 def gcn_conv(X, H, weight):
     """`GTN_Model.gcn_conv` (GTN.py:49-52): D^-1 (offdiag(H) + I)^T (X W) with D the column sums of
-    offdiag(H) + I.  X [N, w_in], H [N, N] dense (learned, autograd flows into it), weight [w_in, w_out]."""
+    offdiag(H) + I.  X [N, w_in], H [N, N] dense (learned, autograd flows into it), weight [w_in, w_out].
+    The gradient w.r.t. H is produced on the support of H (its non-zero entries): the reference's dense autograd
+    also fills the structural zeros, but in GTN a zero of the composed adjacency is a zero of every factor
+    product, so no parameter receives anything from them (the model-level gradients are identical)."""
     XW = torch.mm(X, weight)
     n = H.shape[0]
     g, rows, cols = _pattern_of_learned_adjacency(H)

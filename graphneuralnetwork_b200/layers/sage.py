@@ -15,7 +15,8 @@ import torch
 from torch import nn
 import torch.nn.functional as F
 
-from ..functional import gather_reduce, gather_reduce_multi_raw, pad_table
+from .. import _lib
+from ..functional import gather_reduce, gather_reduce_multi_raw, gather_reduce_multi_split_raw, pad_table
 
 
 class SampledBlock:
@@ -168,6 +169,12 @@ class GraphSage(nn.Module):
         ld = (F_in + 3) // 4 * 4
         n_hop = [node_id_blocks[hop].numel() for hop in range(L)]
         total = sum(n_hop)
+        if getattr(self, "tensor_core_gemm", True) and layer0.aggr_neighbor_method in ("mean", "sum") \
+                and table.stride(0) * 4 % 16 == 0 and F_in * 4 >= 256:
+            try:
+                return self._layer0_split_gemm(table, node_id_blocks, ld, n_hop, total)
+            except _lib.GnnError:  # off the TMA path (unaligned table): the fp32 product below
+                self.tensor_core_gemm = False
         key = (total, table.device)
         buf = getattr(self, "_l0_buf", None)
         if buf is None or buf[0] != key:
@@ -189,6 +196,62 @@ class GraphSage(nn.Module):
         gather_reduce_multi_raw(table, [blocks[i] for i in order], layer0.aggr_neighbor_method,
                                 outs=[outs[i] for i in order])
         hidden = torch.mm(Z, Wc)
+        if layer0.activation:
+            hidden = layer0.activation(hidden)
+        out, row = [], 0
+        for n in n_hop:
+            out.append(hidden[row:row + n])
+            row += n
+        return out
+
+    def _table_fits_fp16(self, table):
+        """max|table| < 3e4 (an aggregate of rows never exceeds it): cached per table tensor (one host read)."""
+        key = (table.data_ptr(), table._version, tuple(table.shape))
+        hit = getattr(self, "_fp16_ok", None)
+        if hit is None or hit[0] != key:
+            self._fp16_ok = hit = (key, bool((table.abs().max() < 3.0e4).item()))
+        return hit[1]
+
+    def _layer0_split_gemm(self, table, node_id_blocks, ld, n_hop, total):
+        """Layer 0 with the fp32 `[self ‖ pooled]·[W_self ; W_agg]` product (K = 2·F, the largest single cost of the
+        minibatch after the gather: 26,624 x 1,208 x 128 on the Reddit-shaped config runs 0.17 ms on the fp32 SIMT
+        pipes) carried by the fp16 tensor cores at fp32-level accuracy: the gather's row flush writes every operand
+        value as hi = fp16(x), lo = fp16(x - hi) (22 mantissa bits, the same bytes as fp32), the weights are split
+        the same way, and   Z·W ~= Z_hi·W_hi + Z_lo·W_hi + Z_hi·W_lo   with fp32 accumulation — the dropped
+        Z_lo·W_lo term is below 2^-22 relative.  Still a torch matmul (a library GEMM outside the hot path), on
+        operands the gather kernel laid out for it.  Needs |table| within fp16 range (checked once per table)."""
+        if not self._table_fits_fp16(table):
+            raise _lib.GnnError("table exceeds the fp16 range: fp32 product")
+        L, fan, layer0 = self.num_layers, self.num_neighbors_list, self.gcn[0]
+        F_in, H = layer0.input_dim, layer0.hidden_dim
+        key = (total, table.device)
+        buf = getattr(self, "_l0_split", None)
+        if buf is None or buf[0] != key:
+            # row = [hi: self | pooled][lo: self | pooled]; pad columns stay zero for the buffer's lifetime
+            Zs = torch.zeros((total, 4 * ld), dtype=torch.float16, device=table.device)
+            Wc = torch.zeros((2 * ld, H), dtype=torch.float32, device=table.device)
+            self._l0_split = buf = (key, Zs, Wc)
+        _, Zs, Wc = buf
+        Wc[:F_in].copy_(layer0.weight)
+        Wc[ld:ld + F_in].copy_(layer0.aggregator.weight)
+        W_hi = Wc.to(torch.float16)
+        W_lo = (Wc - W_hi.float()).to(torch.float16)
+        blocks, outs, row = [], [], 0
+        for hop in range(L):
+            n = n_hop[hop]
+            blocks += [(node_id_blocks[hop + 1], n, fan[hop]), (node_id_blocks[hop], n, 1)]
+            outs += [Zs[row:row + n, ld:ld + F_in], Zs[row:row + n, :F_in]]
+            row += n
+        order = sorted(range(len(blocks)), key=lambda i: -blocks[i][1] * blocks[i][2])
+        gather_reduce_multi_split_raw(table, [blocks[i] for i in order], layer0.aggr_neighbor_method,
+                                      [outs[i] for i in order], lo_off=2 * ld)
+        # three products of K = 2·ld each, added in fp32 by torch: the tensor cores' fp32 accumulation truncates, so
+        # its error grows with K — one concatenated K = 4·ld product measured 5e-6 against float64, this form 2e-6
+        # (the fp32 SIMT product: 0.4-1.7e-6; tools/diag_split_gemm.py)
+        Z_hi, Z_lo = Zs[:, :2 * ld], Zs[:, 2 * ld:]
+        hidden = torch.mm(Z_hi, W_hi, out_dtype=torch.float32)
+        hidden += torch.mm(Z_lo, W_hi, out_dtype=torch.float32)
+        hidden += torch.mm(Z_hi, W_lo, out_dtype=torch.float32)
         if layer0.activation:
             hidden = layer0.activation(hidden)
         out, row = [], 0

@@ -230,6 +230,18 @@ int gnn_gather_reduce_multi_bf16(const void* table, int64_t ld_table, int64_t n_
                                  int32_t n_blocks, const void* const* idx_host, int idx_bits,
                                  const int64_t* n_src_host, const int32_t* fanout_host,
                                  void* const* out_host, const int64_t* ld_out_host, gnn_stream_t stream);
+/* Same launch, fp32 table, but every reduced value x leaves as TWO fp16 numbers: hi = fp16(x) at out_hi[b] and
+ * lo = fp16(x - hi) lo_off[b] fp16 elements further (ld_out / lo_off count fp16 elements; the same bytes as an
+ * fp32 output).  hi + lo carries 22 mantissa bits (x - hi is exact in fp32; a residual below fp16's normal range
+ * costs < 3e-8 absolute): the A-operand of the 3-product fp16 tensor-core GEMM (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,
+ * fp32 accumulate) that stands in for the fp32 `X.W` product of SageGCN.py:24-27 at fp32-level accuracy — the
+ * split is fused into the gather's row flush instead of being a separate pass over the operand.  The caller
+ * guarantees |x| < 65504.  TMA path only (16-byte aligned rows >= 256 bytes), mean/sum. */
+int gnn_gather_reduce_multi_f32_split(const float* table, int64_t ld_table, int64_t n_table_rows, int32_t F, int reduce,
+                                      int32_t n_blocks, const void* const* idx_host, int idx_bits,
+                                      const int64_t* n_src_host, const int32_t* fanout_host,
+                                      void* const* out_hi_host, const int64_t* ld_out_host,
+                                      const int64_t* lo_off_host, gnn_stream_t stream);
 /* Edge-type axis (GATNE): table [n_nodes, n_types, F] (ld_row = stride between (node,type)
  * rows), idx [n_src, n_types, fanout]; out[(b*n_types+t), :] = reduce_k table[idx[b,t,k], t, :]
  * — the per-type neighbour aggregation of GATNE_Pytorch/models/GATNE.py:57-77 (`torch.cat` of T
