@@ -52,19 +52,19 @@ SIGNATURES = {
     "gnn_sample_neighbors": (cint, [ptr, ptr, ptr, cint, i64, i32, u64, ptr, ptr, cint, ptr]),
     "gnn_gat_scores_f32": (cint, [ptr, i64, ptr, ptr, i64, i32, i32, ptr, ptr, ptr]),
     "gnn_gat_fused_fwd_f32": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr, ptr,
-                                     i64, ptr, ptr, ptr, i64, i64, ptr]),
+                                     i64, ptr, ptr, ptr, i64, i64, i64, ptr]),
     "gnn_gat_fused_bwd_f32": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
                                      i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64, cint,
-                                     ptr, ptr, ptr]),
+                                     ptr, ptr, i64, ptr]),
     "gnn_gat_fused_fwd_train_f32": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr,
-                                           ptr, ptr, ptr, i64, ptr, ptr, ptr, i64, i64, ptr]),
+                                           ptr, ptr, ptr, i64, ptr, ptr, ptr, i64, i64, i64, ptr]),
     "gnn_gat_fused_fwd_train_bf16": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr,
-                                            ptr, ptr, ptr, i64, ptr, ptr, ptr, i64, i64, ptr]),
+                                            ptr, ptr, ptr, i64, ptr, ptr, ptr, i64, i64, i64, ptr]),
     "gnn_gat_fused_fwd_bf16": (cint, [ptr, ptr, ptr, i64, ptr, ptr, i64, i64, i32, i32, f32, cint, cint, ptr, ptr, ptr,
-                                      i64, ptr, ptr, ptr, i64, i64, ptr]),
+                                      i64, ptr, ptr, ptr, i64, i64, i64, ptr]),
     "gnn_gat_fused_bwd_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr, i64, i64, i32,
                                       i32, f32, cint, ptr, ptr, i64, ptr, ptr, ptr, i64, ptr, i64, ptr, i64, i64, cint,
-                                      ptr, ptr, ptr]),
+                                      ptr, ptr, i64, ptr]),
     "gnn_synth_powerlaw_degrees": (cint, [i64, i64, f64, f64, i64, u64, ptr, ptr]),
     "gnn_synth_powerlaw_fill": (cint, [i64, i64, i64, ptr, f64, f64, i64, u64, ptr, ptr]),
     "gnn_synth_gcn_values": (cint, [i64, i64, ptr, ptr, ptr, ptr, ptr]),

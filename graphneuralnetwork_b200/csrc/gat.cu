@@ -50,6 +50,11 @@ struct GatArgs {
   int64_t ldo;
   float* row_max;
   float* row_sum;
+  // batched graphs (HAN's M metapaths over the same nodes, HAN/models/HAN.py:16-23, in ONE launch): the CSR is the
+  // block diagonal of M graphs of batch_n nodes (row r = graph r / batch_n, node r % batch_n; col ids offset
+  // likewise); s, t, row statistics and d_s / d_t are indexed by the batched row, graph m's feature columns sit
+  // at column offset m * HF of Wh / out / d_out / d_Wh.  0 = one graph.
+  int64_t batch_n;
   int SE;
   int packed;  // bf16 rows 4-byte aligned with even head width: lanes own column pairs (PK = 2)
   // backward
@@ -201,8 +206,11 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
   const int64_t e0 = __ldg(a.rowptr + i), e1 = __ldg(a.rowptr + i + 1);
   const int64_t d = e1 - e0;
   if (W == 1 && a.skip_deg_gt > 0 && d > a.skip_deg_gt) return;  // a long row: the CTA-per-row launch owns it
-  T* orow = reinterpret_cast<T*>(a.out) + i * a.ldo;
-  T* arow = a.out_act ? reinterpret_cast<T*>(a.out_act) + i * a.ldo : nullptr;
+  const int64_t gm = a.batch_n ? i / a.batch_n : 0;      // graph of this row (batched launch)
+  const int64_t joff = gm * a.batch_n;                    // its col ids are offset by joff
+  const int64_t coff = gm * a.HF;                         // its feature columns start at coff
+  T* orow = reinterpret_cast<T*>(a.out) + (i - joff) * a.ldo + coff;
+  T* arow = a.out_act ? reinterpret_cast<T*>(a.out_act) + (i - joff) * a.ldo + coff : nullptr;
   const bool seeded = a.keep == nullptr && a.keep_prob > 0.f;
   const uint64_t dseed = seeded ? drop_seed_of(a) : 0;
   const uint32_t thresh24 = (uint32_t)(a.keep_prob * 16777216.f);
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
       for (int c = 0; c < CPL; ++c)
         if (cv[c]) {
           const int ci = col_of<PK>(lane, c);
-          const float v0 = a.col_mean ? a.col_mean[ci] : 0.f;
+          const float v0 = a.col_mean ? a.col_mean[coff + ci] : 0.f;
           stv(orow + ci, arow ? v0 : act_elu(v0, a.elu));
           if (arow) stv(arow + ci, act_elu(v0, a.elu));
           if (ci % a.Fp == 0) {
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
     // A: logits, one lane per edge
     for (int k = lane; k < ne; k += 32) {
       const int j = __ldg(a.col + e0 + c0 + k);
-      cols[k] = j;
+      cols[k] = j - (int)joff;  // node id within its graph: the feature-row gathers of phase C
       const float* tj = a.t + (int64_t)j * H;
       if (HT) {
         float tv[HT ? HT : 1];
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_fwd_kernel(const
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const bool ok = k0 + u < ne;
-        const T* wr = reinterpret_cast<const T*>(a.Wh) + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
+        const T* wr = reinterpret_cast<const T*>(a.Wh) + coff + (int64_t)(ok ? cols[k0 + u] : 0) * a.ldw;
 #pragma unroll
         for (int q = 0; q < CPL / PK; ++q) x[u][q] = (ok && cv[q * PK]) ? ld_stage<T, PK>(wr, lane, q) : 0;
       }
@@ -436,13 +444,15 @@ __global__ void __launch_bounds__(256) gat_rowstat_kernel(const T* __restrict__ 
                                                           const float* __restrict__ row_max,
                                                           const float* __restrict__ row_sum, int64_t n, int H, int Fp,
                                                           float* __restrict__ rowstat, int apply_elu,
-                                                          T* __restrict__ d_pre) {
+                                                          T* __restrict__ d_pre, int64_t batch_n) {
   const int64_t total = n * H;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(p % H);
     const int64_t i = p / H;
-    const T* a = d_out + i * ldo + h * Fp;
-    const T* b = out_pre + i * ldo + h * Fp;
+    const int64_t gm = batch_n ? i / batch_n : 0;
+    const int64_t fo = (i - gm * batch_n) * ldo + gm * (int64_t)H * Fp + h * Fp;  // (node row, graph's column block)
+    const T* a = d_out + fo;
+    const T* b = out_pre + fo;
     float acc = 0.f;
     for (int f = 0; f < Fp; ++f) {
       float g = ldv<T>(a + f);
@@ -453,7 +463,7 @@ __global__ void __launch_bounds__(256) gat_rowstat_kernel(const T* __restrict__ 
           g *= y1 > 0.f ? 1.f : __expf(y1);
         }
         g *= x > 0.f ? 1.f : __expf(x);
-        stv(d_pre + i * ldo + h * Fp + f, g);
+        stv(d_pre + fo + f, g);
         g = round_as<T>(g);  // the passes read the ROUNDED value (bf16): keep D consistent with them
       }
       acc = fmaf(g, x, acc);
@@ -500,6 +510,9 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
   const int64_t d = e1 - e0;
   if (W == 1 && a.skip_deg_gt > 0 && d > a.skip_deg_gt) return;
   const int H = HT ? HT : a.H, Hp = HT ? HT : a.Hp, SE = a.SE, HF = a.HF, Fp = a.Fp;
+  const int64_t gm = a.batch_n ? r / a.batch_n : 0;
+  const int64_t joff = gm * a.batch_n;
+  const int64_t coff = gm * a.HF;
   const int PW = gat_bwd_warp_floats(SE, H, HF, TR);
   float* w2s = sm + (size_t)warp * PW;
   float* qs = w2s + SE * H;
@@ -548,7 +561,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
     for (int k = lane; k < ne; k += 32) {
       const int64_t e = e0 + c0 + k;
       const int o = __ldg(a.col + e);
-      cols[k] = o;
+      cols[k] = o - (int)joff;  // node id within its graph (feature-row gathers); o itself indexes t / rowstat
       const float* ot = TR ? a.rowstat + (int64_t)o * 4 * H : a.t + (int64_t)o * H;
       const int64_t kslot = (TR && a.perm && (a.keep || seeded)) ? __ldg(a.perm + e) : e;  // forward edge slot
       if (HT) {
@@ -623,7 +636,7 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
     if (hsub < H)
       for (int k = g; k < ne; k += ngrp) qsum += qs[k * H + hsub];
     // C: one lane per column, 8 row gathers in flight
-    const T* base = reinterpret_cast<const T*>(TR ? a.d_out : a.Wh);
+    const T* base = reinterpret_cast<const T*>(TR ? a.d_out : a.Wh) + coff;
     const int64_t ldb = TR ? a.ldo : a.ldw;
     for (int k0 = 0; k0 < ne; k0 += 8) {
       typename RawOf<T>::type x[8][CPL / PK];
@@ -678,13 +691,13 @@ __global__ void __launch_bounds__(GatBlock<W>::kWarps * 32) gat_bwd2_kernel(cons
   // finalize (one warp): the head-wise contraction of the accumulated vector with this row's own vector
   float* buf = w2s;  // [HF] scratch (this warp's staging area is free now)
   __syncwarp();
-  const T* own = reinterpret_cast<const T*>(TR ? a.Wh : a.d_out) + r * (TR ? a.ldw : a.ldo);
+  const T* own = reinterpret_cast<const T*>(TR ? a.Wh : a.d_out) + (r - joff) * (TR ? a.ldw : a.ldo) + coff;
 #pragma unroll
   for (int c = 0; c < CPL; ++c)
     if (cv[c]) {
       const int ci = col_of<PK>(lane, c);
       buf[ci] = acc2[c] * ldv<T>(own + ci);
-      if (TR) stv(reinterpret_cast<T*>(a.d_Wh) + r * a.ld_dwh + ci, acc1[c]);
+      if (TR) stv(reinterpret_cast<T*>(a.d_Wh) + (r - joff) * a.ld_dwh + coff + ci, acc1[c]);
     }
   __syncwarp();
   if (lane < H) {
@@ -792,7 +805,7 @@ int gat_fwd_impl(const int64_t* rowptr, const int32_t* col, const T* Wh, int64_t
                  int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode, int apply_elu,
                  const float* col_mean, const float* edge_keep, T* out, int64_t ldo, float* row_max, float* row_sum,
                  const int64_t* long_rows, int64_t n_long, int64_t long_threshold, cudaStream_t st,
-                 T* out_act = nullptr, const gnn_gat_dropout* drop = nullptr) {
+                 T* out_act = nullptr, const gnn_gat_dropout* drop = nullptr, int64_t batch_nodes = 0) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
@@ -800,8 +813,13 @@ int gat_fwd_impl(const int64_t* rowptr, const int32_t* col, const T* Wh, int64_t
   GNN_REQUIRE(mode == GNN_GAT_SOFTMAX || mode == GNN_GAT_EXPNEG, GNN_ERR_BAD_ARG, "unknown mode %d", mode);
   GNN_REQUIRE(apply_elu >= 0 && apply_elu <= 2, GNN_ERR_BAD_ARG, "apply_elu must be 0, 1 or 2");
   const int HF = H * Fp;
-  GNN_REQUIRE(ldw >= HF && ldo >= HF, GNN_ERR_BAD_ARG, "leading dimension smaller than H*Fp");
+  GNN_REQUIRE(batch_nodes >= 0 && (batch_nodes == 0 || n % batch_nodes == 0), GNN_ERR_BAD_ARG,
+              "batch_nodes must divide the batched row count");
+  const int64_t n_graphs = batch_nodes ? n / batch_nodes : 1;
+  GNN_REQUIRE(ldw >= n_graphs * HF && ldo >= n_graphs * HF, GNN_ERR_BAD_ARG,
+              "leading dimension smaller than (graphs x) H*Fp");
   GatArgs a{};
+  a.batch_n = batch_nodes;
   a.rowptr = rowptr;
   a.col = col;
   a.Wh = Wh;
@@ -888,7 +906,7 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
                  float alpha, int mode, const float* edge_keep, T* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
                  float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long, const int64_t* long_rows_t,
                  int64_t n_long_t, int64_t long_threshold, cudaStream_t st, int apply_elu = 0, T* d_pre = nullptr,
-                 const gnn_gat_dropout* drop = nullptr) {
+                 const gnn_gat_dropout* drop = nullptr, int64_t batch_nodes = 0) {
   int rc = check_common(n, H, Fp);
   if (rc != GNN_OK) return rc;
   if (n == 0) return GNN_OK;
@@ -902,8 +920,13 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
               "apply_elu must be 0..2 and needs the d_pre scratch when > 0");
   GNN_REQUIRE(mode == GNN_GAT_SOFTMAX || mode == GNN_GAT_EXPNEG, GNN_ERR_BAD_ARG, "unknown mode %d", mode);
   const int HF = H * Fp;
-  GNN_REQUIRE(ldw >= HF && ldo >= HF && ld_dwh >= HF, GNN_ERR_BAD_ARG, "leading dimension smaller than H*Fp");
+  GNN_REQUIRE(batch_nodes >= 0 && (batch_nodes == 0 || n % batch_nodes == 0), GNN_ERR_BAD_ARG,
+              "batch_nodes must divide the batched row count");
+  const int64_t n_graphs = batch_nodes ? n / batch_nodes : 1;
+  GNN_REQUIRE(ldw >= n_graphs * HF && ldo >= n_graphs * HF && ld_dwh >= n_graphs * HF, GNN_ERR_BAD_ARG,
+              "leading dimension smaller than (graphs x) H*Fp");
   GatArgs a{};
+  a.batch_n = batch_nodes;
   a.Wh = Wh;
   a.ldw = ldw;
   a.s = s;
@@ -932,7 +955,7 @@ int gat_bwd_impl(const int64_t* rowptr, const int32_t* col, const int64_t* rowpt
     const int64_t cap = (int64_t)num_sms() * 16;
     grid = grid > cap ? cap : grid;
     gat_rowstat_kernel<T><<<(unsigned)grid, 256, 0, st>>>(d_out, out_pre, ldo, s, row_max, row_sum, n, H, Fp,
-                                                         row_scratch, apply_elu, d_pre);
+                                                         row_scratch, apply_elu, d_pre, batch_nodes);
     GNN_LAUNCH_CHECK();
   }
   a.packed = sizeof(T) == 2 && Fp % 2 == 0 && ldw % 2 == 0 && ldo % 2 == 0 && aligned_to(Wh, 4) &&
@@ -1002,19 +1025,21 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
                           const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode,
                           int apply_elu, const float* col_mean, const float* edge_keep, float* out, int64_t ldo,
                           float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
-                          int64_t long_threshold, gnn_stream_t stream) {
+                          int64_t long_threshold, int64_t batch_nodes, gnn_stream_t stream) {
   return gat_fwd_impl<float>(rowptr, col, Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode, apply_elu, col_mean, edge_keep, out,
-                             ldo, row_max, row_sum, long_rows, n_long, long_threshold, (cudaStream_t)stream);
+                             ldo, row_max, row_sum, long_rows, n_long, long_threshold, (cudaStream_t)stream, nullptr,
+                             nullptr, batch_nodes);
 }
 
 int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw, const float* s,
                            const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp, float alpha, int mode,
                            int apply_elu, const float* col_mean, const float* edge_keep, void* out, int64_t ldo,
                            float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
-                           int64_t long_threshold, gnn_stream_t stream) {
+                           int64_t long_threshold, int64_t batch_nodes, gnn_stream_t stream) {
   return gat_fwd_impl<__nv_bfloat16>(rowptr, col, (const __nv_bfloat16*)Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode,
                                      apply_elu, col_mean, edge_keep, (__nv_bfloat16*)out, ldo, row_max, row_sum,
-                                     long_rows, n_long, long_threshold, (cudaStream_t)stream);
+                                     long_rows, n_long, long_threshold, (cudaStream_t)stream, nullptr, nullptr,
+                                     batch_nodes);
 }
 
 int gnn_gat_fused_fwd_train_f32(const int64_t* rowptr, const int32_t* col, const float* Wh, int64_t ldw,
@@ -1022,11 +1047,11 @@ int gnn_gat_fused_fwd_train_f32(const int64_t* rowptr, const int32_t* col, const
                                 float alpha, int mode, int apply_elu, const float* col_mean, const float* edge_keep,
                                 const gnn_gat_dropout* dropout, float* out_pre, float* out_act, int64_t ldo,
                                 float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
-                                int64_t long_threshold, gnn_stream_t stream) {
+                                int64_t long_threshold, int64_t batch_nodes, gnn_stream_t stream) {
   GNN_REQUIRE(out_act || apply_elu == 0, GNN_ERR_BAD_ARG, "apply_elu > 0 needs out_act");
   return gat_fwd_impl<float>(rowptr, col, Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode, apply_elu, col_mean, edge_keep,
                              out_pre, ldo, row_max, row_sum, long_rows, n_long, long_threshold, (cudaStream_t)stream,
-                             apply_elu > 0 ? out_act : nullptr, dropout);
+                             apply_elu > 0 ? out_act : nullptr, dropout, batch_nodes);
 }
 
 int gnn_gat_fused_fwd_train_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw,
@@ -1034,12 +1059,12 @@ int gnn_gat_fused_fwd_train_bf16(const int64_t* rowptr, const int32_t* col, cons
                                  float alpha, int mode, int apply_elu, const float* col_mean, const float* edge_keep,
                                  const gnn_gat_dropout* dropout, void* out_pre, void* out_act, int64_t ldo,
                                  float* row_max, float* row_sum, const int64_t* long_rows, int64_t n_long,
-                                 int64_t long_threshold, gnn_stream_t stream) {
+                                 int64_t long_threshold, int64_t batch_nodes, gnn_stream_t stream) {
   GNN_REQUIRE(out_act || apply_elu == 0, GNN_ERR_BAD_ARG, "apply_elu > 0 needs out_act");
   return gat_fwd_impl<__nv_bfloat16>(rowptr, col, (const __nv_bfloat16*)Wh, ldw, s, t, n, nnz, H, Fp, alpha, mode,
                                      apply_elu, col_mean, edge_keep, (__nv_bfloat16*)out_pre, ldo, row_max, row_sum,
                                      long_rows, n_long, long_threshold, (cudaStream_t)stream,
-                                     apply_elu > 0 ? (__nv_bfloat16*)out_act : nullptr, dropout);
+                                     apply_elu > 0 ? (__nv_bfloat16*)out_act : nullptr, dropout, batch_nodes);
 }
 
 int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
@@ -1049,11 +1074,11 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col, const int64
                           const float* edge_keep, float* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
                           float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
                           const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, int apply_elu,
-                          float* d_pre, const gnn_gat_dropout* dropout, gnn_stream_t stream) {
+                          float* d_pre, const gnn_gat_dropout* dropout, int64_t batch_nodes, gnn_stream_t stream) {
   return gat_bwd_impl<float>(rowptr, col, rowptr_t, col_t, perm_t, Wh, ldw, s, t, row_max, row_sum, out_pre, d_out, ldo,
                              n, H, Fp, alpha, mode, edge_keep, d_Wh, ld_dwh, d_s, d_t, row_scratch, nnz, long_rows,
                              n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream, apply_elu, d_pre,
-                             dropout);
+                             dropout, batch_nodes);
 }
 
 int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col, const int64_t* rowptr_t, const int32_t* col_t,
@@ -1063,12 +1088,12 @@ int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col, const int6
                            const float* edge_keep, void* d_Wh, int64_t ld_dwh, float* d_s, float* d_t,
                            float* row_scratch, int64_t nnz, const int64_t* long_rows, int64_t n_long,
                            const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold, int apply_elu,
-                           void* d_pre, const gnn_gat_dropout* dropout, gnn_stream_t stream) {
+                           void* d_pre, const gnn_gat_dropout* dropout, int64_t batch_nodes, gnn_stream_t stream) {
   return gat_bwd_impl<__nv_bfloat16>(rowptr, col, rowptr_t, col_t, perm_t, (const __nv_bfloat16*)Wh, ldw, s, t, row_max,
                                      row_sum, (const __nv_bfloat16*)out_pre, (const __nv_bfloat16*)d_out, ldo, n, H, Fp,
                                      alpha, mode, edge_keep, (__nv_bfloat16*)d_Wh, ld_dwh, d_s, d_t, row_scratch, nnz,
                                      long_rows, n_long, long_rows_t, n_long_t, long_threshold, (cudaStream_t)stream,
-                                     apply_elu, (__nv_bfloat16*)d_pre, dropout);
+                                     apply_elu, (__nv_bfloat16*)d_pre, dropout, batch_nodes);
 }
 
 }  // extern "C"

@@ -387,8 +387,13 @@ class _GatherReduceFn(torch.autograd.Function):
         idx, argmax = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
             return None, None, None, None, None
-        if d_out.dtype != torch.float32:
-            raise _lib.GnnError("gather_reduce backward is fp32 only")
+        # bf16-feature variant: the ordered scatter accumulates in fp32 (the fp32 kernels) and the table gradient is
+        # returned in the table's dtype — one rounding at the end, like every other bf16 path here
+        out_dtype = d_out.dtype
+        if d_out.dtype == torch.bfloat16:
+            d_out = d_out.float()
+        elif d_out.dtype != torch.float32:
+            raise _lib.GnnError(f"gather_reduce backward: unsupported dtype {d_out.dtype}")
         lib = _lib.load()
         d_out = d_out.contiguous()
         scale = 1.0 / fanout if reduce == "mean" else 1.0
@@ -400,7 +405,7 @@ class _GatherReduceFn(torch.autograd.Function):
                                                            _p(d_table), _stream_ptr()), "gnn_gather_reduce_bwd_dense_f32")
             if N > n_src * fanout:
                 d_table[n_src * fanout:].zero_()
-            return d_table, None, None, None, None
+            return d_table.to(out_dtype), None, None, None, None
         if reduce == "max":
             raise _lib.GnnError("max backward into a gathered table is not implemented (the reference's max path "
                                 "raises TypeError, GraphSAGE_Pytorch/models/Aggregator.py:24,29)")
@@ -409,7 +414,7 @@ class _GatherReduceFn(torch.autograd.Function):
         _lib.check(lib.gnn_gather_reduce_bwd_f32(_p(rowptr_t), _p(pos_t), N, fanout, scale, _p(d_out), _ld(d_out),
                                                  _p(d_table), _ld(d_table), F, _stream_ptr()),
                    "gnn_gather_reduce_bwd_f32")
-        return d_table, None, None, None, None
+        return d_table.to(out_dtype), None, None, None, None
 
 
 def gather_reduce(table: torch.Tensor, idx: Optional[torch.Tensor], n_src: int, fanout: int,
@@ -574,12 +579,15 @@ def _gat_groups(H: int, Fp: int):
 
 
 def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=0, keep=None, save_stats=False,
-                out=None, dropout: Optional[AttentionDropout] = None, out_act: Optional[torch.Tensor] = None):
+                out=None, dropout: Optional[AttentionDropout] = None, out_act: Optional[torch.Tensor] = None,
+                batch: int = 1):
     """Forward of the fused attention aggregation (no autograd).  Wh fp32 or bf16 ([n, H*Fp]); s, t fp32 [n,H];
     `out` has Wh's dtype.  Layers wider than one call's 256 columns (e.g. 8 heads x 64) are run as head groups /
     column tiles of a head; the softmax statistics are per head, so a tiled head recomputes them per tile.
     Training form (`out_act` given): `out` receives the PRE-activation aggregate and `out_act` the activated one
-    (elu applied `elu` times) in the same launch.  `dropout`: seeded attention dropout (or `keep`: explicit mask)."""
+    (elu applied `elu` times) in the same launch.  `dropout`: seeded attention dropout (or `keep`: explicit mask).
+    batch = M > 1: `g` is the block diagonal of M graphs over the same N nodes (CSRGraph.block_diagonal), Wh / out are
+    [N, M*H*Fp] (graph m's columns at m*H*Fp), s / t are [M*N, H] (batched-row major) — HAN's metapaths in one launch."""
     _require_cuda(Wh, s, t, keep)
     lib = _lib.load()
     Wh = _rowmajor(Wh)
@@ -588,18 +596,24 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
     s = s.float().contiguous()
     t = t.float().contiguous()
     n = g.n_rows
-    if Wh.shape != (n, H * Fp) or g.n_cols != n:
-        raise _lib.GnnError(f"gat: Wh {tuple(Wh.shape)} does not match graph n={n}, H*Fp={H * Fp}")
+    M = int(batch)
+    nodes = n // M
+    if M < 1 or n % M or Wh.shape != (nodes, M * H * Fp) or g.n_cols != n or s.shape != (n, H) or t.shape != (n, H):
+        raise _lib.GnnError(f"gat: Wh {tuple(Wh.shape)} / s {tuple(s.shape)} do not match graph rows={n}, batch={M}, "
+                            f"H*Fp={H * Fp}")
+    if M > 1 and H * Fp > 256:
+        raise _lib.GnnError("gat: batched graphs need H*Fp <= 256 per graph")
     if out is None:
-        out = torch.empty((n, H * Fp), dtype=Wh.dtype, device=Wh.device)
-    elif out.shape != (n, H * Fp) or out.dtype != Wh.dtype or out.stride(1) != 1 or not out.is_cuda:
-        raise _lib.GnnError("gat: `out` must be a CUDA [n, H*Fp] view of Wh's dtype with unit column stride")
+        out = torch.empty((nodes, M * H * Fp), dtype=Wh.dtype, device=Wh.device)
+    elif out.shape != (nodes, M * H * Fp) or out.dtype != Wh.dtype or out.stride(1) != 1 or not out.is_cuda:
+        raise _lib.GnnError("gat: `out` must be a CUDA [nodes, batch*H*Fp] view of Wh's dtype with unit column stride")
     if out_act is not None and (out_act.shape != out.shape or out_act.dtype != out.dtype or
                                 out_act.stride() != out.stride()):
         raise _lib.GnnError("gat: `out_act` must match `out` in shape, dtype and strides")
     row_max = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     row_sum = torch.empty((n, H), dtype=torch.float32, device=Wh.device) if save_stats else None
     col_mean = Wh.float().mean(dim=0).contiguous() if g.has_empty_rows() else None
+    bn = nodes if M > 1 else 0
     lr, thr = g.gat_long_rows()
     f32 = Wh.dtype == torch.float32
     train = out_act is not None or (dropout is not None and dropout.p > 0.0)
@@ -634,11 +648,11 @@ def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=
                           float(alpha), mode, elu if act_buf is not None else 0, _p(cm), _p(kg),
                           C.byref(dstruct) if dstruct is not None else None, pre_buf.data_ptr() + c0 * esz,
                           None if act_buf is None else act_buf.data_ptr() + c0 * esz, _ld(out), _p(rm), _p(rs),
-                          _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd_train")
+                          _p(lr), lr.numel(), thr, bn, _stream_ptr()), "gnn_gat_fused_fwd_train")
         else:
             _lib.check(fn(_p(g.rowptr), _p(g.col), Wh.data_ptr() + c0 * esz, _ld(Wh), _p(sg), _p(tg), n, g.nnz, Hg, Fg,
                           float(alpha), mode, elu, _p(cm), _p(kg), out.data_ptr() + c0 * esz, _ld(out), _p(rm), _p(rs),
-                          _p(lr), lr.numel(), thr, _stream_ptr()), "gnn_gat_fused_fwd")
+                          _p(lr), lr.numel(), thr, bn, _stream_ptr()), "gnn_gat_fused_fwd")
         if not whole and save_stats:
             row_max[:, h0:h1] = rm
             row_sum[:, h0:h1] = rs
@@ -651,15 +665,16 @@ class _GatFn(torch.autograd.Function):
     chain inside its first kernel — neither the activations nor their gradients are separate launches."""
 
     @staticmethod
-    def forward(ctx, Wh, s, t, g: CSRGraph, H, Fp, alpha, mode, keep, elu, dropout):
+    def forward(ctx, Wh, s, t, g: CSRGraph, H, Fp, alpha, mode, keep, elu, dropout, batch=1):
         Wh = _rowmajor(Wh)
         if dropout is not None and dropout.p > 0.0 and len(list(_gat_groups(H, Fp))) > 1:
             keep, dropout = attention_keep_mask_from_seed(g, H, dropout), None
-        out_pre = torch.empty((g.n_rows, H * Fp), dtype=Wh.dtype, device=Wh.device)
+        out_pre = torch.empty((g.n_rows // batch, batch * H * Fp), dtype=Wh.dtype, device=Wh.device)
         out_act = torch.empty_like(out_pre) if elu > 0 else None
         _, row_max, row_sum = gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep, save_stats=True,
-                                          out=out_pre, dropout=dropout, out_act=out_act)
+                                          out=out_pre, dropout=dropout, out_act=out_act, batch=batch)
         ctx.g, ctx.cfg = g, (H, Fp, float(alpha), mode, int(elu))
+        ctx.batch = int(batch)
         ctx.dropout = dropout
         ctx.st_dtypes = (s.dtype, t.dtype)
         ctx.save_for_backward(Wh, s.float().contiguous(), t.float().contiguous(), row_max, row_sum, out_pre,
@@ -682,7 +697,9 @@ class _GatFn(torch.autograd.Function):
             d_out = d_out.contiguous()  # out is contiguous [n, H*Fp]: one leading dimension for both
         gt = g.transpose()
         dev = Wh.device
-        d_Wh = torch.empty((n, H * Fp), dtype=Wh.dtype, device=dev)
+        M = ctx.batch
+        bn = n // M if M > 1 else 0
+        d_Wh = torch.empty_like(Wh)
         d_s = torch.empty((n, H), dtype=torch.float32, device=dev)
         d_t = torch.empty((n, H), dtype=torch.float32, device=dev)
         d_pre = torch.empty_like(out) if elu > 0 else None
@@ -709,7 +726,7 @@ class _GatFn(torch.autograd.Function):
                           d_Wh.data_ptr() + c0 * esz, _ld(d_Wh), _p(ds), _p(dt), _p(row_scratch), g.nnz, _p(lr),
                           lr.numel(), _p(lrt), lrt.numel(), thr, elu,
                           None if d_pre is None else d_pre.data_ptr() + c0 * esz,
-                          C.byref(dstruct) if dstruct is not None else None, _stream_ptr()), "gnn_gat_fused_bwd")
+                          C.byref(dstruct) if dstruct is not None else None, bn, _stream_ptr()), "gnn_gat_fused_bwd")
             if not whole:
                 # dz is linear in (head dot, row dot): the tiles of one head add up (first tile assigns)
                 if f0 == 0:
@@ -722,13 +739,20 @@ class _GatFn(torch.autograd.Function):
             # rows without edges output the mean of all Wh rows (GAT/models/layers.py:28-30).  Sync-free
             # (no boolean-mask indexing): this runs inside CapturedTrainStep's CUDA-graph capture
             dpre = (d_pre if elu > 0 else d_out).float()
-            d_Wh += ((dpre * g.empty_row_mask().unsqueeze(1)).sum(dim=0, keepdim=True) / n).to(d_Wh.dtype)
-        return d_Wh, d_s.to(ctx.st_dtypes[0]), d_t.to(ctx.st_dtypes[1]), None, None, None, None, None, None, None, None
+            if M > 1:  # per graph: its empty rows spread their gradient over its own column block
+                mask = g.empty_row_mask().view(M, n // M, 1)
+                blocks = dpre.view(n // M, M, H * Fp).permute(1, 0, 2)
+                d_Wh += ((blocks * mask).sum(dim=1) / (n // M)).reshape(1, M * H * Fp).to(d_Wh.dtype)
+            else:
+                d_Wh += ((dpre * g.empty_row_mask().unsqueeze(1)).sum(dim=0, keepdim=True) / n).to(d_Wh.dtype)
+        return (d_Wh, d_s.to(ctx.st_dtypes[0]), d_t.to(ctx.st_dtypes[1]), None, None, None, None, None, None, None, None,
+                None)
 
 
 def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tensor, H: int, Fp: int, alpha: float,
                   mode: int = _lib.GAT_SOFTMAX, elu: int = 0, keep: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None, dropout: Optional[AttentionDropout] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, dropout: Optional[AttentionDropout] = None,
+                  batch: int = 1) -> torch.Tensor:
     """Fused edge-score + LeakyReLU + edge-softmax + weighted aggregation over all H heads, with the ELU(s) that
     follow (elu = 0 | 1 | 2) in the kernel epilogue — with and without autograd.
     Wh may be fp32 or bf16 (the bf16-feature variant: bf16 rows, fp32 scores / softmax / accumulation).
@@ -737,10 +761,10 @@ def gat_aggregate(g: CSRGraph, Wh: torch.Tensor, s: torch.Tensor, t: torch.Tenso
     if not need_grad:
         # `out` (optional): a strided [n, H*Fp] view the kernel writes in place, e.g. one metapath's
         # slice of HAN's [N, M, H*Fp] semantic stack
-        return gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep, out=out, dropout=dropout)[0]
+        return gat_fwd_raw(g, Wh, s, t, H, Fp, alpha, mode, elu=elu, keep=keep, out=out, dropout=dropout, batch=batch)[0]
     if out is not None:
         raise _lib.GnnError("gat_aggregate: `out` is only supported without autograd")
-    return _GatFn.apply(Wh, s, t, g, H, Fp, alpha, mode, keep, elu, dropout)
+    return _GatFn.apply(Wh, s, t, g, H, Fp, alpha, mode, keep, elu, dropout, batch)
 
 
 def attention_keep_mask(g: CSRGraph, H: int, p: float, generator: Optional[torch.Generator] = None) -> torch.Tensor:

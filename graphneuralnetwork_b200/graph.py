@@ -89,6 +89,8 @@ class CSRGraph:
                                              ws_bytes, _stream_ptr()), "gnn_csr_transpose")
             self._t = CSRGraph(rowptr_t, col_t, val_t, self.n_cols, self.n_rows)
             self._t._t = self
+            if getattr(self, "_gat_long_thr", None):
+                self._t._gat_long_thr = self._gat_long_thr
             self._perm_t = perm_t
         return self._t
 
@@ -145,7 +147,7 @@ class CSRGraph:
         """(long_rows int64, threshold): rows the attention kernels hand to a whole CTA (host-side plan,
         cached)."""
         if getattr(self, "_gat_long", None) is None:
-            thr = _lib.get_tuning("gat.long_row")
+            thr = getattr(self, "_gat_long_thr", None) or _lib.get_tuning("gat.long_row")
             deg = self.rowptr[1:] - self.rowptr[:-1]
             self._gat_long = (torch.nonzero(deg > thr).flatten().contiguous(), thr)
         return self._gat_long
@@ -161,6 +163,37 @@ class CSRGraph:
         if getattr(self, "_empty_mask", None) is None:
             self._empty_mask = ((self.rowptr[1:] - self.rowptr[:-1]) == 0).to(torch.float32)
         return self._empty_mask
+
+    _block_cache = {}
+
+    @staticmethod
+    def block_diagonal(graphs) -> "CSRGraph":
+        """Block diagonal of M square pattern graphs over the same N nodes (HAN's metapath adjacencies): row
+        m*N + i is row i of graph m, its column ids offset by m*N.  One fused attention launch walks all M graphs
+        (`gat_aggregate(..., batch=M)`).  Cached per tuple of graphs."""
+        graphs = list(graphs)
+        key = tuple(id(g) for g in graphs)
+        hit = CSRGraph._block_cache.get(key)
+        if hit is not None and all(a is b for a, b in zip(hit[0], graphs)):
+            return hit[1]
+        n = graphs[0].n_rows
+        assert all(g.n_rows == n and g.n_cols == n and g.val is None for g in graphs), "square pattern graphs over the same nodes"
+        parts, cols, off = [], [], 0
+        for m, g in enumerate(graphs):
+            parts.append(g.rowptr[:-1] + off)
+            cols.append(g.col + m * n)
+            off += g.nnz
+        parts.append(torch.tensor([off], dtype=torch.int64, device=graphs[0].device))
+        big = CSRGraph(torch.cat(parts), torch.cat(cols).to(torch.int32), None, len(graphs) * n, len(graphs) * n)
+        # a dense member graph (one whose rows would each get a CTA on its own: gat.coop_min_avg_deg) keeps CTA rows
+        # inside the batch even when the batch's average degree falls under that bar: its rows join the long-row list
+        coop = _lib.get_tuning("gat.coop_min_avg_deg")
+        if big.nnz // max(big.n_rows, 1) < coop and any(g.nnz // max(g.n_rows, 1) >= coop for g in graphs):
+            big._gat_long_thr = coop
+        if len(CSRGraph._block_cache) >= 8:
+            CSRGraph._block_cache.pop(next(iter(CSRGraph._block_cache)))
+        CSRGraph._block_cache[key] = (graphs, big)
+        return big
 
     # -- builders --------------------------------------------------------------------
     @staticmethod

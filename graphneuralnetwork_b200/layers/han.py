@@ -21,8 +21,10 @@ from torch import nn
 import torch.nn.functional as F
 
 from .. import _lib
-from ..graph import adj_cache
+from ..functional import gat_aggregate, next_attention_dropout
+from ..graph import CSRGraph, adj_cache
 from .gat import GraphAttentionLayer, _fused_heads
+from . import gat as _gat
 
 
 class GATConv(nn.Module):
@@ -93,8 +95,47 @@ class HANLayer(nn.Module):
         self.semantic_attention = SemanticAttention(in_size=out_size * layer_num_heads)
         self._width = out_size * layer_num_heads
 
+    def _batched(self, gs, h):
+        """All M metapath GATConvs (HAN.py:16-21) in ONE attention launch over the block diagonal of the M graphs:
+        `z[:, m, :]` is metapath m's multi-head output — the tensor `torch.stack(semantic_embeddings, dim=1)` builds.
+        Per-metapath feature dropout (NodeAttention.py:59: every GATConv draws its own mask) is kept."""
+        convs = list(self.gat_layers)
+        M, n = len(convs), h.shape[0]
+        graphs = [adj_cache.get(g) for g in gs]
+        big = CSRGraph.block_diagonal(graphs)
+        heads0 = list(convs[0].attentions)
+        H, Fp, alpha = len(heads0), heads0[0].out_features, heads0[0].alpha
+        p, training = convs[0].dropout, self.training
+        drop_active = training and p > 0.0
+        Ws = [torch.cat([hd.W for hd in conv.attentions], dim=1) for conv in convs]            # M x [F_in, H*Fp]
+        # one product per metapath, exactly the per-GATConv GEMM shape: Wh is then bit-identical to the unbatched path
+        # (a single [F_in, M*H*Fp] product rounds differently, and LeakyReLU's kink at s_i + t_j = 0 turns a 1e-6
+        # perturbation of one score into a 1e-4 change of that edge's gradient: measured on the ACM-sized golden);
+        # per-metapath feature dropout draws its own mask per GATConv as the reference does
+        Wh = torch.cat([torch.mm(F.dropout(h, p, training=True) if drop_active else h, W) for W in Ws], dim=1)
+        a = torch.stack([torch.stack([hd.a[:, 0] for hd in conv.attentions]) for conv in convs])  # [M, H, 2*Fp]
+        Wh4 = Wh.view(n, M, H, Fp).float()
+        s = (Wh4 * a[None, :, :, :Fp].float()).sum(-1).permute(1, 0, 2).reshape(M * n, H)     # batched-row major
+        t = (Wh4 * a[None, :, :, Fp:].float()).sum(-1).permute(1, 0, 2).reshape(M * n, H)
+        keep = drop = None
+        if drop_active:
+            if _gat.EXPLICIT_DROPOUT_MASK:
+                keep = _gat.attention_keep_mask(big, H, p)
+            else:
+                drop = next_attention_dropout(p, Wh.device)
+        double_elu = convs[0].num_class is None and not drop_active
+        z = gat_aggregate(big, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=2 if double_elu else 1, keep=keep,
+                          dropout=drop, batch=M)                                                 # [N, M*H*Fp]
+        if not double_elu:
+            z = F.elu(F.dropout(z, p, training=training))  # NodeAttention.py:60-62, all metapaths at once
+        return z.view(n, M, H * Fp)
+
     def forward(self, gs, h):
         convs = list(self.gat_layers)
+        heads0 = list(convs[0].attentions)
+        if (getattr(self, "batched", True) and len(convs) > 1 and all(c.num_class is None for c in convs)
+                and len(heads0) * heads0[0].out_features <= 256 and h.dtype in (torch.float32, torch.bfloat16)):
+            return self.semantic_attention(self._batched(gs, h))
         if torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in self.parameters())):
             z = torch.stack([conv(h, g).flatten(1) for g, conv in zip(gs, convs)], dim=1)  # (N, M, H·F')
         else:

@@ -299,7 +299,15 @@ int gnn_gat_fused_fwd_f32(const int64_t* rowptr, const int32_t* col, const float
                           const float* edge_keep, float* out, int64_t ldo,
                           float* row_max, float* row_sum,
                           const int64_t* long_rows /*nullable*/, int64_t n_long, int64_t long_threshold,
+                          int64_t batch_nodes /*0 = one graph; see "batched graphs" below*/,
                           gnn_stream_t stream);
+/* Batched graphs (batch_nodes > 0): HAN runs M independent multi-head GATs over M metapath adjacencies of the SAME
+ * N nodes (HAN/models/HAN.py:16-23).  One launch serves all of them: the CSR passed in is the block diagonal of the
+ * M graphs (n = M*N rows, row r = graph r / N, node r % N, column ids offset by the graph's first row); s, t, the
+ * row statistics, d_s and d_t are [M*N, H] indexed by the batched row; graph m's feature columns are the block
+ * [m*H*Fp, (m+1)*H*Fp) of Wh / out / out_pre / d_out / d_Wh, whose leading dimensions are >= M*H*Fp — so `out` IS the
+ * [N, M, H*Fp] stack HANLayer builds with torch.stack (HAN.py:21).  col_mean is [M*H*Fp]. */
+
 /* Seeded attention dropout (GAT/models/layers.py:31, HAN/models/NodeAttention.py:31): instead of a materialised
  * [nnz,H] mask the kernels recompute, from (seed, forward edge slot, head), whether an attention weight is kept
  * (probability 1-p, kept weights scaled by 1/(1-p)) — identically in the forward and in both backward passes.
@@ -324,7 +332,7 @@ int gnn_gat_fused_fwd_train_f32(const int64_t* rowptr, const int32_t* col, const
                                 float* out_pre, float* out_act /*nullable when apply_elu == 0*/, int64_t ldo,
                                 float* row_max, float* row_sum,
                                 const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
-                                gnn_stream_t stream);
+                                int64_t batch_nodes, gnn_stream_t stream);
 int gnn_gat_fused_fwd_train_bf16(const int64_t* rowptr, const int32_t* col, const void* Wh, int64_t ldw,
                                  const float* s, const float* t, int64_t n, int64_t nnz, int32_t H, int32_t Fp,
                                  float alpha, int mode, int apply_elu, const float* col_mean,
@@ -332,7 +340,7 @@ int gnn_gat_fused_fwd_train_bf16(const int64_t* rowptr, const int32_t* col, cons
                                  void* out_pre, void* out_act, int64_t ldo,
                                  float* row_max, float* row_sum,
                                  const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
-                                 gnn_stream_t stream);
+                                 int64_t batch_nodes, gnn_stream_t stream);
 
 /* Backward.  out_pre is the pre-activation aggregate of the forward.  d_out is the gradient w.r.t. the
  * pre-activation aggregate when apply_elu == 0; with apply_elu > 0 it is the gradient w.r.t. the ACTIVATED
@@ -361,7 +369,7 @@ int gnn_gat_fused_bwd_f32(const int64_t* rowptr, const int32_t* col,
                           const int64_t* long_rows, int64_t n_long /*forward CSR*/,
                           const int64_t* long_rows_t, int64_t n_long_t /*transposed CSR*/, int64_t long_threshold,
                           int apply_elu, float* d_pre /*nullable when apply_elu == 0*/,
-                          const gnn_gat_dropout* dropout /*nullable*/,
+                          const gnn_gat_dropout* dropout /*nullable*/, int64_t batch_nodes,
                           gnn_stream_t stream);
 /* bf16-feature variants (north_star: "bf16-feature variants within 1e-2"): Wh, out, out_pre, d_out and
  * d_Wh are bf16; the scores s/t, the softmax statistics and every accumulation stay fp32.
@@ -372,7 +380,7 @@ int gnn_gat_fused_fwd_bf16(const int64_t* rowptr, const int32_t* col, const void
                            const float* edge_keep, void* out, int64_t ldo,
                            float* row_max, float* row_sum,
                            const int64_t* long_rows, int64_t n_long, int64_t long_threshold,
-                           gnn_stream_t stream);
+                           int64_t batch_nodes, gnn_stream_t stream);
 int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col,
                            const int64_t* rowptr_t, const int32_t* col_t, const int64_t* perm_t,
                            const void* Wh, int64_t ldw, const float* s, const float* t,
@@ -384,7 +392,7 @@ int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col,
                            int64_t nnz,
                            const int64_t* long_rows, int64_t n_long,
                            const int64_t* long_rows_t, int64_t n_long_t, int64_t long_threshold,
-                           int apply_elu, void* d_pre, const gnn_gat_dropout* dropout,
+                           int apply_elu, void* d_pre, const gnn_gat_dropout* dropout, int64_t batch_nodes,
                            gnn_stream_t stream);
 
 /* ---- synthetic graphs for the benchmark shapes ---------------- */

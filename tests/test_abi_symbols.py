@@ -58,5 +58,5 @@ def test_bad_arguments_return_status_not_abort(lib):
     rc = lib.gnn_gather_reduce_f32(None, 8, 4, None, 64, 4, 2, 8, 7, None, 8, None, None)
     assert rc == 1 and b"unknown reduce" in lib.gnn_last_error_string()
     rc = lib.gnn_gat_fused_fwd_f32(None, None, None, 8, None, None, 4, 0, 64, 8, 0.2, 0, 0, None, None, None, 8,
-                                   None, None, None, 0, 0, None)
+                                   None, None, None, 0, 0, 0, None)
     assert rc == 3  # more than 32 heads per call

@@ -391,6 +391,26 @@ def test_gather_reduce_backward_matches_autograd(lib):
         assert rel_err(ng.grad.cpu().numpy(), nc.grad.numpy()) < TOL32
 
 
+def test_gather_reduce_backward_bf16(lib):
+    """bf16-feature variant of the gather backward (refused): fp32 ordered accumulation, bf16 result,
+    within 1e-2 of float64 on the rounded inputs; both index layouts."""
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(400, 130, generator=g).to(DEV).bfloat16()
+    idx = torch.randint(0, 400, (64 * 6,), generator=g).to(DEV)
+    gy = torch.randn(64, 130, generator=g).to(DEV).bfloat16()
+    t = table.clone().requires_grad_(True)
+    out = Fn.gather_reduce(t, idx, 64, 6, "mean")
+    out.backward(gy)
+    assert t.grad.dtype == torch.bfloat16
+    ref = torch.zeros(400, 130, dtype=torch.float64)
+    ref.index_add_(0, idx.cpu(), (gy.double().cpu() / 6).repeat_interleave(6, 0))
+    assert rel_err(t.grad.float().cpu().numpy(), ref.numpy()) < TOLBF
+    pre = table[:64 * 6].clone().requires_grad_(True)  # the reference call surface: pre-gathered [n_src*fanout, F]
+    Fn.gather_reduce(pre, None, 64, 6, "sum").backward(gy)
+    assert pre.grad.dtype == torch.bfloat16
+    assert rel_err(pre.grad.float().cpu().numpy(), gy.double().cpu().repeat_interleave(6, 0).numpy()) < TOLBF
+
+
 def test_graphsage_model_vs_reference_golden(lib):
     g = load_golden("sage_small.npz")
     table = np.random.default_rng(int(g["table_seed"])).standard_normal((500, 602), dtype=np.float32)
@@ -874,6 +894,48 @@ def test_han_acm_size_vs_reference_golden(lib):
     assert abs(loss.item() - float(g["loss"])) < 1e-5
     loss.backward()
     check_grads(model, g, tol=2e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32])
+def test_han_batched_metapaths_equal_per_metapath_launches(lib, dtype):
+    """HANLayer's one block-diagonal attention launch over all M metapaths (batch=M) against M separate GATConv
+    launches (HAN.py:16-21): forward and every parameter / input gradient, ragged metapath densities incl. a
+    metapath with isolated nodes."""
+    n, F_in, M = 700, 48, 3
+    masks = [S.symmetric_mask(n, t, seed=31 + i) for i, t in enumerate((500, 9000, 120000))]
+    masks[0][5:40, :] = 0.0
+    masks[0][:, 5:40] = 0.0  # isolated nodes in metapath 0: rows without neighbours -> uniform-softmax corner
+    gs = [cuda(m) for m in masks]
+    X = cuda(np.random.default_rng(3).standard_normal((n, F_in), dtype=np.float32))
+    torch.manual_seed(4)
+    layer = layers.HANLayer(M, F_in, 8, 8, 0.0).to(DEV)
+    res = {}
+    for batched in (True, False):
+        layer.batched = batched
+        layer.zero_grad()
+        x = X.clone().requires_grad_(True)
+        out = layer(gs, x)
+        out.square().sum().backward()
+        res[batched] = (out.detach().cpu().numpy(), x.grad.cpu().numpy(),
+                        {k: p.grad.cpu().numpy().copy() for k, p in layer.named_parameters()})
+    assert rel_err(res[True][0], res[False][0]) < TOL32
+    assert rel_err(res[True][1], res[False][1]) < 2e-5
+    for k in res[True][2]:
+        assert rel_err(res[True][2][k], res[False][2][k]) < 2e-5, k
+    layer.eval()
+    with torch.no_grad():
+        layer.batched = True
+        a = layer(gs, X)
+        layer.batched = False
+        b = layer(gs, X)
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < TOL32
+    # training with dropout through the batched launch: finite, a fresh mask per call, gradients flow to every head
+    layer_d = layers.HANLayer(M, F_in, 8, 8, 0.5).to(DEV)
+    layer_d.train()
+    o1, o2 = layer_d(gs, X), layer_d(gs, X)
+    assert torch.isfinite(o1).all() and torch.isfinite(o2).all() and not torch.equal(o1, o2)
+    o1.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in layer_d.parameters())
 
 
 def test_gat_cora_train_mode_vs_reference_golden(lib, monkeypatch):

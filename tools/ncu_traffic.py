@@ -40,9 +40,17 @@ def main():
     for path in sys.argv[1:]:
         for rec in parse(path):
             k = rec["kernel"]
-            key = ("sage_multi" if "sage_tma_kernel" in k else "gat_fwd" if "gat_fwd_kernel" in k else
-                   "gat_bwd_rows" if ("gat_bwd2_kernel" in k and "false" in k.split("gat_bwd2_kernel")[1][:60].replace("(bool)0", "false")) else
-                   "gat_bwd_cols" if "gat_bwd2_kernel" in k else "spmm_rbs" if "spmm_rbs_kernel" in k else None)
+            key = None
+            if "sage_tma_kernel" in k:
+                key = "sage_multi"
+            elif "gat_fwd_kernel" in k:
+                key = "gat_fwd_bf16" if "bfloat16" in k else "gat_fwd"
+            elif "gat_bwd2_kernel" in k:
+                targs = k.split("gat_bwd2_kernel<")[1].split(">")[0].replace("(bool)", "").replace("(int)", "").split(",")
+                tr = targs[4].strip() in ("1", "true")
+                key = "gat_bwd_pass2_transposed" if tr else "gat_bwd_pass1_rows"
+            elif "spmm_rbs_kernel" in k:
+                key = "spmm_rbs"
             if key is None:
                 continue
             rec["dram_bytes"] = rec.get("dram_read", 0.0) + rec.get("dram_write", 0.0)

@@ -106,13 +106,15 @@ def main():
     for transport in (a.transports if world > 1 else ["none"]):
         for cfg in configs:
             parts = cfg.split(":")
-            K, c0 = int(parts[0]), (None if parts[1] == "auto" else int(parts[1]))
+            K = None if parts[0] == "auto" else int(parts[0])  # auto: (K, c0) by the cross-rank byte model
+            c0 = None if parts[1] == "auto" else int(parts[1])
             mover, ctas, warps = parts[2], int(parts[3]), int(parts[4])
             dedicated = int(parts[5]) if len(parts) > 5 else 0
             fused = (parts[6] != "sep") if len(parts) > 6 else True
             inter = int(parts[7]) if len(parts) > 7 else 0
             if transport == "nccl":
                 K, c0 = 1, (1 if c0 is None else min(c0, 1))
+            want_K = K
             key = (K, c0)
             if key not in plans:
                 plans.clear()
@@ -134,14 +136,16 @@ def main():
             else:
                 allstats = [stats]
             line = {"bench": "spmm_partitioned", "world": world, "n": a.n, "nnz": nnz_total, "F": a.F, "dtype": a.dtype,
-                    "transport": transport, "waves": K, "two_pass_chunks": [int(s[3]) for s in allstats],
+                    "transport": transport, "waves": plan.waves, "waves_requested": "auto" if want_K is None else want_K, "two_pass_chunks": [int(s[3]) for s in allstats],
                     "mover": mover, "fused_signal": bool(op._wave_table is not None) if world > 1 else None, "interleave": inter, "mover_ctas": ctas, "mover_warps": warps, "dedicated_sms": dedicated,
                     "ms": ms, "edges_per_s": nnz_total / ms * 1e3, "max_rel_err_sampled_rows": err, "ok": err < tol,
                     "p_local": a.p_local, "window": a.window,
                     "halo_gb_recv_max": max(int(s[0]) for s in allstats) * a.F * X.element_size() / 1e9,
                     "send_gb_max": max(int(s[1]) for s in allstats) * a.F * X.element_size() / 1e9,
                     "interior_row_frac": sum(int(s[2]) for s in allstats) / a.n,
-                    "model_ms": {k: round(v, 2) for k, v in plan.model.items() if k.startswith("c0=") or k == "exchange_ms"}}
+                    "mover_geometry": [op.mover_ctas, op.mover_warps],
+                    "model_ms": {k: (round(v, 2) if isinstance(v, float) else v) for k, v in plan.model.items()
+                                 if k.startswith("c0=") or k in ("exchange_ms", "auto_schedule_ms_sum_over_ranks")}}
             if a.backward:
                 dY = S.hashed_feature_block(lo, hi, a.F, dev, dtype, salt=977)
                 dX = torch.empty_like(Y)
