@@ -757,7 +757,7 @@ def run_partitioned_spmm(rank, world, dev, steps=5, graphs=("random", "locality"
                "halo_rows_max": int(halo_max), "halo_gb_received_max": halo_max * F * 4 / 1e9,
                "schedule": {"waves": plan.waves, "two_pass_chunks": plan.two_pass_chunks,
                             "model_ms": {k: round(v, 2) for k, v in plan.model.items()
-                                         if k.startswith("c0=") or k == "exchange_ms"}} if world > 1 else None,
+                                         if k.startswith("c0=") or k in ("exchange_ms", "compute_ms")}} if world > 1 else None,
                "transport": ("gnn_halo_push_waves: single-launch TMA mover (%d CTAs x %d warps), arrival flags raised "
                              "per wave from inside the kernel, overlapped with the local-column SpMM"
                              % (op.mover_ctas, op.mover_warps)) if world > 1 else "none (single GPU)"}

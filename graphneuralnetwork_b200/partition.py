@@ -52,7 +52,12 @@ NVLINK_BPS_BY_WORLD = {2: 640e9, 3: 600e9, 4: 560e9}
 NVLINK_BPS_LARGE = 480e9
 HBM_BPS = 5.6e12
 WAVE_OVERHEAD_S = 0.3e-3
+SPMM_EDGES_PER_S = 11.9e9  # F=128 rows, one B200 (1.61 G edges in 135.3 ms)
 AUTO_MAX_WAVES = 8
+# modelled exchange time / modelled SpMM time above which the step is exchange-bound: the mover then runs on 32 CTAs
+# (8 GPUs, random graph, 31.9 GB received per rank: 59.0 ms with 32 mover CTAs, 73.0 with 64, 81.0 with 148 — more
+# writers only congest the receivers' ingress; profiles/r02_dist_8gpu.jsonl)
+EXCHANGE_BOUND_RATIO = 2.5
 
 
 def nvlink_bps(world: int) -> float:
@@ -206,6 +211,11 @@ def choose_two_pass_chunks(K: int, F: int, elem: int, nnz_p1_base: int, rows_int
         if best is None or t < best[1] - 1e-9:
             best = (c0, t)
     report["exchange_ms"] = t_x * 1e3
+    nnz_all = nnz_p1_base + sum(m_nnz_loc) + sum(m_nnz_rem)
+    # the whole block as one single-pass SpMM: gather-model bytes at the HBM rate, never faster than the kernel's
+    # edge rate (bf16 rows halve the bytes, not the time: 137.9 ms vs 135.3 ms on one GPU)
+    report["compute_ms"] = max((nnz_all * edge_b + (rows_interior + sum(m_rows)) * row_b) / HBM_BPS,
+                               nnz_all / SPMM_EDGES_PER_S) * 1e3
     return best[0], report
 
 
@@ -377,6 +387,13 @@ def build_halo_plan(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch
     if auto_report is not None:
         report["auto_schedule_ms_sum_over_ranks"] = auto_report
     c0 = c0_model if two_pass_chunks is None else max(0, min(int(two_pass_chunks), K))
+    # exchange-bound steps (the modelled exchange outlasts the whole SpMM several times over): nothing is left to hide
+    # behind the exchange, so every chunk is single-pass — the consumers park on their wave's flag and Y is written
+    # once.  8 GPUs, random graph: c0 = 0 / 4 / 8 -> 60.2 / 71.4 / 65.6 ms at 32 mover CTAs (r02, r2i_rand).
+    exchange_bound = world > 1 and report["exchange_ms"] >= EXCHANGE_BOUND_RATIO * max(report["compute_ms"], 1e-9)
+    report["exchange_bound"] = bool(exchange_bound)
+    if exchange_bound and (two_pass_chunks is None or auto_report is not None):
+        c0 = 0
     plan.two_pass_chunks = c0
     plan.model = dict(report, chosen=c0, model_choice=c0_model, rows_interior=rows_interior,
                       rows_mixed=sum(m_rows), nnz_interior=nnz_interior)
@@ -524,7 +541,9 @@ class PartitionedSpmm:
             raise ValueError(f"unknown transport {transport!r}")
         self.mover = {"auto": 0, "vector": 1, "tma": 2}[mover]
         if int(mover_ctas) < 0:
-            mover_ctas = 32 if plan.two_pass_chunks == 0 else 48
+            model = getattr(plan, "model", None) or {}
+            exchange_bound = model.get("exchange_ms", 0.0) >= EXCHANGE_BOUND_RATIO * max(model.get("compute_ms", 0.0), 1e-9)
+            mover_ctas = 32 if (plan.two_pass_chunks == 0 or exchange_bound) else 48
         if int(mover_warps) < 0:
             mover_warps = 4
         self.mover_ctas, self.mover_warps, self.dedicated = int(mover_ctas), int(mover_warps), int(dedicated_sms)
