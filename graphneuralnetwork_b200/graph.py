@@ -89,8 +89,6 @@ class CSRGraph:
                                              ws_bytes, _stream_ptr()), "gnn_csr_transpose")
             self._t = CSRGraph(rowptr_t, col_t, val_t, self.n_cols, self.n_rows)
             self._t._t = self
-            if getattr(self, "_gat_long_thr", None):
-                self._t._gat_long_thr = self._gat_long_thr
             self._perm_t = perm_t
         return self._t
 
@@ -147,7 +145,7 @@ class CSRGraph:
         """(long_rows int64, threshold): rows the attention kernels hand to a whole CTA (host-side plan,
         cached)."""
         if getattr(self, "_gat_long", None) is None:
-            thr = getattr(self, "_gat_long_thr", None) or _lib.get_tuning("gat.long_row")
+            thr = _lib.get_tuning("gat.long_row")
             deg = self.rowptr[1:] - self.rowptr[:-1]
             self._gat_long = (torch.nonzero(deg > thr).flatten().contiguous(), thr)
         return self._gat_long
@@ -185,11 +183,6 @@ class CSRGraph:
             off += g.nnz
         parts.append(torch.tensor([off], dtype=torch.int64, device=graphs[0].device))
         big = CSRGraph(torch.cat(parts), torch.cat(cols).to(torch.int32), None, len(graphs) * n, len(graphs) * n)
-        # a dense member graph (one whose rows would each get a CTA on its own: gat.coop_min_avg_deg) keeps CTA rows
-        # inside the batch even when the batch's average degree falls under that bar: its rows join the long-row list
-        coop = _lib.get_tuning("gat.coop_min_avg_deg")
-        if big.nnz // max(big.n_rows, 1) < coop and any(g.nnz // max(g.n_rows, 1) >= coop for g in graphs):
-            big._gat_long_thr = coop
         if len(CSRGraph._block_cache) >= 8:
             CSRGraph._block_cache.pop(next(iter(CSRGraph._block_cache)))
         CSRGraph._block_cache[key] = (graphs, big)
