@@ -1,3 +1,6 @@
+"""Diagnostic (GPU): the batched block-diagonal HAN attention launch against M separate launches on the ACM-sized
+golden's parameters — out / dWh / ds / dt of both, and both against a float64 dense autograd of metapath 1.
+    gpurun -- python tools/diag_han_batched.py"""
 import sys, numpy as np, torch
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from graphneuralnetwork_b200 import layers, synthetic as S, _lib

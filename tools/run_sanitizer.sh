@@ -5,6 +5,9 @@
 #     gpurun --timeout 1500 -- 'bash tools/run_sanitizer.sh racecheck'
 # The plain run goes first; the sanitizer only runs if it exits 0.  Output: gpurun_out/sanitizer_<tool>.log
 # (copy the summary lines into profiles/ when quoting them).
+# NOTE (r02): compute-sanitizer is CLOSED on this pool (the wrapper refuses it: runs under it have left GPUs needing a
+# reset) — the script is kept for a pool where it is open.  In-tree substitutes: ABI-side index validation, the
+# out-of-range / ragged / empty-row GPU tests and tests/test_gpu_properties.py.
 set -x
 TOOL=${1:-memcheck}
 O=gpurun_out
