@@ -41,6 +41,11 @@ SIGNATURES = {
     "gnn_spmm_csr_planned_bf16": (cint, [ptr, ptr, ptr, ptr, ptr, i64, i64, i32, i64, i64, ptr, i64, i64, ptr, i64, i32,
                                          cint, i32, ptr, i32, ptr, size_t, ptr]),
     "gnn_sddmm_coo_f32": (cint, [ptr, ptr, cint, i64, ptr, i64, ptr, i64, i32, ptr, ptr]),
+    "gnn_semantic_workspace_size": (i64, [i32]),
+    "gnn_semantic_scores_f32": (cint, [ptr, i64, ptr, ptr, i64, i32, i32, ptr, ptr, ptr, i64, ptr]),
+    "gnn_semantic_combine_f32": (cint, [ptr, ptr, i64, i32, i32, ptr, ptr]),
+    "gnn_semantic_combine_bwd_f32": (cint, [ptr, ptr, ptr, i64, i32, i32, ptr, ptr, ptr, i64, ptr]),
+    "gnn_semantic_scores_bwd_f32": (cint, [ptr, i64, ptr, ptr, ptr, i64, i32, i32, ptr, i64, ptr, ptr, ptr, i64, ptr]),
     "gnn_gather_reduce_f32": (cint, [ptr, i64, i64, ptr, cint, i64, i32, i32, cint, ptr, i64, ptr, ptr]),
     "gnn_gather_reduce_bf16": (cint, [ptr, i64, i64, ptr, cint, i64, i32, i32, cint, ptr, i64, ptr, ptr]),
     "gnn_gather_reduce_multi_f32": (cint, [ptr, i64, i64, i32, cint, i32, ptr, cint, ptr, ptr, ptr, ptr, ptr]),

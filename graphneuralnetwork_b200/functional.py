@@ -565,19 +565,6 @@ def attention_keep_mask_from_seed(g: CSRGraph, H: int, drop: AttentionDropout) -
     return keep.view(g.nnz, H)
 
 
-def _gat_groups(H: int, Fp: int):
-    """Column groups one kernel call can take (H_g*Fp_g <= 256, H_g <= 32): whole heads when a head fits,
-    else column tiles of ONE head.  Yields (h0, h1, f0, f1): heads [h0,h1), columns [f0,f1) of each."""
-    if Fp <= 256:
-        per = max(1, min(32, 256 // Fp))
-        for h0 in range(0, H, per):
-            yield h0, min(H, h0 + per), 0, Fp
-    else:
-        for h in range(H):
-            for f0 in range(0, Fp, 256):
-                yield h, h + 1, f0, min(Fp, f0 + 256)
-
-
 def gat_fwd_raw(g: CSRGraph, Wh, s, t, H, Fp, alpha, mode=_lib.GAT_SOFTMAX, elu=0, keep=None, save_stats=False,
                 out=None, dropout: Optional[AttentionDropout] = None, out_act: Optional[torch.Tensor] = None,
                 batch: int = 1):
@@ -772,3 +759,86 @@ def attention_keep_mask(g: CSRGraph, H: int, p: float, generator: Optional[torch
     keep = torch.empty((g.nnz, H), dtype=torch.float32, device=g.device)
     keep.bernoulli_(1.0 - p, generator=generator).div_(1.0 - p)
     return keep
+
+
+# ---- HAN semantic attention (HAN/models/SemanticAttention.py:15-20) --------------------------------------------
+_semantic_ws = {}
+
+
+def _semantic_workspace(K: int, device) -> torch.Tensor:
+    """Zeroed once per (device, stream, K): the kernels' ticket counter must start at zero and every call leaves it
+    zero; one workspace per stream keeps concurrent streams apart, and it persists for CUDA-graph replays."""
+    key = (torch.device(device), torch.cuda.current_stream(device).cuda_stream, int(K))
+    ws = _semantic_ws.get(key)
+    if ws is None:
+        nbytes = int(_lib.load().gnn_semantic_workspace_size(int(K)))
+        if nbytes < 0:
+            raise _lib.GnnError(f"semantic_attention: hidden width {K} unsupported")
+        ws = _semantic_ws[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    return ws
+
+
+SEMANTIC_MAX_M, SEMANTIC_MAX_K = 32, 256
+
+
+class _SemanticFn(torch.autograd.Function):
+    """out = sum_m softmax_M(mean_N(q . tanh(z W1^T + b)))_m z[:, m, :]: one GEMM + two launches forward, two
+    launches + two GEMMs backward (csrc/semantic.cu)."""
+
+    @staticmethod
+    def forward(ctx, z, W1, b1, q):
+        lib = _lib.load()
+        N, M, D = z.shape
+        K = W1.shape[0]
+        z = z.contiguous()
+        W1c, qv = W1.contiguous(), q.reshape(-1).contiguous()
+        b1c = None if b1 is None else b1.contiguous()
+        P = torch.mm(z.view(N * M, D), W1c.t())                      # [N*M, K], the library GEMM
+        ws = _semantic_workspace(K, z.device)
+        scores = torch.empty(M, dtype=torch.float32, device=z.device)
+        beta = torch.empty(M, dtype=torch.float32, device=z.device)
+        out = torch.empty((N, D), dtype=torch.float32, device=z.device)
+        st = _stream_ptr()
+        _lib.check(lib.gnn_semantic_scores_f32(_p(P), P.stride(0), _p(b1c), _p(qv), N, M, K, _p(scores), _p(beta), _p(ws),
+                                               ws.numel(), st), "gnn_semantic_scores_f32")
+        _lib.check(lib.gnn_semantic_combine_f32(_p(beta), _p(z), N, M, D, _p(out), st), "gnn_semantic_combine_f32")
+        ctx.save_for_backward(z, W1c, b1c if b1c is not None else z.new_empty(0), qv, P, beta)
+        ctx.has_bias, ctx.q_shape = b1 is not None, tuple(q.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        z, W1, b1, qv, P, beta = ctx.saved_tensors
+        N, M, D = z.shape
+        K = W1.shape[0]
+        d_out = d_out.contiguous()
+        ws = _semantic_workspace(K, z.device)
+        dz = torch.empty_like(z)
+        dsn = torch.empty(M, dtype=torch.float32, device=z.device)
+        dP = torch.empty_like(P)
+        dq = torch.empty(K, dtype=torch.float32, device=z.device)
+        db = torch.empty(K, dtype=torch.float32, device=z.device) if ctx.has_bias else None
+        st = _stream_ptr()
+        _lib.check(lib.gnn_semantic_combine_bwd_f32(_p(d_out), _p(z), _p(beta), N, M, D, _p(dz), _p(dsn), _p(ws),
+                                                    ws.numel(), st), "gnn_semantic_combine_bwd_f32")
+        _lib.check(lib.gnn_semantic_scores_bwd_f32(_p(P), P.stride(0), _p(b1) if ctx.has_bias else None, _p(qv), _p(dsn),
+                                                   N, M, K, _p(dP), dP.stride(0), _p(dq), _p(db), _p(ws), ws.numel(), st),
+                   "gnn_semantic_scores_bwd_f32")
+        z2 = z.view(N * M, D)
+        dW1 = torch.mm(dP.t(), z2) if ctx.needs_input_grad[1] else None                 # [K, D]
+        if ctx.needs_input_grad[0]:
+            dz = torch.addmm(dz.view(N * M, D), dP, W1).view(N, M, D)                    # direct term + dP·W1
+        else:
+            dz = None
+        return dz, dW1, db, dq.view(ctx.q_shape)
+
+
+def semantic_attention(z: torch.Tensor, W1: torch.Tensor, b1: Optional[torch.Tensor], q: torch.Tensor) -> torch.Tensor:
+    """HAN semantic attention over z [N, M, D] with project = Linear(D,K; W1,b1) -> tanh -> Linear(K,1; q, no bias)
+    (SemanticAttention.py:8-20): returns [N, D].  fp32, M <= 32, K <= 256."""
+    _require_cuda(z, W1, q)
+    if z.dtype != torch.float32 or z.dim() != 3 or z.shape[1] > SEMANTIC_MAX_M or W1.shape[0] > SEMANTIC_MAX_K or \
+            W1.shape[1] != z.shape[2] or q.numel() != W1.shape[0] or z.shape[0] == 0:
+        raise _lib.GnnError(f"semantic_attention: unsupported shapes z {tuple(z.shape)} W1 {tuple(W1.shape)} q {tuple(q.shape)}")
+    return _SemanticFn.apply(z, W1, b1, q)

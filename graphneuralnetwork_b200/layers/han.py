@@ -12,16 +12,18 @@ Re-designed for the device:
     fused into the same kernel's epilogue (double ELU) whenever no dropout sits between them;
   * without autograd the M metapath kernels write straight into their `[:, m, :]` slice of the
     `[N, M, H·F']` semantic stack — `torch.stack` (HAN.py:21) never copies;
-  * semantic attention (SemanticAttention.py:15-20) reduces the `[N·M, ·]` projection to M scores
-    and applies `softmax_M` as one `[M] x [N, M, D]` contraction instead of broadcasting β to
-    `[N, M, 1]` and materialising `β·z`.
+  * semantic attention (SemanticAttention.py:15-20) keeps only its `[N·M, D]·[D, K]` product as a GEMM; tanh, the
+    K→1 projection, the mean over nodes, `softmax_M` and the weighted sum are two launches forward and two backward
+    (`functional.semantic_attention`), nothing of `[N, M, ·]` shape besides P is materialised (bf16 / CPU tensors
+    take the plain torch formula).
 """
 import torch
 from torch import nn
 import torch.nn.functional as F
 
 from .. import _lib
-from ..functional import gat_aggregate, next_attention_dropout
+from ..functional import (SEMANTIC_MAX_K, SEMANTIC_MAX_M, gat_aggregate, next_attention_dropout,
+                          semantic_attention)
 from ..graph import CSRGraph, adj_cache
 from .gat import GraphAttentionLayer, _fused_heads
 from . import gat as _gat
@@ -79,6 +81,11 @@ class SemanticAttention(nn.Module):
 
     def forward(self, z):
         n, m, d = z.shape
+        lin, proj = self.project[0], self.project[2]
+        if (getattr(self, "fused", True) and z.is_cuda and z.dtype == torch.float32 and 0 < m <= SEMANTIC_MAX_M and n > 0
+                and lin.out_features <= SEMANTIC_MAX_K and lin.weight.dtype == torch.float32):
+            # one GEMM + two launches (tanh . q, mean over nodes, softmax over M, weighted sum: csrc/semantic.cu)
+            return semantic_attention(z, lin.weight, lin.bias, proj.weight)
         scores = self.project(z.reshape(n * m, d)).view(n, m).mean(dim=0)  # [M]
         beta = torch.softmax(scores, dim=0)
         return torch.einsum('m,nmd->nd', beta, z)

@@ -395,6 +395,35 @@ int gnn_gat_fused_bwd_bf16(const int64_t* rowptr, const int32_t* col,
                            int apply_elu, void* d_pre, const gnn_gat_dropout* dropout, int64_t batch_nodes,
                            gnn_stream_t stream);
 
+/* ---- HAN semantic attention: everything around its one GEMM -------------------- */
+/* HAN/models/SemanticAttention.py:15-20:
+ *     w = project(z).mean(0); beta = softmax(w, dim=0); out = (beta.expand(N,M,1) * z).sum(1)
+ * with project = Linear(D,K) -> Tanh -> Linear(K,1,bias=False) (SemanticAttention.py:8-12).
+ * The caller keeps P = z·W1^T [N*M, K] (row n*M+m) as a library GEMM; these four launches replace the tanh, the
+ * K->1 projection, the mean over nodes, the softmax over the M metapaths, the weighted sum and all their
+ * gradients.  z and dz are contiguous [N, M, D]; M <= 32, K <= 256.  Ordered sums (deterministic).
+ * workspace: gnn_semantic_workspace_size(K) bytes, 16-byte aligned, ZERO before its first use (its first word is a
+ * ticket counter every call leaves at zero again); calls sharing a workspace must be stream-ordered. */
+int64_t gnn_semantic_workspace_size(int32_t K);
+/* scores[m] = 1/N sum_n sum_k q[k] tanh(P[n*M+m, k] + bias[k]) (bias nullable); beta = softmax_M(scores) */
+int gnn_semantic_scores_f32(const float* P, int64_t ldp, const float* bias /*[K]*/, const float* q /*[K]*/,
+                            int64_t N, int32_t M, int32_t K, float* scores /*[M]*/, float* beta /*[M]*/,
+                            void* workspace, int64_t workspace_bytes, gnn_stream_t stream);
+/* out[n, :] = sum_m beta[m] z[n, m, :] */
+int gnn_semantic_combine_f32(const float* beta, const float* z, int64_t N, int32_t M, int32_t D,
+                             float* out /*[N, D]*/, gnn_stream_t stream);
+/* dz[n, m, :] = beta[m] d_out[n, :] (the direct term; the caller adds dP·W1);
+ * d_scores_over_n[m] = beta[m] (dbeta[m] - sum_j beta[j] dbeta[j]) / N with dbeta[m] = sum_n <d_out[n], z[n, m]> */
+int gnn_semantic_combine_bwd_f32(const float* d_out, const float* z, const float* beta, int64_t N, int32_t M,
+                                 int32_t D, float* dz, float* d_scores_over_n /*[M]*/, void* workspace,
+                                 int64_t workspace_bytes, gnn_stream_t stream);
+/* dP[r, k] = d_scores_over_n[r % M] q[k] (1 - tanh^2(P[r, k] + bias[k])); dq[k] = sum_r d_scores_over_n[r % M] tanh(.);
+ * dbias[k] = sum_r dP[r, k] (dbias nullable) */
+int gnn_semantic_scores_bwd_f32(const float* P, int64_t ldp, const float* bias, const float* q,
+                                const float* d_scores_over_n, int64_t N, int32_t M, int32_t K,
+                                float* dP, int64_t lddp, float* dq /*[K]*/, float* dbias /*[K]*/,
+                                void* workspace, int64_t workspace_bytes, gnn_stream_t stream);
+
 /* ---- synthetic graphs for the benchmark shapes ---------------- */
 /* Power-law CSR generated on the device, row by row, from a counter-based hash of
  * (seed,row,k): degrees ~ truncated Pareto with the given mean, targets skewed to

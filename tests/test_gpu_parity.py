@@ -938,6 +938,68 @@ def test_han_batched_metapaths_equal_per_metapath_launches(lib, dtype):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in layer_d.parameters())
 
 
+@pytest.mark.parametrize("n,m,d,k,bias", [(3025, 3, 64, 128, True), (77, 5, 20, 100, True), (1, 1, 8, 16, False),
+                                          (513, 32, 33, 256, True)])
+def test_semantic_attention_fused_vs_reference_formula(lib, n, m, d, k, bias):
+    """csrc/semantic.cu against the reference's own lines (HAN/models/SemanticAttention.py:15-20) in float64:
+    forward and the gradients of z, W1, b1 and q; ragged sizes (K not dividing the CTA, one node, 32 metapaths)."""
+    g = torch.Generator().manual_seed(n + m)
+    z = torch.randn(n, m, d, generator=g)
+    W1 = torch.randn(k, d, generator=g) * 0.3
+    b1 = torch.randn(k, generator=g) * 0.1 if bias else None
+    q = torch.randn(1, k, generator=g) * 0.5
+    gy = torch.randn(n, d, generator=g)
+
+    def reference(z, W1, b1, q):  # the reference's lines, verbatim semantics
+        w = torch.tanh(z @ W1.t() + (b1 if b1 is not None else 0)) @ q.t()     # project(z): [N, M, 1]
+        beta = torch.softmax(w.mean(0), dim=0)                                 # [M, 1]
+        beta = beta.expand((z.shape[0],) + beta.shape)                         # [N, M, 1]
+        return (beta * z).sum(1)
+
+    ref_in = [t.double().requires_grad_(True) if t is not None else None for t in (z, W1, b1, q)]
+    want = reference(*ref_in)
+    want.backward(gy.double())
+    got_in = [t.to(DEV).requires_grad_(True) if t is not None else None for t in (z, W1, b1, q)]
+    got = Fn.semantic_attention(*got_in)
+    got.backward(gy.to(DEV))
+    assert rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL32
+    for name, a, b in zip(("z", "W1", "b1", "q"), got_in, ref_in):
+        if a is not None:
+            assert a.grad.shape == b.grad.shape
+            assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) < 2e-5, name
+    # deterministic (ordered sums, no float atomics) and the workspace's ticket counter is left at zero
+    again = Fn.semantic_attention(*[t.detach() if t is not None else None for t in got_in])
+    assert torch.equal(again, got.detach())
+
+
+def test_semantic_attention_module_fused_and_torch_paths(lib):
+    """layers.SemanticAttention: the fused path (default) and the plain torch formula (`fused = False`) against the
+    same module in float64 on the CPU."""
+    import copy
+    torch.manual_seed(0)
+    sa = layers.SemanticAttention(64)
+    z = torch.randn(500, 3, 64)
+    ref = copy.deepcopy(sa).double()
+    zr = z.double().requires_grad_(True)
+    want = ref(zr)                      # CPU tensors take the torch formula
+    want.square().sum().backward()
+    want_all = [want.detach(), zr.grad] + [p.grad for p in ref.parameters()]
+    sa = sa.to(DEV)
+    for fused in (True, False):
+        sa.fused = fused
+        sa.zero_grad()
+        zz = z.to(DEV).requires_grad_(True)
+        out = sa(zz)
+        out.square().sum().backward()
+        got_all = [out.detach(), zz.grad] + [p.grad for p in sa.parameters()]
+        # the projection's gradients all carry the factor beta_m (dbeta_m - sum_j beta_j dbeta_j): with this loss the
+        # dbeta_m are sums of N*D positive terms that nearly cancel in the bracket, so fp32 (either path) keeps
+        # 3-4 digits of them; out and dz are not affected.  The parametrised test above pins every gradient to 2e-5.
+        for i, (a, b) in enumerate(zip(got_all, want_all)):
+            err = rel_err(a.cpu().numpy(), b.numpy())
+            assert a.shape == b.shape and err < (2e-5 if i < 2 else 2e-3), (fused, i, err)
+
+
 def test_gat_cora_train_mode_vs_reference_golden(lib, monkeypatch):
     """Cora-sized GAT in TRAIN mode with dropout 0.6 (GAT/run.py:9), forward + every gradient: the reference's
     dropout masks (features: GAT.py:15,17; attention matrices: layers.py:31) are replayed from the fixture's seeds —
