@@ -146,7 +146,7 @@ class HANLayer(nn.Module):
         if torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in self.parameters())):
             z = torch.stack([conv(h, g).flatten(1) for g, conv in zip(gs, convs)], dim=1)  # (N, M, H·F')
         else:
-            z = h.new_empty(h.shape[0], len(convs), self._width, dtype=torch.float32)
+            z = h.new_empty(h.shape[0], len(convs), self._width)  # the kernels write the features' dtype (fp32 / bf16)
             for m, (g, conv) in enumerate(zip(gs, convs)):
                 conv(h, g, out=z[:, m, :])
         return self.semantic_attention(z)

@@ -896,7 +896,7 @@ def test_han_acm_size_vs_reference_golden(lib):
     check_grads(model, g, tol=2e-5)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_han_batched_metapaths_equal_per_metapath_launches(lib, dtype):
     """HANLayer's one block-diagonal attention launch over all M metapaths (batch=M) against M separate GATConv
     launches (HAN.py:16-21): forward and every parameter / input gradient, ragged metapath densities incl. a
@@ -906,9 +906,10 @@ def test_han_batched_metapaths_equal_per_metapath_launches(lib, dtype):
     masks[0][5:40, :] = 0.0
     masks[0][:, 5:40] = 0.0  # isolated nodes in metapath 0: rows without neighbours -> uniform-softmax corner
     gs = [cuda(m) for m in masks]
-    X = cuda(np.random.default_rng(3).standard_normal((n, F_in), dtype=np.float32))
+    X = cuda(np.random.default_rng(3).standard_normal((n, F_in), dtype=np.float32)).to(dtype)
     torch.manual_seed(4)
-    layer = layers.HANLayer(M, F_in, 8, 8, 0.0).to(DEV)
+    layer = layers.HANLayer(M, F_in, 8, 8, 0.0).to(DEV).to(dtype)   # bf16: bf16-feature kernels, torch semantic path
+    tol_out, tol_grad = (TOL32, 2e-5) if dtype == torch.float32 else (TOLBF, 3e-2)
     res = {}
     for batched in (True, False):
         layer.batched = batched
@@ -916,21 +917,21 @@ def test_han_batched_metapaths_equal_per_metapath_launches(lib, dtype):
         x = X.clone().requires_grad_(True)
         out = layer(gs, x)
         out.square().sum().backward()
-        res[batched] = (out.detach().cpu().numpy(), x.grad.cpu().numpy(),
-                        {k: p.grad.cpu().numpy().copy() for k, p in layer.named_parameters()})
-    assert rel_err(res[True][0], res[False][0]) < TOL32
-    assert rel_err(res[True][1], res[False][1]) < 2e-5
+        res[batched] = (out.detach().float().cpu().numpy(), x.grad.float().cpu().numpy(),
+                        {k: p.grad.float().cpu().numpy().copy() for k, p in layer.named_parameters()})
+    assert rel_err(res[True][0], res[False][0]) < tol_out
+    assert rel_err(res[True][1], res[False][1]) < tol_grad
     for k in res[True][2]:
-        assert rel_err(res[True][2][k], res[False][2][k]) < 2e-5, k
+        assert rel_err(res[True][2][k], res[False][2][k]) < tol_grad, k
     layer.eval()
     with torch.no_grad():
         layer.batched = True
         a = layer(gs, X)
         layer.batched = False
         b = layer(gs, X)
-    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < TOL32
+    assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < tol_out
     # training with dropout through the batched launch: finite, a fresh mask per call, gradients flow to every head
-    layer_d = layers.HANLayer(M, F_in, 8, 8, 0.5).to(DEV)
+    layer_d = layers.HANLayer(M, F_in, 8, 8, 0.5).to(DEV).to(dtype)
     layer_d.train()
     o1, o2 = layer_d(gs, X), layer_d(gs, X)
     assert torch.isfinite(o1).all() and torch.isfinite(o2).all() and not torch.equal(o1, o2)

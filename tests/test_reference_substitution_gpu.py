@@ -109,3 +109,27 @@ def test_reference_han_model_with_dropin_gatconv(lib, monkeypatch):
     assert rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < 1e-5
     for (name, p), (_, q) in zip(model.named_parameters(), ref_model.named_parameters()):
         assert rel_err(p.grad.cpu().numpy(), q.grad.numpy()) < 2e-5, name
+
+
+def test_reference_semantic_attention_state_dict_and_gradients(lib):
+    """The reference's own SemanticAttention (HAN/models/SemanticAttention.py:5-20) on the CPU against the fused
+    drop-in on the GPU: identical state_dict keys (strict load), forward and every gradient."""
+    mods = ref_loader.han()
+    n, m, d = 300, 3, 64
+    torch.manual_seed(2)
+    ref = mods["SemanticAttention"].SemanticAttention(in_size=d)
+    z = torch.randn(n, m, d)
+    gy = torch.randn(n, d)
+    zr = z.clone().requires_grad_(True)
+    want = ref(zr)
+    want.backward(gy)
+    ours = layers.SemanticAttention(in_size=d)
+    ours.load_state_dict(copy.deepcopy(ref.state_dict()), strict=True)
+    ours = ours.to(DEV)
+    zg = z.to(DEV).requires_grad_(True)
+    got = ours(zg)
+    got.backward(gy.to(DEV))
+    assert got.shape == want.shape and rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < 1e-5
+    assert rel_err(zg.grad.cpu().numpy(), zr.grad.numpy()) < 2e-5
+    for (name, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad.cpu().numpy(), q.grad.numpy()) < 1e-4, name  # fp32 reference on the other side
