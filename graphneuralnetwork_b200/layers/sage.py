@@ -212,6 +212,32 @@ class GraphSage(nn.Module):
             self._fp16_ok = hit = (key, bool((table.abs().max() < 3.0e4).item()))
         return hit[1]
 
+    def _weight_planes(self, ld, device):
+        """fp16 hi / lo planes of `[W_self ; W_agg]` (rows padded to ld each), recomputed only when a weight changed
+        (`_version` / storage of the two parameters): an inference loop — and a captured graph, whose runner calls
+        this before every replay — pays the five small launches of the split once, not per minibatch."""
+        layer0 = self.gcn[0]
+        w, wa = layer0.weight, layer0.aggregator.weight
+        F_in, H = layer0.input_dim, layer0.hidden_dim
+        geom = (int(ld), torch.device(device))
+        ver = (w._version, wa._version, w.data_ptr(), wa.data_ptr())
+        planes = getattr(self, "_l0_planes", None)
+        if planes is None or planes["geom"] != geom:
+            planes = self._l0_planes = {
+                "geom": geom, "ver": None,
+                "Wc": torch.zeros((2 * ld, H), dtype=torch.float32, device=device),
+                "hi": torch.zeros((2 * ld, H), dtype=torch.float16, device=device),
+                "lo": torch.zeros((2 * ld, H), dtype=torch.float16, device=device)}
+        if planes["ver"] != ver:
+            Wc, W_hi, W_lo = planes["Wc"], planes["hi"], planes["lo"]
+            with torch.no_grad():
+                Wc[:F_in].copy_(w)
+                Wc[ld:ld + F_in].copy_(wa)
+                W_hi.copy_(Wc)
+                W_lo.copy_(Wc - W_hi.float())
+            planes["ver"] = ver
+        return planes["hi"], planes["lo"]
+
     def _layer0_split_gemm(self, table, node_id_blocks, ld, n_hop, total):
         """Layer 0 with the fp32 `[self ‖ pooled]·[W_self ; W_agg]` product (K = 2·F, the largest single cost of the
         minibatch after the gather: 26,624 x 1,208 x 128 on the Reddit-shaped config runs 0.17 ms on the fp32 SIMT
@@ -229,13 +255,9 @@ class GraphSage(nn.Module):
         if buf is None or buf[0] != key:
             # row = [hi: self | pooled][lo: self | pooled]; pad columns stay zero for the buffer's lifetime
             Zs = torch.zeros((total, 4 * ld), dtype=torch.float16, device=table.device)
-            Wc = torch.zeros((2 * ld, H), dtype=torch.float32, device=table.device)
-            self._l0_split = buf = (key, Zs, Wc)
-        _, Zs, Wc = buf
-        Wc[:F_in].copy_(layer0.weight)
-        Wc[ld:ld + F_in].copy_(layer0.aggregator.weight)
-        W_hi = Wc.to(torch.float16)
-        W_lo = (Wc - W_hi.float()).to(torch.float16)
+            self._l0_split = buf = (key, Zs)
+        _, Zs = buf
+        W_hi, W_lo = self._weight_planes(ld, table.device)
         blocks, outs, row = [], [], 0
         for hop in range(L):
             n = n_hop[hop]
@@ -250,8 +272,16 @@ class GraphSage(nn.Module):
         # (the fp32 SIMT product: 0.4-1.7e-6; tools/diag_split_gemm.py)
         Z_hi, Z_lo = Zs[:, :2 * ld], Zs[:, 2 * ld:]
         hidden = torch.mm(Z_hi, W_hi, out_dtype=torch.float32)
-        hidden += torch.mm(Z_lo, W_hi, out_dtype=torch.float32)
-        hidden += torch.mm(Z_hi, W_lo, out_dtype=torch.float32)
+        if getattr(self, "_addmm_out_dtype", True):
+            try:  # the two fp32 adds ride in the GEMM epilogues (beta = 1) instead of two elementwise launches
+                hidden = torch.addmm(hidden, Z_lo, W_hi, out_dtype=torch.float32)
+                hidden = torch.addmm(hidden, Z_hi, W_lo, out_dtype=torch.float32)
+            except (RuntimeError, NotImplementedError):  # settled in the warm-up call, before any graph capture
+                self._addmm_out_dtype = False
+                hidden = torch.mm(Z_hi, W_hi, out_dtype=torch.float32)
+        if not getattr(self, "_addmm_out_dtype", True):
+            hidden += torch.mm(Z_lo, W_hi, out_dtype=torch.float32)
+            hidden += torch.mm(Z_hi, W_lo, out_dtype=torch.float32)
         if layer0.activation:
             hidden = layer0.activation(hidden)
         out, row = [], 0
@@ -366,6 +396,7 @@ class CapturedGraphSage:
             for dst, src in zip(self.ids[:self._n_in], slot["stage"]):
                 dst.copy_(src)                               # device copy into the graph's static inputs
             slot["ev_free"].record(self.stream)
+            self._refresh_model_state()                      # weight planes the graph reads, if a weight changed
             self.graph.replay()
             slot["out"].copy_(self.logits)
             slot["ev_done"].record(self.stream)
@@ -375,6 +406,13 @@ class CapturedGraphSage:
             slot["ev_out"].record(self._d2h)
         self._submitted += 1
         return self._submitted - 1
+
+    def _refresh_model_state(self):
+        """Out-of-graph state the captured forward reads: the fp16 weight planes of the layer-0 product follow the
+        parameters' versions (an optimiser step or load_state_dict between replays is picked up here)."""
+        planes = getattr(self.model, "_l0_planes", None)
+        if planes is not None:
+            self.model._weight_planes(*planes["geom"])
 
     def collect(self) -> torch.Tensor:
         """Logits of the oldest minibatch in flight (pinned host tensor, valid until two more submits)."""

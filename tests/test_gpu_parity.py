@@ -515,6 +515,12 @@ def test_captured_graphsage_runner(lib):
     out = runner([b.cpu().pin_memory() for b in blocks]).clone()
     with torch.no_grad():
         assert torch.equal(out, model.forward_sampled(table, blocks).cpu())
+    # a weight update between replays reaches the captured graph (its fp16 weight planes are refreshed out of graph)
+    with torch.no_grad():
+        model.gcn[0].weight.mul_(1.25)
+    out2 = runner([b.cpu().pin_memory() for b in blocks]).clone()
+    with torch.no_grad():
+        assert torch.equal(out2, model.forward_sampled(table, blocks).cpu()) and not torch.equal(out2, out)
     # two minibatches in flight (submit / collect): same logits as one at a time, in submission order
     batches = [torch.arange(s, s + 32, dtype=torch.int32) for s in (0, 50, 200, 333, 568)]
     host = [[b.cpu().pin_memory() for b in Fn.multihop_sampling(csr, bt.to(DEV), [5, 3], seed=20 + k)]
@@ -562,7 +568,7 @@ def test_forward_sampled_one_launch_one_gemm_matches_reference_call_surface(lib)
     assert launches == 2  # layer-0 gather (4 blocks) + the layer-1 mean
     assert rel_err(fast.cpu().numpy(), ref.cpu().numpy()) < TOL32  # fp16x3 tensor-core product: fp32-level accuracy
     assert torch.allclose(fast, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
-    _, Zs, Wc = model._l0_split
+    _, Zs = model._l0_split
     ld = 604
     hi, lo = Zs[:, :2 * ld].float(), Zs[:, 2 * ld:].float()
     assert float(hi[:, 602:604].abs().max()) == 0.0 and float(lo[:, 1206:].abs().max()) == 0.0  # pads stay zero
@@ -580,7 +586,15 @@ def test_forward_sampled_one_launch_one_gemm_matches_reference_call_surface(lib)
     _, Z, _ = model._l0_buf
     assert float(Z[:, 602:604].abs().max()) == 0.0 and float(Z[:, 1206:].abs().max()) == 0.0
     assert torch.equal(Z[:B, :602], rows0)  # fanout-1 block = the rows themselves, bit for bit
+    # the fp16 weight planes follow the parameters: an in-place update between two inference calls is picked up
+    with torch.no_grad():
+        model.gcn[0].weight.mul_(1.5)
+        model.gcn[0].aggregator.weight.add_(0.01)
+        fast2 = model.forward_sampled(table, blocks)
+        ref2 = model([table[b.long()].contiguous() for b in blocks])
+    assert rel_err(fast2.cpu().numpy(), ref2.cpu().numpy()) < TOL32 and not torch.allclose(fast2, fast)
     # training still takes the autograd path and agrees
+    ref = ref2
     model.train()
     out = model.forward_sampled(table, blocks)
     out.sum().backward()
