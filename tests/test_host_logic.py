@@ -141,3 +141,27 @@ def test_padded_views():
     out = Fn._padded_empty(5, 602, torch.bfloat16, "cpu")
     assert out.stride(0) == 608
     assert Fn._ld(out) == 608 and Fn._ld(out[:1]) == 602
+
+
+def test_sage_weight_planes_follow_parameter_versions():
+    """GraphSage._weight_planes (host logic, device-agnostic): the fp16 hi/lo planes of [W_self ; W_agg] are rebuilt
+    only when a parameter's version or storage changes, in place (a captured graph keeps reading the same buffers),
+    and hi + lo reproduces the fp32 weights to 2^-21."""
+    torch.manual_seed(0)
+    model = layers.GraphSage(10, [6, 3], [4, 2])
+    ld = 12
+    hi, lo = model._weight_planes(ld, "cpu")
+    l0 = model.gcn[0]
+    Wc = torch.zeros(2 * ld, 6)
+    Wc[:10], Wc[ld:ld + 10] = l0.weight.detach(), l0.aggregator.weight.detach()
+    assert hi.dtype == lo.dtype == torch.float16 and tuple(hi.shape) == (2 * ld, 6)
+    assert float((hi.float() + lo.float() - Wc).abs().max()) <= 2.0 ** -21 * float(Wc.abs().max())
+    assert float(hi[10:12].abs().max()) == 0.0 and float(hi[22:].abs().max()) == 0.0  # pad rows meet zero weights
+    ver = model._l0_planes["ver"]
+    hi2, lo2 = model._weight_planes(ld, "cpu")
+    assert hi2 is hi and lo2 is lo and model._l0_planes["ver"] == ver  # unchanged weights: nothing recomputed
+    with torch.no_grad():
+        l0.weight.mul_(2.0)
+    hi3, lo3 = model._weight_planes(ld, "cpu")
+    assert hi3 is hi and model._l0_planes["ver"] != ver               # same buffers, new contents
+    assert torch.allclose(hi3[:10].float() + lo3[:10].float(), l0.weight.detach(), rtol=0, atol=1e-6)

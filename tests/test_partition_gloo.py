@@ -23,8 +23,16 @@ def _free_port():
     return p
 
 
-def _global_graph(n, seed):
+def _global_graph(n, seed, kind="skewed"):
     rng = np.random.default_rng(seed)
+    if kind == "cross":
+        # every row reads two rows of the opposite half, every halo row is needed exactly once or twice: as many
+        # halo rows as edges, the exchange-bound corner (F = 128: the width the schedule model is calibrated on)
+        rowptr = (2 * np.arange(n + 1)).astype(np.int64)
+        i = np.repeat(np.arange(n), 2)
+        col = ((i + n // 2 + 7 * (np.arange(2 * n) % 2)) % n).astype(np.int64)
+        val = rng.standard_normal(2 * n).astype(np.float32)
+        return rowptr, col, val, rng.standard_normal((n, 128)).astype(np.float32)
     deg = rng.poisson(6, size=n)
     deg[::11] = 0
     deg[5] = 300  # a hub row
@@ -36,12 +44,12 @@ def _global_graph(n, seed):
     return rowptr, col, val, X
 
 
-def _worker(rank, world, port, n, seed, waves, c0, out_q):
+def _worker(rank, world, port, n, seed, waves, c0, out_q, kind="skewed"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        rowptr, col, val, X = _global_graph(n, seed)
+        rowptr, col, val, X = _global_graph(n, seed, kind)
         bounds = balanced_bounds(torch.from_numpy(rowptr), world)
         lo, hi = bounds[rank], bounds[rank + 1]
         rp = torch.from_numpy(rowptr[lo:hi + 1] - rowptr[lo])
@@ -134,7 +142,8 @@ def _worker(rank, world, port, n, seed, waves, c0, out_q):
         dX = A_loc.T @ dY[lo:hi]
         np.add.at(dX, plan.send_rows.numpy(), back.numpy())
         err_b = float(np.abs(dX - (A.T @ dY)[lo:hi]).max())
-        out_q.put((rank, max(err, err_b), len(h), bounds, plan.two_pass_chunks, plan.waves))
+        out_q.put((rank, max(err, err_b), len(h), bounds, plan.two_pass_chunks, plan.waves,
+                   bool(plan.model.get("exchange_bound", False))))
     finally:
         dist.destroy_process_group()
 
@@ -152,12 +161,30 @@ def test_halo_plan_reproduces_global_spmm(world, waves, c0):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err, n_halo, bounds, chosen, k_used in results:
+    for rank, err, n_halo, bounds, chosen, k_used, _ in results:
         assert err < 1e-9, (rank, err)
         assert n_halo > 0 and bounds[0] == 0 and bounds[-1] == 400
         assert 0 <= chosen <= k_used and (c0 is None or chosen == c0)
     if waves is None:  # the automatic schedule is a consensus: every rank runs the same (K, c0)
         assert len({(r[5], r[4]) for r in results}) == 1
+
+
+def test_exchange_bound_graph_runs_single_pass():
+    """As many halo rows as edges (modelled exchange >= 2.5x the SpMM): the automatic schedule keeps every chunk
+    single-pass (c0 = 0) on every rank, and the replayed exchange still reproduces the global product."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 400, 7, None, None, q, "cross")) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, n_halo, bounds, chosen, k_used, exchange_bound in results:
+        assert err < 1e-9 and n_halo > 150
+        assert exchange_bound and chosen == 0, (rank, chosen, k_used, exchange_bound)
 
 
 def test_select_rows_compacts_csr():
