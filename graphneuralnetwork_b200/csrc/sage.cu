@@ -331,11 +331,15 @@ __global__ void __launch_bounds__(kSageThreads) sage_tma_kernel(const SageArgs<T
 
 template <typename T, int NV, int OP, bool PK>
 int launch_tma_pk(const SageArgs<T>& a, size_t smem_bytes, int grid, cudaStream_t st) {
-  static size_t configured = 0;  // benign race: attribute set is idempotent
-  if (smem_bytes > configured) {
+  // function attributes belong to a device's context: remember the largest size set PER DEVICE (a process driving
+  // several GPUs must not skip the call on the second one); benign race: setting the attribute is idempotent
+  static size_t configured[64] = {};
+  int dev = 0;
+  const bool cached = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64;
+  if (!cached || smem_bytes > configured[dev]) {
     GNN_CUDA(cudaFuncSetAttribute(sage_tma_kernel<T, NV, OP, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_bytes));
-    configured = smem_bytes;
+    if (cached) configured[dev] = smem_bytes;
   }
   sage_tma_kernel<T, NV, OP, PK><<<grid, kSageThreads, smem_bytes, st>>>(a);
   GNN_LAUNCH_CHECK();
