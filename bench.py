@@ -351,7 +351,10 @@ def run_sage_b200(args, rank, world, dev):
                                          "in L2 from the previous minibatch, so the no-reuse byte model overcounts "
                                          "DRAM traffic there and no HBM fraction is claimed for it"},
                      "traffic": measured_traffic("sage_multi")[0],
-                     "traffic_source": measured_traffic("sage_multi")[1]},
+                     "traffic_source": measured_traffic("sage_multi")[1],
+                     # the same launch on the DRAM bytes ncu counted (L2 de-duplicates repeated rows of a minibatch)
+                     "frac_on_traffic": (measured_traffic("sage_multi")[0] / (k2_ms * 1e-3) / 1e9 / peak
+                                         if measured_traffic("sage_multi")[0] else None)},
         "e2e": {"value": world * args.steps * SAGE_EDGES / (e2e_ms * 1e-3), "unit": "edges/s",
                 "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "graphneuralnetwork_b200.layers.CapturedGraphSage(GraphSage.forward_sampled).submit/collect: "
